@@ -1,0 +1,180 @@
+"""Generate tests/golden/*.npz by running the REFERENCE ITSELF (its own Encoder/Decoder/
+GreedySearch/tokenizer modules from /root/reference, third-party classes restated in
+oracle/ref_shims) on seeded synthetic checkpoints and seeded inputs.
+
+Run in the build container only (needs /root/reference):
+    python -m oracle.make_golden
+The fixtures are small, committed, and are what pins oracle/restate.py and the CUDA path
+on the GPU box, where the reference does not exist.  Inputs/weights are never stored: both
+sides regenerate them from seeds (molnextr_b200/synth.py, torch CPU generator).
+"""
+from __future__ import annotations
+
+import json
+import os
+import random
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from molnextr_b200 import synth  # noqa: E402
+from oracle import ref_loader  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+LOGPROB_STEPS = (0, 1, 2, 3, 7, 20, 60, 140)
+
+
+def seeded_images(seed: int, b: int, h: int, w: int) -> torch.Tensor:
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.randn((b, 3, h, w), generator=g, dtype=torch.float32)
+
+
+def seeded_features(seed: int, b: int, s: int, c: int = 1024) -> torch.Tensor:
+    """Synthetic encoder maps: per-token noise plus a per-image common component (rows then
+    finish at different steps, which exercises compaction and the row-rank PE rule)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    tok = torch.randn((b, s, c), generator=g, dtype=torch.float32)
+    img = torch.randn((b, 1, c), generator=g, dtype=torch.float32)
+    return 0.4 * tok + 0.9 * img
+
+
+def _pack_predictions(preds, raw_ids, raw_logp, raw_hidden, max_len):
+    B = len(preds)
+    ids = np.zeros((B, max_len), np.int32)
+    logp = np.zeros((B, max_len), np.float64)
+    lens = np.zeros((B,), np.int32)
+    kmax = max([len(p["edges"]) for p in preds] + [1])
+    edges = np.full((B, kmax, kmax), -1, np.int8)
+    natoms = np.zeros((B,), np.int32)
+    atom_idx = np.full((B, kmax), -1, np.int32)
+    hidden_sub = np.zeros((B, max_len, 16), np.float32)
+    hidden_sum = np.zeros((B, max_len), np.float32)
+    for i, p in enumerate(preds):
+        L = len(raw_ids[i])
+        lens[i] = L
+        ids[i, :L] = raw_ids[i]
+        logp[i, :L] = raw_logp[i]
+        h = raw_hidden[i]
+        hidden_sub[i, :L] = h[:, ::16]
+        hidden_sum[i, :L] = h.sum(1)
+        k = len(p["edges"])
+        natoms[i] = k
+        if k:
+            edges[i, :k, :k] = np.asarray(p["edges"], np.int8)
+            atom_idx[i, :k] = p["chartok_coords"]["indices"]
+    meta = [dict(smiles=p["chartok_coords"]["smiles"], symbols=p["chartok_coords"]["symbols"],
+                 coords=p["chartok_coords"]["coords"], indices=p["chartok_coords"]["indices"]) for p in preds]
+    return dict(ids=ids, token_scores=logp, lens=lens, edges=edges, natoms=natoms, atom_idx=atom_idx,
+                hidden_sub=hidden_sub, hidden_sum=hidden_sum, meta=np.array(json.dumps(meta)))
+
+
+def _run_reference_decode(dec, features):
+    """decoder.decode through the reference, recording what GreedySearch.advance was fed."""
+    import MolNexTR.components as comp
+    rec = {"lp": []}
+    orig_advance = comp.GreedySearch.advance
+
+    def advance(self, log_probs, attn=None, hidden=None, label=None):
+        orig_advance(self, log_probs, attn, hidden, label)   # ensure_min_length edits in place first
+        rec["lp"].append(log_probs.detach().clone())
+
+    comp.GreedySearch.advance = advance
+    try:
+        with torch.no_grad():
+            ar = dec.decoder["chartok_coords"]
+            from MolNexTR.utils import FORMAT_INFO
+            max_len = FORMAT_INFO["chartok_coords"]["max_len"]
+            outputs, scores, token_scores, hiddens = ar.decode(features, 1, 1, max_length=max_len)
+            preds = dec.decode(features, None)
+    finally:
+        comp.GreedySearch.advance = orig_advance
+    # the second call re-ran the same deterministic decode; keep the first call's log-probs
+    nsteps = len(rec["lp"]) // 2
+    lps = rec["lp"][:nsteps]
+    raw_ids = [o[0].numpy() for o in outputs]
+    raw_logp = [np.asarray(t[0], np.float64) for t in token_scores]   # exp(log-prob), as the reference reports it
+    raw_hidden = [h[0].numpy() for h in hiddens]
+    return preds, raw_ids, raw_logp, raw_hidden, lps, scores
+
+
+def make_swin_e2e(name, seed, b, h, w):
+    ck = synth.synthetic_checkpoint(seed, "sensitised")
+    enc, dec, tok = ref_loader.build_reference(ck)
+    x = seeded_images(1000 + seed, b, h, w)
+    with torch.no_grad():
+        feats, hiddens = enc(x)
+    preds, raw_ids, raw_logp, raw_hidden, lps, scores = _run_reference_decode(dec, feats)
+    out = _pack_predictions(preds, raw_ids, raw_logp, raw_hidden, 480)
+    f = feats.numpy()
+    out.update(feat_sub=f[:, ::4, ::32].copy(), feat_sum=f.sum((1, 2)), feat_abs=np.abs(f).sum((1, 2)),
+               stage_mean=np.array([float(hd.mean()) for hd in hiddens], np.float32),
+               stage_std=np.array([float(hd.std()) for hd in hiddens], np.float32),
+               seq_score=np.array([s[0] for s in scores], np.float32),
+               cfg=np.array(json.dumps(dict(ckpt_seed=seed, variant="sensitised", img_seed=1000 + seed, b=b, h=h, w=w))))
+    for st in LOGPROB_STEPS:
+        if st < len(lps):
+            out[f"logprobs_step{st}"] = lps[st].numpy()
+    np.savez_compressed(os.path.join(GOLDEN, name), **out)
+    print(name, "lens", out["lens"].tolist(), "atoms", out["natoms"].tolist())
+
+
+def make_decoder_only(name, seed, b, s):
+    ck = synth.synthetic_checkpoint(seed, "sensitised")
+    _, dec, tok = ref_loader.build_reference(ck)
+    feats = seeded_features(2000 + seed, b, s)
+    preds, raw_ids, raw_logp, raw_hidden, lps, scores = _run_reference_decode(dec, feats)
+    out = _pack_predictions(preds, raw_ids, raw_logp, raw_hidden, 480)
+    out.update(seq_score=np.array([sc[0] for sc in scores], np.float32),
+               cfg=np.array(json.dumps(dict(ckpt_seed=seed, variant="sensitised", feat_seed=2000 + seed, b=b, s=s))))
+    for st in LOGPROB_STEPS:
+        if st < len(lps):
+            out[f"logprobs_step{st}"] = lps[st].numpy()
+    np.savez_compressed(os.path.join(GOLDEN, name), **out)
+    print(name, "lens", out["lens"].tolist(), "atoms", out["natoms"].tolist())
+
+
+def make_tokenizer_and_edges(name):
+    ck = synth.synthetic_checkpoint(0, "sensitised")
+    _, dec, tok = ref_loader.build_reference(ck)
+    import MolNexTR.components as comp
+    rt = tok["chartok_coords"]
+    rnd = random.Random(7)
+    seqs, outs = [], []
+    for _ in range(400):
+        L = rnd.randint(0, 70)
+        seq = [rnd.choice([rnd.randint(0, 228), rnd.randint(5, 100), rnd.randint(101, 164), rnd.randint(165, 228),
+                           57, 14, 15, 40, 56, 46, 68, 69]) for _ in range(L)]
+        seqs.append(seq)
+        outs.append(rt.sequence_to_smiles(seq))
+    masks = np.array([rt.get_output_mask(i) for i in range(len(rt))], bool)
+    g = np.random.default_rng(11)
+    edge_cases = []
+    for n in (0, 1, 2, 5, 17):
+        p = g.random((n, n, 7)).astype(np.float32)
+        p = p / p.sum(2, keepdims=True) if n else p
+        pred, score = comp.get_edge_prediction(p.astype(np.float64).tolist())
+        edge_cases.append(dict(prob=p.tolist(), pred=pred, score=score))
+    np.savez_compressed(os.path.join(GOLDEN, name), masks=masks, vocab_len=len(rt), offset=rt.offset,
+                        tok=np.array(json.dumps(dict(seqs=seqs, outs=outs))),
+                        edges=np.array(json.dumps(edge_cases)))
+    print(name, "ok")
+
+
+def main():
+    assert ref_loader.available(), "needs /root/reference (build container)"
+    os.makedirs(GOLDEN, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    make_tokenizer_and_edges("tokenizer_edges.npz")
+    make_decoder_only("decoder_b6_s144.npz", seed=0, b=6, s=144)
+    make_decoder_only("decoder_b3_s64.npz", seed=1, b=3, s=64)
+    make_swin_e2e("swin_b4_384.npz", seed=0, b=4, h=384, w=384)
+    make_swin_e2e("swin_b1_408x424.npz", seed=2, b=1, h=408, w=424)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,436 @@
+"""CPU oracle: a plain torch-fp32 restatement of the reference hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under `molnextr_b200/` may import this module; only
+`tests/`, `__graft_entry__.smoke()` and bench.py's CPU-baseline / `--impl reference` legs do.
+It restates, function by function, what the reference computes between
+`features, hiddens = self.encoder(images)` and the prediction list returned by
+`self.decoder.decode(features, hiddens)` (MolNexTR/model.py:106-108), reading weights straight
+from a checkpoint in the reference's own `.pth` schema.
+
+Pinning status (see oracle/README.md and tests/test_oracle_vs_reference.py):
+  * Swin-B encoder, decoder step, greedy state machine, bond head, tokenizer: PINNED against
+    the reference's own modules imported in the build container (third-party onmt/timm classes
+    restated under oracle/ref_shims) and against the fixtures that run wrote to tests/golden/.
+  * ConvNeXt-B encoder: "parity unpinned" -- the reference's ConvNeXt branch cannot execute in
+    any environment; this file restates timm's published ConvNeXt-B
+    `forward_features` and nothing in the reference can confirm it.
+  * Beam search: "parity unpinned" -- unrunnable in the reference.
+
+Every function cites the reference lines it follows (paths relative to /root/reference).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+PAD_ID, SOS_ID, EOS_ID, UNK_ID, MASK_ID = 0, 1, 2, 3, 4
+SWIN_DEPTHS = (2, 2, 18, 2)
+SWIN_HEADS = (4, 8, 16, 32)
+WINDOW = 12
+CONVNEXT_DEPTHS = (3, 3, 27, 3)
+DEC_LAYERS = 6
+DEC_HEADS = 8
+DEC_DIM = 256
+
+SD = Dict[str, torch.Tensor]
+
+
+def _strip(sd: SD) -> SD:
+    """`module.` prefixes from DDP are dropped on load (MolNexTR/model.py:25-26)."""
+    return {k.replace("module.", ""): v for k, v in sd.items()}
+
+
+# --------------------------------------------------------------------------------------
+# Swin-B encoder  (MolNexTR/models/transformers.py)
+# --------------------------------------------------------------------------------------
+def _window_partition(x: torch.Tensor, ws: int) -> torch.Tensor:
+    # transformers.py:68-80
+    B, H, W, C = x.shape
+    x = x.view(B, H // ws, ws, W // ws, ws, C)
+    return x.permute(0, 1, 3, 2, 4, 5).contiguous().view(-1, ws, ws, C)
+
+
+def _window_reverse(win: torch.Tensor, ws: int, H: int, W: int) -> torch.Tensor:
+    # transformers.py:83-97
+    B = win.shape[0] // ((H // ws) * (W // ws))
+    x = win.view(B, H // ws, W // ws, ws, ws, -1)
+    return x.permute(0, 1, 3, 2, 4, 5).contiguous().view(B, H, W, -1)
+
+
+def swin_shift_mask(Hp: int, Wp: int, ws: int, shift: int) -> Optional[torch.Tensor]:
+    """(nW, ws*ws, ws*ws) additive mask, 0 / -100  (transformers.py:220-243)."""
+    if shift == 0:
+        return None
+    img = torch.zeros((1, Hp, Wp, 1))
+    cnt = 0
+    for h in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
+        for w in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
+            img[:, h, w, :] = cnt
+            cnt += 1
+    mw = _window_partition(img, ws).view(-1, ws * ws)
+    m = mw.unsqueeze(1) - mw.unsqueeze(2)
+    return m.masked_fill(m != 0, -100.0).masked_fill(m == 0, 0.0)
+
+
+def _swin_block(sd: SD, p: str, x: torch.Tensor, H: int, W: int, heads: int, shift: int) -> torch.Tensor:
+    # SwinTransformerBlock.forward, transformers.py:245-292
+    B, L, C = x.shape
+    ws = WINDOW
+    shortcut = x
+    x = F.layer_norm(x, (C,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], 1e-5).view(B, H, W, C)
+    pad_r = (ws - W % ws) % ws
+    pad_b = (ws - H % ws) % ws
+    x = F.pad(x, (0, 0, 0, pad_r, 0, pad_b))
+    Hp, Wp = x.shape[1], x.shape[2]
+    if shift > 0:
+        x = torch.roll(x, shifts=(-shift, -shift), dims=(1, 2))
+    xw = _window_partition(x, ws).view(-1, ws * ws, C)
+    mask = swin_shift_mask(Hp, Wp, ws, shift)
+    # WindowAttention.forward, transformers.py:147-178
+    B_, N, _ = xw.shape
+    hd = C // heads
+    qkv = F.linear(xw, sd[p + "attn.qkv.weight"], sd[p + "attn.qkv.bias"])
+    qkv = qkv.reshape(B_, N, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    q = q * (hd ** -0.5)
+    attn = q @ k.transpose(-2, -1)
+    idx = sd[p + "attn.relative_position_index"].view(-1)
+    bias = sd[p + "attn.relative_position_bias_table"][idx].view(N, N, -1).permute(2, 0, 1).contiguous()
+    attn = attn + bias.unsqueeze(0)
+    if mask is not None:
+        nW = mask.shape[0]
+        attn = attn.view(B_ // nW, nW, heads, N, N) + mask.unsqueeze(1).unsqueeze(0)
+        attn = attn.view(-1, heads, N, N)
+    attn = torch.softmax(attn, dim=-1)
+    xo = (attn @ v).transpose(1, 2).reshape(B_, N, C)
+    xo = F.linear(xo, sd[p + "attn.proj.weight"], sd[p + "attn.proj.bias"])
+    x = _window_reverse(xo.view(-1, ws, ws, C), ws, Hp, Wp)
+    if shift > 0:
+        x = torch.roll(x, shifts=(shift, shift), dims=(1, 2))
+    if pad_r > 0 or pad_b > 0:
+        x = x[:, :H, :W, :].contiguous()
+    x = shortcut + x.view(B, H * W, C)
+    y = F.layer_norm(x, (C,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], 1e-5)
+    y = F.linear(y, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"])
+    y = F.gelu(y)
+    y = F.linear(y, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])
+    return x + y
+
+
+def _patch_merging(sd: SD, p: str, x: torch.Tensor, H: int, W: int):
+    # PatchMerging.forward, transformers.py:310-336
+    B, L, C = x.shape
+    x = x.view(B, H, W, C)
+    if H % 2 == 1 or W % 2 == 1:
+        x = F.pad(x, (0, 0, 0, W % 2, 0, H % 2))
+    x = torch.cat([x[:, 0::2, 0::2], x[:, 1::2, 0::2], x[:, 0::2, 1::2], x[:, 1::2, 1::2]], -1)
+    H2, W2 = x.shape[1], x.shape[2]
+    x = x.view(B, -1, 4 * C)
+    x = F.layer_norm(x, (4 * C,), sd[p + "norm.weight"], sd[p + "norm.bias"], 1e-5)
+    return F.linear(x, sd[p + "reduction.weight"]), H2, W2
+
+
+def swin_b_features(enc_sd: SD, images: torch.Tensor, return_stage_outputs: bool = False):
+    """Vision_Transformer.forward (transformers.py:504-515) for `swin_base` (:547-551).
+    images: (B,3,H,W) fp32 normalised -> (B, (H/32)*(W/32), 1024)."""
+    sd = _strip(enc_sd)
+    t = "transformer."
+    x = images
+    # PatchEmbed.forward, transformers.py:405-419
+    _, _, H, W = x.shape
+    if W % 4 != 0:
+        x = F.pad(x, (0, 4 - W % 4))
+    if H % 4 != 0:
+        x = F.pad(x, (0, 0, 0, 4 - H % 4))
+    x = F.conv2d(x, sd[t + "patch_embed.proj.weight"], sd[t + "patch_embed.proj.bias"], stride=4)
+    H, W = x.shape[2], x.shape[3]
+    x = x.flatten(2).transpose(1, 2)
+    x = F.layer_norm(x, (128,), sd[t + "patch_embed.norm.weight"], sd[t + "patch_embed.norm.bias"], 1e-5)
+    stage_out = []
+    for s, (depth, heads) in enumerate(zip(SWIN_DEPTHS, SWIN_HEADS)):
+        for j in range(depth):
+            shift = 0 if j % 2 == 0 else WINDOW // 2
+            x = _swin_block(sd, f"{t}layers.{s}.blocks.{j}.", x, H, W, heads, shift)
+        stage_out.append(x)
+        if s < 3:
+            x, H, W = _patch_merging(sd, f"{t}layers.{s}.downsample.", x, H, W)
+    x = F.layer_norm(x, (1024,), sd[t + "norm.weight"], sd[t + "norm.bias"], 1e-5)
+    if return_stage_outputs:
+        return x, stage_out
+    return x
+
+
+# --------------------------------------------------------------------------------------
+# ConvNeXt-B encoder (timm ConvNeXt.forward_features; the reference branch at
+# MolNexTR/components.py:121-126,163-166 is dead code -> PARITY UNPINNED)
+# --------------------------------------------------------------------------------------
+def _ln2d(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float) -> torch.Tensor:
+    return F.layer_norm(x.permute(0, 2, 3, 1), (x.shape[1],), w, b, eps).permute(0, 3, 1, 2)
+
+
+def convnext_b_features(enc_sd: SD, images: torch.Tensor) -> torch.Tensor:
+    """stem -> 4 stages -> NHWC -> (B, HW, 1024), as `features.permute(0,2,3,1)` then the
+    decoder's flatten (components.py:165, :207-209)."""
+    sd = _strip(enc_sd)
+    c = "cnn."
+    x = F.conv2d(images, sd[c + "stem.0.weight"], sd[c + "stem.0.bias"], stride=4)
+    x = _ln2d(x, sd[c + "stem.1.weight"], sd[c + "stem.1.bias"], 1e-6)
+    for s, depth in enumerate(CONVNEXT_DEPTHS):
+        if s > 0:
+            p = f"{c}stages.{s}.downsample."
+            x = _ln2d(x, sd[p + "0.weight"], sd[p + "0.bias"], 1e-6)
+            x = F.conv2d(x, sd[p + "1.weight"], sd[p + "1.bias"], stride=2)
+        for j in range(depth):
+            p = f"{c}stages.{s}.blocks.{j}."
+            C = x.shape[1]
+            y = F.conv2d(x, sd[p + "conv_dw.weight"], sd[p + "conv_dw.bias"], padding=3, groups=C)
+            y = y.permute(0, 2, 3, 1)
+            y = F.layer_norm(y, (C,), sd[p + "norm.weight"], sd[p + "norm.bias"], 1e-6)
+            y = F.linear(y, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"])
+            y = F.gelu(y)
+            y = F.linear(y, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])
+            y = y.permute(0, 3, 1, 2)
+            x = x + y * sd[p + "gamma"].reshape(1, -1, 1, 1)
+    B, C = x.shape[0], x.shape[1]
+    return x.permute(0, 2, 3, 1).reshape(B, -1, C)
+
+
+def encoder_features(enc_sd: SD, images: torch.Tensor) -> torch.Tensor:
+    """Encoder.forward (components.py:162-174): backbone chosen by the state-dict prefix."""
+    key = next(iter(_strip(enc_sd)))
+    if key.startswith("transformer."):
+        return swin_b_features(enc_sd, images)
+    if key.startswith("cnn."):
+        return convnext_b_features(enc_sd, images)
+    raise ValueError(f"unrecognised encoder state-dict (first key {key!r})")
+
+
+# --------------------------------------------------------------------------------------
+# Decoder  (components.py:177-334, models/decoder.py, models/embedding.py, onmt MHA/FFN)
+# --------------------------------------------------------------------------------------
+_P = "decoder.chartok_coords."
+
+
+def memory_bank(dec_sd: SD, features: torch.Tensor) -> torch.Tensor:
+    # TransformerDecoderBase.enc_transform, components.py:206-216 (enc_pos_emb is off)
+    sd = _strip(dec_sd)
+    B, C = features.size(0), features.size(-1)
+    return F.linear(features.view(B, -1, C), sd[_P + "enc_trans_layer.0.weight"], sd[_P + "enc_trans_layer.0.bias"])
+
+
+def _shape(x: torch.Tensor) -> torch.Tensor:
+    return x.view(x.size(0), -1, DEC_HEADS, DEC_DIM // DEC_HEADS).transpose(1, 2)
+
+
+def _unshape(x: torch.Tensor) -> torch.Tensor:
+    return x.transpose(1, 2).contiguous().view(x.size(0), -1, DEC_DIM)
+
+
+def _mha(sd: SD, p: str, key, value, query, cache: dict, kind: str, mask=None):
+    """onmt.modules.MultiHeadedAttention.forward with a layer cache (OpenNMT-py 2.2.0; call
+    sites models/decoder.py:144-151 and :269-276)."""
+    lin = lambda name, x: F.linear(x, sd[f"{p}{name}.weight"], sd[f"{p}{name}.bias"])
+    if kind == "self":
+        q, k, v = lin("linear_query", query), _shape(lin("linear_keys", query)), _shape(lin("linear_values", query))
+        if cache["self_keys"] is not None:
+            k = torch.cat((cache["self_keys"], k), dim=2)
+            v = torch.cat((cache["self_values"], v), dim=2)
+        cache["self_keys"], cache["self_values"] = k, v
+    else:
+        q = lin("linear_query", query)
+        if cache["memory_keys"] is None:
+            cache["memory_keys"] = _shape(lin("linear_keys", key))
+            cache["memory_values"] = _shape(lin("linear_values", value))
+        k, v = cache["memory_keys"], cache["memory_values"]
+    q = _shape(q) / math.sqrt(DEC_DIM // DEC_HEADS)
+    scores = torch.matmul(q, k.transpose(2, 3)).float()
+    if mask is not None:
+        scores = scores.masked_fill(mask.unsqueeze(1), -1e18)
+    attn = torch.softmax(scores, dim=-1)
+    ctx = _unshape(torch.matmul(attn, v))
+    return lin("final_linear", ctx)
+
+
+class DecoderState:
+    """The per-layer cache dict of TransformerDecoder (_init_cache, models/decoder.py:482-486)."""
+
+    def __init__(self):
+        self.layers = [dict(memory_keys=None, memory_values=None, self_keys=None, self_values=None)
+                       for _ in range(DEC_LAYERS)]
+
+    def index_select(self, idx: torch.Tensor):
+        # TransformerDecoderAR.map_state, components.py:337-347
+        for c in self.layers:
+            for k, v in c.items():
+                if v is not None:
+                    c[k] = v.index_select(0, idx)
+
+
+def decoder_step(dec_sd: SD, tokens: torch.Tensor, mem: torch.Tensor, state: DecoderState) -> torch.Tensor:
+    """One autoregressive step for the alive rows.  tokens (R,) int64, mem (R,S,256).
+    Returns dec_out (R,256) = final-LayerNorm output (the `hidden` greedy search stores).
+
+    Embedding: Embeddings.forward / PositionalEncoding.forward (models/embedding.py:236-255,
+    :42-61) are fed a batch-first (R,1,256) tensor and no `step`, so row r receives pe[r]
+     -- reproduced here on purpose.
+    Layers: TransformerDecoderLayer._forward (models/decoder.py:224-279)."""
+    sd = _strip(dec_sd)
+    R = tokens.numel()
+    emb_w = sd[_P + "embeddings.make_embedding.emb_luts.0.weight"]
+    pe = sd[_P + "embeddings.make_embedding.pe.pe"]
+    if pe.size(0) < R:
+        raise RuntimeError(f"Sequence is {R} but PositionalEncoding is limited to {pe.size(0)}")
+    x = emb_w[tokens].view(R, 1, DEC_DIM) * math.sqrt(DEC_DIM) + pe[:R]
+    src_pad_mask = torch.zeros((R, 1, mem.size(1)), dtype=torch.bool)
+    for l in range(DEC_LAYERS):
+        p = f"{_P}decoder.transformer_layers.{l}."
+        cache = state.layers[l]
+        n1 = F.layer_norm(x, (DEC_DIM,), sd[p + "layer_norm_1.weight"], sd[p + "layer_norm_1.bias"], 1e-6)
+        x = _mha(sd, p + "self_attn.", n1, n1, n1, cache, "self") + x
+        n2 = F.layer_norm(x, (DEC_DIM,), sd[p + "layer_norm_2.weight"], sd[p + "layer_norm_2.bias"], 1e-6)
+        x = _mha(sd, p + "context_attn.", mem, mem, n2, cache, "context", mask=src_pad_mask) + x
+        # onmt PositionwiseFeedForward.forward (activation 'gelu', components.py:203)
+        h = F.layer_norm(x, (DEC_DIM,), sd[p + "feed_forward.layer_norm.weight"], sd[p + "feed_forward.layer_norm.bias"], 1e-6)
+        h = F.gelu(F.linear(h, sd[p + "feed_forward.w_1.weight"], sd[p + "feed_forward.w_1.bias"]))
+        x = F.linear(h, sd[p + "feed_forward.w_2.weight"], sd[p + "feed_forward.w_2.bias"]) + x
+    x = F.layer_norm(x, (DEC_DIM,), sd[_P + "decoder.layer_norm.weight"], sd[_P + "decoder.layer_norm.bias"], 1e-6)
+    return x.view(R, DEC_DIM)
+
+
+def grammar_mask(tokens: torch.Tensor, offset: int, maxx: int, maxy: int) -> torch.Tensor:
+    """CharTokenizer.get_output_mask (tokenization.py:383-392) for each INPUT token: True = blocked."""
+    V = offset + maxx + maxy
+    ids = torch.arange(V).unsqueeze(0)
+    t = tokens.view(-1, 1)
+    is_x = (t >= offset) & (t < offset + maxx)
+    is_y = t >= offset + maxx
+    return (is_x & (ids < offset + maxx)) | (is_y & (ids >= offset))
+
+
+def greedy_decode(dec_sd: SD, features: torch.Tensor, max_len: int = 480,
+                  grammar=(101, 64, 64), record_logprobs: bool = False,
+                  forced_ids: Optional[torch.Tensor] = None, min_length: int = 1):
+    """TransformerDecoderAR.decode with GreedySearch (components.py:253-334,
+    decoding/greedy_search.py:33-128, decode_strategy.py:4-62).
+
+    Returns a list (one per image) of dicts: ids int64 (L,) incl. <eos> and excl. <sos>;
+    logp fp32 (L,); hidden fp32 (L,256); score = exp(mean(logp)).  With `record_logprobs`
+    each dict also has `logprobs` (L,V): the masked log-probabilities GreedySearch.advance saw.
+    `forced_ids` (B,T) teacher-forces the chosen token (all rows must then share one length;
+    used only to compare per-step log-probs at tensor level)."""
+    sd = _strip(dec_sd)
+    B = features.size(0)
+    mem = memory_bank(sd, features)
+    state = DecoderState()
+    w_out, b_out = sd[_P + "output_layer.weight"], sd[_P + "output_layer.bias"]
+    alive_seq = torch.full((B, 1), SOS_ID, dtype=torch.long)
+    alive_logp = torch.zeros((B, 0))
+    alive_hidden = None
+    alive_lp_rec = [] if record_logprobs else None
+    orig_idx = torch.arange(B)
+    results: List[Optional[dict]] = [None] * B
+    with torch.no_grad():
+        for step in range(max_len):
+            tgt = alive_seq[:, -1]
+            dec_out = decoder_step(sd, tgt, mem, state)
+            logits = F.linear(dec_out, w_out, b_out)
+            log_probs = F.log_softmax(logits, dim=-1)
+            log_probs.masked_fill_(grammar_mask(tgt, *grammar), -10000)
+            if alive_seq.shape[1] <= min_length:          # ensure_min_length
+                log_probs[:, EOS_ID] = -1e20
+            topk_scores, topk_ids = log_probs.topk(1, dim=-1)
+            if forced_ids is not None:
+                topk_ids = forced_ids[orig_idx, step].view(-1, 1)
+                topk_scores = log_probs.gather(1, topk_ids)
+            is_finished = topk_ids.eq(EOS_ID).view(-1)
+            alive_seq = torch.cat([alive_seq, topk_ids], -1)
+            alive_logp = torch.cat([alive_logp, topk_scores], -1)
+            h = dec_out.unsqueeze(1)
+            alive_hidden = h if alive_hidden is None else torch.cat([alive_hidden, h], 1)
+            if record_logprobs:
+                alive_lp_rec.append(log_probs.clone())
+            if alive_seq.shape[1] == max_len + 1:         # ensure_max_length
+                is_finished = torch.ones_like(is_finished)
+            if is_finished.any():
+                # update_finished, greedy_search.py:100-127
+                for b in is_finished.nonzero().view(-1).tolist():
+                    r = dict(ids=alive_seq[b, 1:].clone(), logp=alive_logp[b].clone(),
+                             hidden=alive_hidden[b].clone(),
+                             score=float(torch.exp(torch.mean(alive_logp[b]))))
+                    if record_logprobs:
+                        r["logprobs"] = torch.stack([lp[b] for lp in alive_lp_rec], 0)
+                    results[int(orig_idx[b])] = r
+                if bool(is_finished.all()):
+                    break
+                alive = ~is_finished
+                alive_seq, alive_logp, alive_hidden = alive_seq[alive], alive_logp[alive], alive_hidden[alive]
+                if record_logprobs:
+                    alive_lp_rec = [lp[alive] for lp in alive_lp_rec]
+                select = alive.nonzero().view(-1)
+                orig_idx = orig_idx[alive]
+                mem = mem.index_select(0, select)
+                state.index_select(select)
+    return results
+
+
+# --------------------------------------------------------------------------------------
+# Bond head  (components.py:350-400, driver :470-491)
+# --------------------------------------------------------------------------------------
+def edge_probabilities(dec_sd: SD, hidden: torch.Tensor, indices: Sequence[int]) -> torch.Tensor:
+    """GraphPredictor.forward on one image + softmax: (k,k,7) fp32 (components.py:365-380, :481)."""
+    sd = _strip(dec_sd)
+    idx = torch.as_tensor(list(indices), dtype=torch.long)
+    h = hidden[idx]
+    k = h.size(0)
+    hh = torch.cat([h.unsqueeze(1).expand(k, k, DEC_DIM), h.unsqueeze(0).expand(k, k, DEC_DIM)], dim=2)
+    y = F.linear(hh, sd["decoder.edges.mlp.0.weight"], sd["decoder.edges.mlp.0.bias"])
+    y = F.linear(F.gelu(y), sd["decoder.edges.mlp.2.weight"], sd["decoder.edges.mlp.2.bias"])
+    return F.softmax(y, dim=2)
+
+
+def get_edge_prediction(prob: np.ndarray):
+    """get_edge_prediction (components.py:383-400) in double precision, as the reference runs
+    it on Python floats obtained from `.tolist()`.  The 5/6 rule reads edge_prob[i][j][5]
+    AFTER it was overwritten, exactly as the reference does."""
+    n = prob.shape[0]
+    if n == 0:
+        return [], []
+    p = prob.astype(np.float64).copy()
+    for i in range(n):
+        for j in range(i + 1, n):
+            for k in range(5):
+                p[i, j, k] = (p[i, j, k] + p[j, i, k]) / 2
+                p[j, i, k] = p[i, j, k]
+            p[i, j, 5] = (p[i, j, 5] + p[j, i, 6]) / 2
+            p[i, j, 6] = (p[i, j, 6] + p[j, i, 5]) / 2
+            p[j, i, 5] = p[i, j, 6]
+            p[j, i, 6] = p[i, j, 5]
+    return np.argmax(p, axis=2).tolist(), np.max(p, axis=2).tolist()
+
+
+def decode(dec_sd: SD, features: torch.Tensor, tokenizer, max_len: int = 480, return_raw: bool = False):
+    """Decoder.decode (components.py:443-492) for formats [chartok_coords, edges],
+    compute_confidence off: list of {'chartok_coords': {...}, 'edges': [[int]]}."""
+    raw = greedy_decode(dec_sd, features, max_len=max_len,
+                        grammar=(tokenizer.offset, tokenizer.maxx, tokenizer.maxy))
+    preds = []
+    for r in raw:
+        ct = tokenizer.sequence_to_smiles(r["ids"].tolist())
+        if len(ct["indices"]) > 0:
+            prob = edge_probabilities(dec_sd, r["hidden"], ct["indices"]).numpy()
+            edges, _ = get_edge_prediction(prob)
+        else:
+            edges = []
+        preds.append({"chartok_coords": ct, "edges": edges})
+    return (preds, raw) if return_raw else preds
+
+
+def predict(ckpt: dict, images: torch.Tensor, tokenizer, max_len: int = 480):
+    """encoder + decoder.decode as called from molnextr.predict_images (model.py:105-108)."""
+    with torch.no_grad():
+        feats = encoder_features(ckpt["encoder"], images)
+        return decode(ckpt["decoder"], feats, tokenizer, max_len=max_len)

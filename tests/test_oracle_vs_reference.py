@@ -1,0 +1,34 @@
+"""Build-container only: oracle/restate.py against the reference's OWN modules imported from
+/root/reference (skipped where the reference is absent, e.g. on the GPU box)."""
+import pytest
+import torch
+
+from molnextr_b200 import synth
+from molnextr_b200.tokenization import CharTokenizer
+from oracle import ref_loader, restate
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present")
+
+
+def test_reference_state_dict_schema_matches_synthetic():
+    ck = synth.synthetic_checkpoint(3, "sensitised")
+    enc, dec, tok = ref_loader.build_reference(ck)      # strict=True load
+    assert set(enc.state_dict()) == set(ck["encoder"]) and set(dec.state_dict()) == set(ck["decoder"])
+    pe = dec.state_dict()["decoder.chartok_coords.embeddings.make_embedding.pe.pe"]
+    assert torch.equal(pe, synth.positional_encoding_table())
+    idx = enc.state_dict()["transformer.layers.0.blocks.0.attn.relative_position_index"]
+    assert torch.equal(idx, synth.relative_position_index(12))
+
+
+def test_oracle_equals_reference_swin_decode():
+    ck = synth.synthetic_checkpoint(5, "sensitised")
+    enc, dec, tok = ref_loader.build_reference(ck)
+    g = torch.Generator().manual_seed(123)
+    x = torch.randn((2, 3, 384, 384), generator=g)
+    with torch.no_grad():
+        f_ref, _ = enc(x)
+        f_or = restate.swin_b_features(ck["encoder"], x)
+        assert torch.allclose(f_ref, f_or, rtol=0, atol=1e-5)
+        p_ref = dec.decode(f_ref, None)
+    p_or = restate.decode(ck["decoder"], f_or, CharTokenizer(64))
+    assert p_ref == p_or
