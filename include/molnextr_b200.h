@@ -1,0 +1,145 @@
+/*
+ * molnextr_b200 -- C ABI of the B200-native MolNexTR inference engine.
+ *
+ * One engine handle per GPU.  The handle owns the repacked weights and every workspace
+ * (KV caches, memory K/V, activations, CUDA graphs); the caller owns all input / output
+ * buffers and passes plain device pointers plus the CUDA stream to run on.  No torch types
+ * cross this boundary.  One call in flight per handle (the reference decoder is not
+ * re-entrant either: its KV cache is a module attribute, MolNexTR/models/decoder.py:287).
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the
+ * reference repository root):
+ *
+ *   mnx_create / mnx_load_tensor / mnx_finalize_weights
+ *        <- molnextr.__init__/_get_model + loading()          MolNexTR/model.py:40-48,83-95,17-28
+ *           (state-dict keys are the reference's own; unlike `strict=False` there, a
+ *            missing or unexpected key is an error here)
+ *   mnx_encode            <- Encoder.forward                  MolNexTR/components.py:162-174
+ *                            (Swin-B: MolNexTR/models/transformers.py:504-515;
+ *                             ConvNeXt-B: timm forward_features, components.py:121-126)
+ *   mnx_decode_greedy     <- TransformerDecoderAR.decode + GreedySearch
+ *                            MolNexTR/components.py:253-334, MolNexTR/decoding/greedy_search.py:33-128
+ *   mnx_atom_indices      <- CharTokenizer.sequence_to_smiles (the `indices` output only)
+ *                            MolNexTR/tokenization.py:464-515
+ *   mnx_edges             <- GraphPredictor.forward + get_edge_prediction
+ *                            MolNexTR/components.py:365-400, driver :470-484
+ *   mnx_predict           <- `features, hiddens = self.encoder(images)` followed by
+ *                            `self.decoder.decode(features, hiddens)`  MolNexTR/model.py:106-108
+ *
+ * All functions return MNX_OK (0) or a negative status; mnx_last_error() gives the message.
+ * There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef MOLNEXTR_B200_H
+#define MOLNEXTR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MNX_OK 0
+#define MNX_ERR_INVALID (-1)   /* bad argument / shape / state            */
+#define MNX_ERR_CUDA (-2)      /* a CUDA runtime or driver call failed    */
+#define MNX_ERR_WEIGHTS (-3)   /* missing / unexpected / mis-shaped tensor */
+#define MNX_ERR_CAPACITY (-4)  /* request exceeds the sizes given at create */
+
+#define MNX_ENCODER_NONE 0      /* decoder-only handle: mnx_encode unavailable */
+#define MNX_ENCODER_SWIN_B 1    /* state-dict prefix `transformer.`            */
+#define MNX_ENCODER_CONVNEXT_B 2 /* state-dict prefix `cnn.`                   */
+
+#define MNX_DEC_DIM 256
+#define MNX_EDGE_CLASSES 7
+
+typedef struct mnx_engine mnx_engine;
+
+typedef struct mnx_config {
+    int32_t device;        /* CUDA device ordinal                                          */
+    int32_t encoder_kind;  /* MNX_ENCODER_*                                                */
+    int32_t max_batch;     /* images (= decoder rows) per call                             */
+    int32_t max_height;    /* input image height bound (pixels)                            */
+    int32_t max_width;     /* input image width bound                                      */
+    int32_t max_len;       /* decode cap, 480 for chartok_coords (MolNexTR/utils.py:25)    */
+    int32_t vocab;         /* 229 = 101 symbols + 64 x-bins + 64 y-bins                    */
+    int32_t tok_offset;    /* first x-bin id (101)                                         */
+    int32_t max_x;         /* number of x bins (64)                                        */
+    int32_t max_y;         /* number of y bins (64)                                        */
+    int32_t max_atoms;     /* bond-head capacity per image (<= max_len/3 = 160)            */
+    int32_t encoder_dim;   /* 1024                                                         */
+    /* per-id class bits for the device-side atom scan (bit0 symbol, bit1 atom, bit2 '[',
+     * bit3 ']', bit4 'C', bit5 'l', bit6 'B', bit7 'r'); `vocab` entries, host pointer.   */
+    const uint8_t* token_class;
+} mnx_config;
+
+/* lifecycle ------------------------------------------------------------------------- */
+int mnx_create(const mnx_config* cfg, mnx_engine** out);
+int mnx_destroy(mnx_engine* e);
+/* message of the last failure on this handle (or of the last failed mnx_create if e==NULL) */
+const char* mnx_last_error(const mnx_engine* e);
+
+/* weights: one call per state-dict entry, `name` = "encoder.<key>" or "decoder.<key>" with the
+ * reference's own keys; data is host fp32 (or int64 for index buffers, which are verified
+ * against the recomputed table and otherwise ignored). */
+int mnx_load_tensor(mnx_engine* e, const char* name, const void* host_data,
+                    const int64_t* shape, int32_t ndim, int32_t is_int64);
+int mnx_finalize_weights(mnx_engine* e);
+
+/* hot path --------------------------------------------------------------------------- */
+/* images: device fp32 NCHW (B,3,H,W), already normalised.  features: device fp32
+ * (B, S, encoder_dim) with S = ceil(H/32)*ceil(W/32) (Swin) or (H/32)*(W/32) (ConvNeXt). */
+int mnx_encode(mnx_engine* e, const float* images, int32_t B, int32_t H, int32_t W,
+               float* features, void* cuda_stream);
+
+/* Greedy decode of B rows against their (B,S,encoder_dim) feature maps.
+ * ids        int32 (B, max_len)  chosen ids without <sos>, including <eos>, 0-padded
+ * lens       int32 (B)           number of valid ids per row
+ * token_logp fp32  (B, max_len)  masked log-prob of each chosen id
+ * hidden     fp32  (B, max_len, 256) final-LayerNorm output per step (may be NULL: the
+ *                                engine then keeps it internally for mnx_edges)
+ * Row r of the alive batch receives positional encoding pe[rank of r among alive rows],
+ * exactly as the reference does. */
+int mnx_decode_greedy(mnx_engine* e, const float* features, int32_t B, int32_t S,
+                      int32_t* ids, int32_t* lens, float* token_logp, float* hidden,
+                      void* cuda_stream);
+
+/* atom_idx int32 (B, max_atoms) positions (into ids) right after each atom's Y token,
+ * n_atoms int32 (B).  Atoms beyond max_atoms raise MNX_ERR_CAPACITY at mnx_edges. */
+int mnx_atom_indices(mnx_engine* e, const int32_t* ids, const int32_t* lens, int32_t B,
+                     int32_t* atom_idx, int32_t* n_atoms, void* cuda_stream);
+
+/* edges uint8 (B, max_atoms, max_atoms): argmax class after the reference's symmetrisation;
+ * edge_score fp32 (B, max_atoms, max_atoms) max symmetrised probability (may be NULL).
+ * hidden may be NULL to use the engine-internal copy from the last mnx_decode_greedy. */
+int mnx_edges(mnx_engine* e, const float* hidden, const int32_t* atom_idx, const int32_t* n_atoms,
+              int32_t B, uint8_t* edges, float* edge_score, void* cuda_stream);
+
+/* encoder -> decode -> atom scan -> bond head in one call, device pointers in and out. */
+int mnx_predict(mnx_engine* e, const float* images, int32_t B, int32_t H, int32_t W,
+                int32_t* ids, int32_t* lens, float* token_logp,
+                int32_t* atom_idx, int32_t* n_atoms, uint8_t* edges, void* cuda_stream);
+
+/* Same, with HOST buffers (pinned or pageable): copies in, runs, copies out, synchronises. */
+int mnx_predict_host(mnx_engine* e, const float* images_host, int32_t B, int32_t H, int32_t W,
+                     int32_t* ids_host, int32_t* lens_host, float* token_logp_host,
+                     int32_t* atom_idx_host, int32_t* n_atoms_host, uint8_t* edges_host);
+
+/* introspection ------------------------------------------------------------------------ */
+/* number of kernel launches issued by this handle since creation (graph nodes counted
+ * per replay); used by bench.py for `gpu_launches`. */
+int64_t mnx_launch_count(const mnx_engine* e);
+/* steps executed by the last decode (<= max_len) */
+int32_t mnx_last_decode_steps(const mnx_engine* e);
+/* time one internal phase in isolation for the roofline report: fills ms with the mean
+ * device time of `iters` launches of kernel `which` on the shapes of the last call
+ * (see DESIGN.md for the ids).  Returns MNX_ERR_INVALID for unknown ids. */
+int mnx_time_kernel(mnx_engine* e, int32_t which, int32_t iters, float* ms, void* cuda_stream);
+
+/* stand-alone GEMM entry used by the parity tests of the tensor-core kernel:
+ * C[M,N] (fp32) = A[M,K] (fp32, rounded to bf16) * W[N,K]^T (fp32, rounded to bf16) + bias */
+int mnx_test_gemm_bf16(const float* A, const float* W, const float* bias, float* C,
+                       int32_t M, int32_t N, int32_t K, int32_t epilogue, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOLNEXTR_B200_H */

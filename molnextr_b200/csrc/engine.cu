@@ -1,0 +1,565 @@
+// C ABI of the engine (include/molnextr_b200.h): handle lifetime, weight repacking, workspaces,
+// CUDA-graph management of the decode loop, and the calls that chain encoder -> decoder -> bond
+// head.  Host logic only; every arithmetic kernel lives in decoder.cu / gemm_tc.cu / swin.cu /
+// convnext.cu.
+#include "../../include/molnextr_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "decoder.cuh"
+#include "encoder.cuh"
+
+namespace mnx {
+// decoder.cu
+cudaError_t dec_configure();
+int dec_launch_step(const DecBuffers& b, const DecWeights& w, const Grammar& g, cudaStream_t s, cudaError_t* err);
+cudaError_t dec_precompute(const DecBuffers& b, const DecWeights& w, const float* features, int enc_dim,
+                           cudaStream_t s, int* launches);
+cudaError_t dec_atom_scan(const int* ids, const int* lens, int B, int T, const uint8_t* cls, const Grammar& g,
+                          int max_atoms, int* atom_idx, int* n_atoms, cudaStream_t s);
+cudaError_t dec_edges(const float* hidden, const int* atom_idx, const int* n_atoms, int B, int T, int max_atoms,
+                      const DecWeights& w, float* hg, float* AB, float* prob, uint8_t* edges, float* score,
+                      cudaStream_t s, int* launches);
+cudaError_t dec_time_kernel(int which, int iters, const DecBuffers& b, const DecWeights& w, const Grammar& g,
+                            int step, float* ms, cudaStream_t s);
+}  // namespace mnx
+
+using namespace mnx;
+
+static thread_local std::string g_create_error;
+
+struct HostTensor {
+    std::vector<int64_t> shape;
+    std::vector<float> f;
+    std::vector<int64_t> i;
+    bool used = false;
+    int64_t numel() const {
+        int64_t n = 1;
+        for (auto d : shape) n *= d;
+        return n;
+    }
+};
+
+struct mnx_engine {
+    mnx_config cfg{};
+    std::string err;
+    std::map<std::string, HostTensor> host_w;
+    bool finalized = false;
+    std::vector<void*> allocs;
+    std::vector<uint8_t> cls_host;
+    uint8_t* d_cls = nullptr;
+    DecWeights dw{};
+    Grammar g{};
+    int S_max = 0;
+    // decoder workspaces (sized for max_batch / S_max / max_len)
+    DecState* st = nullptr;
+    int *alive = nullptr, *cur_tok = nullptr, *finished = nullptr;
+    float *xa = nullptr, *xb = nullptr, *q = nullptr, *part = nullptr, *part2 = nullptr, *hbuf = nullptr;
+    float *selfK = nullptr, *selfV = nullptr, *crossK = nullptr, *crossV = nullptr, *membank = nullptr;
+    int *ids = nullptr, *lens = nullptr;
+    float *logp = nullptr, *hidden = nullptr;
+    // bond head
+    float *hg = nullptr, *AB = nullptr, *prob = nullptr;
+    // predict-path staging
+    float* features = nullptr;
+    float* images = nullptr;
+    int *atom_idx = nullptr, *n_atoms = nullptr;
+    uint8_t* edges = nullptr;
+    // graph of STEPS_PER_GRAPH decode steps for one (B, S)
+    cudaGraphExec_t graph = nullptr;
+    int graph_B = -1, graph_S = -1, graph_nodes = 0;
+    cudaStream_t cap_stream = nullptr;   // capture-only stream (the legacy default stream cannot be captured)
+    int* h_done = nullptr;   // pinned
+    int64_t launches = 0;
+    int last_steps = 0;
+    int last_B = 0, last_S = 0;
+    EncoderState enc{};
+};
+
+static const int STEPS_PER_GRAPH = 16;
+
+static int fail(mnx_engine* e, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (e) e->err = buf; else g_create_error = buf;
+    return code;
+}
+#define CUDA_TRY(e, x)                                                                         \
+    do {                                                                                       \
+        cudaError_t _c = (x);                                                                  \
+        if (_c != cudaSuccess)                                                                 \
+            return fail(e, MNX_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(_c), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T>
+static cudaError_t dev_alloc(mnx_engine* e, T** p, size_t count) {
+    void* v = nullptr;
+    cudaError_t c = cudaMalloc(&v, count * sizeof(T) + 256);
+    if (c != cudaSuccess) return c;
+    e->allocs.push_back(v);
+    *p = reinterpret_cast<T*>(v);
+    return cudaSuccess;
+}
+
+// upload a host fp32 array to a fresh device buffer
+cudaError_t mnx_upload(mnx_engine* e, const std::vector<float>& h, const float** out) {
+    float* d = nullptr;
+    cudaError_t c = dev_alloc(e, &d, h.size());
+    if (c != cudaSuccess) return c;
+    c = cudaMemcpy(d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice);
+    *out = d;
+    return c;
+}
+cudaError_t mnx_upload_raw(mnx_engine* e, const void* h, size_t bytes, void** out) {
+    uint8_t* d = nullptr;
+    cudaError_t c = dev_alloc(e, &d, bytes);
+    if (c != cudaSuccess) return c;
+    c = cudaMemcpy(d, h, bytes, cudaMemcpyHostToDevice);
+    *out = d;
+    return c;
+}
+cudaError_t mnx_dev_alloc_bytes(mnx_engine* e, void** p, size_t bytes) {
+    uint8_t* d = nullptr;
+    cudaError_t c = dev_alloc(e, &d, bytes);
+    *p = d;
+    return c;
+}
+
+extern "C" const char* mnx_last_error(const mnx_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int mnx_create(const mnx_config* cfg, mnx_engine** out) {
+    if (!cfg || !out) return fail(nullptr, MNX_ERR_INVALID, "mnx_create: null argument");
+    if (cfg->max_batch < 1 || cfg->max_batch > 5000)
+        return fail(nullptr, MNX_ERR_INVALID, "max_batch must be in [1,5000] (positional-encoding table has 5000 rows)");
+    if (cfg->vocab < 1 || cfg->vocab > 256 || cfg->max_len < 1 || cfg->max_len % STEPS_PER_GRAPH != 0)
+        return fail(nullptr, MNX_ERR_INVALID, "vocab must be <=256 and max_len a multiple of %d", STEPS_PER_GRAPH);
+    if (cfg->tok_offset + cfg->max_x + cfg->max_y != cfg->vocab)
+        return fail(nullptr, MNX_ERR_INVALID, "vocab != tok_offset + max_x + max_y");
+    if (!cfg->token_class) return fail(nullptr, MNX_ERR_INVALID, "token_class table is required");
+    if (cfg->max_atoms < 1 || cfg->max_atoms * 3 > cfg->max_len)
+        return fail(nullptr, MNX_ERR_INVALID, "max_atoms must be in [1, max_len/3]");
+    if (cfg->encoder_dim % 16 != 0) return fail(nullptr, MNX_ERR_INVALID, "encoder_dim must be a multiple of 16");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, MNX_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, MNX_ERR_INVALID, "bad device ordinal %d", cfg->device);
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10)
+        return fail(nullptr, MNX_ERR_CUDA, "device %d is sm_%d%d; this library contains sm_100a code only", cfg->device,
+                    prop.major, prop.minor);
+    mnx_engine* e = new mnx_engine();
+    e->cfg = *cfg;
+    e->cls_host.assign(cfg->token_class, cfg->token_class + cfg->vocab);
+    e->cfg.token_class = nullptr;
+    e->g = Grammar{cfg->vocab, cfg->tok_offset, cfg->max_x, cfg->max_y, /*eos*/ 2, /*sos*/ 1, cfg->max_len};
+    const int hs = (cfg->max_height + 31) / 32, ws = (cfg->max_width + 31) / 32;
+    e->S_max = hs * ws;
+    if (e->S_max < 1 || e->S_max > ATTN_MAXKEYS_HOST) {
+        delete e;
+        return fail(nullptr, MNX_ERR_INVALID, "image bound gives %d memory positions; supported range is [1,%d]", hs * ws,
+                    ATTN_MAXKEYS_HOST);
+    }
+    cudaError_t c = cudaSetDevice(cfg->device);
+    if (c == cudaSuccess) c = dec_configure();
+    if (c == cudaSuccess) c = cudaMallocHost(&e->h_done, sizeof(int));
+    if (c == cudaSuccess) c = cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking);
+    if (c != cudaSuccess) {
+        std::string m = cudaGetErrorString(c);
+        delete e;
+        return fail(nullptr, MNX_ERR_CUDA, "device setup failed: %s", m.c_str());
+    }
+    *out = e;
+    return MNX_OK;
+}
+
+extern "C" int mnx_destroy(mnx_engine* e) {
+    if (!e) return MNX_OK;
+    cudaSetDevice(e->cfg.device);
+    cudaDeviceSynchronize();
+    if (e->graph) cudaGraphExecDestroy(e->graph);
+    encoder_destroy(e->enc);
+    for (void* p : e->allocs) cudaFree(p);
+    if (e->h_done) cudaFreeHost(e->h_done);
+    if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+    delete e;
+    return MNX_OK;
+}
+
+extern "C" int mnx_load_tensor(mnx_engine* e, const char* name, const void* host_data, const int64_t* shape,
+                               int32_t ndim, int32_t is_int64) {
+    if (!e || !name || !host_data || (!shape && ndim > 0)) return fail(e, MNX_ERR_INVALID, "mnx_load_tensor: null argument");
+    if (e->finalized) return fail(e, MNX_ERR_INVALID, "weights already finalized");
+    HostTensor t;
+    t.shape.assign(shape, shape + ndim);
+    const int64_t n = t.numel();
+    if (is_int64) t.i.assign((const int64_t*)host_data, (const int64_t*)host_data + n);
+    else t.f.assign((const float*)host_data, (const float*)host_data + n);
+    std::string key(name);
+    size_t pos;
+    while ((pos = key.find("module.")) != std::string::npos) key.erase(pos, 7);   // DDP prefix, model.py:25-26
+    if (e->host_w.count(key)) return fail(e, MNX_ERR_WEIGHTS, "tensor %s loaded twice", key.c_str());
+    e->host_w.emplace(key, std::move(t));
+    return MNX_OK;
+}
+
+// fetch a required fp32 tensor with an exact shape
+static const HostTensor* need(mnx_engine* e, const std::string& key, std::initializer_list<int64_t> shape) {
+    auto it = e->host_w.find(key);
+    if (it == e->host_w.end()) {
+        fail(e, MNX_ERR_WEIGHTS, "missing tensor %s", key.c_str());
+        return nullptr;
+    }
+    HostTensor& t = it->second;
+    if (t.shape != std::vector<int64_t>(shape) || t.f.empty()) {
+        std::string got;
+        for (auto d : t.shape) got += std::to_string(d) + ",";
+        fail(e, MNX_ERR_WEIGHTS, "tensor %s has shape (%s), not the expected one", key.c_str(), got.c_str());
+        return nullptr;
+    }
+    t.used = true;
+    return &t;
+}
+const std::vector<float>* mnx_need(mnx_engine* e, const std::string& key, std::initializer_list<int64_t> shape) {
+    const HostTensor* t = need(e, key, shape);
+    return t ? &t->f : nullptr;
+}
+const std::vector<int64_t>* mnx_need_i64(mnx_engine* e, const std::string& key, std::initializer_list<int64_t> shape) {
+    auto it = e->host_w.find(key);
+    if (it == e->host_w.end() || it->second.shape != std::vector<int64_t>(shape) || it->second.i.empty()) {
+        fail(e, MNX_ERR_WEIGHTS, "missing or mis-shaped index tensor %s", key.c_str());
+        return nullptr;
+    }
+    it->second.used = true;
+    return &it->second.i;
+}
+void mnx_set_error(mnx_engine* e, const char* msg) { e->err = msg; }
+
+// transpose [N][K] (torch Linear weight) into K-major [K][Npad] at column offset c0
+static void put_transposed(std::vector<float>& dst, int Npad, int c0, const std::vector<float>& W, int N, int K) {
+    for (int n = 0; n < N; ++n)
+        for (int k = 0; k < K; ++k) dst[(size_t)k * Npad + c0 + n] = W[(size_t)n * K + k];
+}
+
+static int finalize_decoder(mnx_engine* e) {
+    const int D = MNX_DEC_D, V = e->cfg.vocab, ED = e->cfg.encoder_dim;
+    const std::string P = "decoder.decoder.chartok_coords.";
+#define NEED(var, key, ...)                          \
+    const HostTensor* var = need(e, key, {__VA_ARGS__}); \
+    if (!var) return MNX_ERR_WEIGHTS
+#define UP(dst, vec) CUDA_TRY(e, mnx_upload(e, vec, &(dst)))
+    std::vector<float> wkv((size_t)D * MNX_DEC_L * 512), bkv((size_t)MNX_DEC_L * 512);
+    for (int l = 0; l < MNX_DEC_L; ++l) {
+        const std::string L = P + "decoder.transformer_layers." + std::to_string(l) + ".";
+        DecLayerW& w = e->dw.layer[l];
+        NEED(ln1w, L + "layer_norm_1.weight", D); NEED(ln1b, L + "layer_norm_1.bias", D);
+        NEED(ln2w, L + "layer_norm_2.weight", D); NEED(ln2b, L + "layer_norm_2.bias", D);
+        NEED(lnfw, L + "feed_forward.layer_norm.weight", D); NEED(lnfb, L + "feed_forward.layer_norm.bias", D);
+        UP(w.ln1_w, ln1w->f); UP(w.ln1_b, ln1b->f); UP(w.ln2_w, ln2w->f); UP(w.ln2_b, ln2b->f);
+        UP(w.lnf_w, lnfw->f); UP(w.lnf_b, lnfb->f);
+        NEED(sq, L + "self_attn.linear_query.weight", D, D); NEED(sqb, L + "self_attn.linear_query.bias", D);
+        NEED(sk, L + "self_attn.linear_keys.weight", D, D); NEED(skb, L + "self_attn.linear_keys.bias", D);
+        NEED(sv, L + "self_attn.linear_values.weight", D, D); NEED(svb, L + "self_attn.linear_values.bias", D);
+        NEED(so, L + "self_attn.final_linear.weight", D, D); NEED(sob, L + "self_attn.final_linear.bias", D);
+        std::vector<float> qkv((size_t)D * 768), bq(768);
+        put_transposed(qkv, 768, 0, sq->f, D, D);
+        put_transposed(qkv, 768, 256, sk->f, D, D);
+        put_transposed(qkv, 768, 512, sv->f, D, D);
+        std::copy(sqb->f.begin(), sqb->f.end(), bq.begin());
+        std::copy(skb->f.begin(), skb->f.end(), bq.begin() + 256);
+        std::copy(svb->f.begin(), svb->f.end(), bq.begin() + 512);
+        UP(w.wqkv_t, qkv); UP(w.bqkv, bq);
+        std::vector<float> tmp((size_t)D * D);
+        put_transposed(tmp, D, 0, so->f, D, D);
+        UP(w.wo_s_t, tmp); UP(w.bo_s, sob->f);
+        NEED(cq, L + "context_attn.linear_query.weight", D, D); NEED(cqb, L + "context_attn.linear_query.bias", D);
+        NEED(ck, L + "context_attn.linear_keys.weight", D, D); NEED(ckb, L + "context_attn.linear_keys.bias", D);
+        NEED(cv, L + "context_attn.linear_values.weight", D, D); NEED(cvb, L + "context_attn.linear_values.bias", D);
+        NEED(co, L + "context_attn.final_linear.weight", D, D); NEED(cob, L + "context_attn.final_linear.bias", D);
+        put_transposed(tmp, D, 0, cq->f, D, D);
+        UP(w.wq_c_t, tmp); UP(w.bq_c, cqb->f);
+        put_transposed(tmp, D, 0, co->f, D, D);
+        UP(w.wo_c_t, tmp); UP(w.bo_c, cob->f);
+        put_transposed(wkv, MNX_DEC_L * 512, l * 512, ck->f, D, D);
+        put_transposed(wkv, MNX_DEC_L * 512, l * 512 + 256, cv->f, D, D);
+        std::copy(ckb->f.begin(), ckb->f.end(), bkv.begin() + l * 512);
+        std::copy(cvb->f.begin(), cvb->f.end(), bkv.begin() + l * 512 + 256);
+        NEED(w1, L + "feed_forward.w_1.weight", MNX_DEC_FF, D); NEED(b1, L + "feed_forward.w_1.bias", MNX_DEC_FF);
+        NEED(w2, L + "feed_forward.w_2.weight", D, MNX_DEC_FF); NEED(b2, L + "feed_forward.w_2.bias", D);
+        std::vector<float> w1t((size_t)D * MNX_DEC_FF), w2t((size_t)MNX_DEC_FF * D);
+        put_transposed(w1t, MNX_DEC_FF, 0, w1->f, MNX_DEC_FF, D);
+        put_transposed(w2t, D, 0, w2->f, D, MNX_DEC_FF);
+        UP(w.w1_t, w1t); UP(w.b1, b1->f); UP(w.w2_t, w2t); UP(w.b2, b2->f);
+    }
+    UP(e->dw.wkv_c_t, wkv); UP(e->dw.bkv_c, bkv);
+    NEED(lnw, P + "decoder.layer_norm.weight", D); NEED(lnb, P + "decoder.layer_norm.bias", D);
+    UP(e->dw.lnF_w, lnw->f); UP(e->dw.lnF_b, lnb->f);
+    NEED(ow, P + "output_layer.weight", V, D); NEED(ob, P + "output_layer.bias", V);
+    std::vector<float> wout((size_t)D * 256, 0.f), bout(256, 0.f);
+    put_transposed(wout, 256, 0, ow->f, V, D);
+    std::copy(ob->f.begin(), ob->f.end(), bout.begin());
+    UP(e->dw.wout_t, wout); UP(e->dw.bout, bout);
+    NEED(emb, P + "embeddings.make_embedding.emb_luts.0.weight", V, D);
+    UP(e->dw.emb, emb->f);
+    NEED(pe, P + "embeddings.make_embedding.pe.pe", 5000, 1, D);
+    UP(e->dw.pe, pe->f);
+    NEED(ew, P + "enc_trans_layer.0.weight", D, ED); NEED(eb, P + "enc_trans_layer.0.bias", D);
+    std::vector<float> wenc((size_t)ED * D);
+    put_transposed(wenc, D, 0, ew->f, D, ED);
+    UP(e->dw.wenc_t, wenc); UP(e->dw.benc, eb->f);
+    NEED(g0, "decoder.decoder.edges.mlp.0.weight", D, 2 * D); NEED(g0b, "decoder.decoder.edges.mlp.0.bias", D);
+    NEED(g2, "decoder.decoder.edges.mlp.2.weight", MNX_EDGE_CLASSES, D); NEED(g2b, "decoder.decoder.edges.mlp.2.bias", MNX_EDGE_CLASSES);
+    std::vector<float> wab((size_t)D * 512);
+    for (int n = 0; n < D; ++n)
+        for (int k = 0; k < D; ++k) {
+            wab[(size_t)k * 512 + n] = g0->f[(size_t)n * 512 + k];
+            wab[(size_t)k * 512 + 256 + n] = g0->f[(size_t)n * 512 + 256 + k];
+        }
+    UP(e->dw.we_a_t, wab); e->dw.we_b_t = nullptr;
+    UP(e->dw.be0, g0b->f); UP(e->dw.we2, g2->f); UP(e->dw.be2, g2b->f);
+#undef NEED
+#undef UP
+    return MNX_OK;
+}
+
+static int alloc_workspaces(mnx_engine* e) {
+    const size_t B = e->cfg.max_batch, T = e->cfg.max_len, S = e->S_max, KA = e->cfg.max_atoms;
+    CUDA_TRY(e, dev_alloc(e, &e->st, 1));
+    CUDA_TRY(e, dev_alloc(e, &e->alive, 2 * B));
+    CUDA_TRY(e, dev_alloc(e, &e->cur_tok, B));
+    CUDA_TRY(e, dev_alloc(e, &e->finished, B));
+    CUDA_TRY(e, dev_alloc(e, &e->xa, B * 256));
+    CUDA_TRY(e, dev_alloc(e, &e->xb, B * 256));
+    CUDA_TRY(e, dev_alloc(e, &e->q, B * 256));
+    CUDA_TRY(e, dev_alloc(e, &e->part, B * 8 * 256));
+    CUDA_TRY(e, dev_alloc(e, &e->part2, B * 8 * 256));
+    CUDA_TRY(e, dev_alloc(e, &e->hbuf, B * 1024));
+    CUDA_TRY(e, dev_alloc(e, &e->selfK, MNX_DEC_L * B * T * 256));
+    CUDA_TRY(e, dev_alloc(e, &e->selfV, MNX_DEC_L * B * T * 256));
+    CUDA_TRY(e, dev_alloc(e, &e->crossK, MNX_DEC_L * B * S * 256));
+    CUDA_TRY(e, dev_alloc(e, &e->crossV, MNX_DEC_L * B * S * 256));
+    CUDA_TRY(e, dev_alloc(e, &e->membank, B * S * 256));
+    CUDA_TRY(e, dev_alloc(e, &e->ids, B * T));
+    CUDA_TRY(e, dev_alloc(e, &e->lens, B));
+    CUDA_TRY(e, dev_alloc(e, &e->logp, B * T));
+    CUDA_TRY(e, dev_alloc(e, &e->hidden, B * T * 256));
+    CUDA_TRY(e, dev_alloc(e, &e->hg, B * KA * 256));
+    CUDA_TRY(e, dev_alloc(e, &e->AB, B * KA * 512));
+    CUDA_TRY(e, dev_alloc(e, &e->prob, B * KA * KA * 8));
+    CUDA_TRY(e, dev_alloc(e, &e->features, B * S * (size_t)e->cfg.encoder_dim));
+    CUDA_TRY(e, dev_alloc(e, &e->atom_idx, B * KA));
+    CUDA_TRY(e, dev_alloc(e, &e->n_atoms, B));
+    CUDA_TRY(e, dev_alloc(e, &e->edges, B * KA * KA));
+    if (e->cfg.encoder_kind != MNX_ENCODER_NONE)
+        CUDA_TRY(e, dev_alloc(e, &e->images, B * 3 * (size_t)e->cfg.max_height * e->cfg.max_width));
+    void* cls = nullptr;
+    CUDA_TRY(e, mnx_upload_raw(e, e->cls_host.data(), e->cls_host.size(), &cls));
+    e->d_cls = (uint8_t*)cls;
+    return MNX_OK;
+}
+
+extern "C" int mnx_finalize_weights(mnx_engine* e) {
+    if (!e) return MNX_ERR_INVALID;
+    if (e->finalized) return fail(e, MNX_ERR_INVALID, "weights already finalized");
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    int rc = finalize_decoder(e);
+    if (rc != MNX_OK) return rc;
+    if (e->cfg.encoder_kind != MNX_ENCODER_NONE) {
+        rc = encoder_finalize(e, e->enc, e->cfg);
+        if (rc != MNX_OK) return rc;
+    }
+    for (auto& kv : e->host_w)
+        if (!kv.second.used) return fail(e, MNX_ERR_WEIGHTS, "unexpected tensor %s (not part of the model)", kv.first.c_str());
+    rc = alloc_workspaces(e);
+    if (rc != MNX_OK) return rc;
+    e->host_w.clear();
+    e->finalized = true;
+    CUDA_TRY(e, cudaDeviceSynchronize());
+    return MNX_OK;
+}
+
+static DecBuffers make_buffers(mnx_engine* e, int B, int S) {
+    DecBuffers b{};
+    b.st = e->st; b.alive = e->alive; b.cur_tok = e->cur_tok; b.finished = e->finished;
+    b.xa = e->xa; b.xb = e->xb; b.q = e->q; b.part = e->part; b.part2 = e->part2; b.hbuf = e->hbuf;
+    b.selfK = e->selfK; b.selfV = e->selfV; b.crossK = e->crossK; b.crossV = e->crossV; b.membank = e->membank;
+    b.B = B; b.S = S; b.T = e->cfg.max_len;
+    b.ids = e->ids; b.lens = e->lens; b.logp = e->logp; b.hidden = e->hidden;
+    return b;
+}
+
+static int ensure_graph(mnx_engine* e, const DecBuffers& b) {
+    if (e->graph && e->graph_B == b.B && e->graph_S == b.S) return MNX_OK;
+    cudaStream_t s = e->cap_stream;
+    if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(e, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    int nodes = 0;
+    cudaError_t kerr = cudaSuccess;
+    for (int i = 0; i < STEPS_PER_GRAPH && kerr == cudaSuccess; ++i) nodes += dec_launch_step(b, e->dw, e->g, s, &kerr);
+    cudaError_t cerr = cudaStreamEndCapture(s, &graph);
+    if (kerr != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        return fail(e, MNX_ERR_CUDA, "decode-step launch failed during capture: %s", cudaGetErrorString(kerr));
+    }
+    CUDA_TRY(e, cerr);
+    cudaError_t ierr = cudaGraphInstantiate(&e->graph, graph, 0);
+    cudaGraphDestroy(graph);
+    CUDA_TRY(e, ierr);
+    e->graph_B = b.B; e->graph_S = b.S; e->graph_nodes = nodes;
+    return MNX_OK;
+}
+
+static int decode_internal(mnx_engine* e, const float* features, int B, int S, cudaStream_t s) {
+    if (!e->finalized) return fail(e, MNX_ERR_INVALID, "weights not finalized");
+    if (B < 1 || B > e->cfg.max_batch) return fail(e, MNX_ERR_CAPACITY, "batch %d exceeds max_batch %d", B, e->cfg.max_batch);
+    if (S < 1 || S > e->S_max) return fail(e, MNX_ERR_CAPACITY, "memory length %d exceeds capacity %d", S, e->S_max);
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    DecBuffers b = make_buffers(e, B, S);
+    const int T = e->cfg.max_len;
+    CUDA_TRY(e, cudaMemsetAsync(e->st, 0, sizeof(DecState), s));
+    CUDA_TRY(e, cudaMemsetAsync(e->finished, 0, sizeof(int) * B, s));
+    CUDA_TRY(e, cudaMemsetAsync(e->lens, 0, sizeof(int) * B, s));
+    CUDA_TRY(e, cudaMemsetAsync(e->ids, 0, sizeof(int) * (size_t)B * T, s));
+    CUDA_TRY(e, cudaMemsetAsync(e->logp, 0, sizeof(float) * (size_t)B * T, s));
+    int nl = 0;
+    CUDA_TRY(e, dec_precompute(b, e->dw, features, e->cfg.encoder_dim, s, &nl));
+    e->launches += nl;
+    int rc = ensure_graph(e, b);
+    if (rc != MNX_OK) return rc;
+    for (int chunk = 0; chunk < T / STEPS_PER_GRAPH; ++chunk) {
+        CUDA_TRY(e, cudaGraphLaunch(e->graph, s));
+        e->launches += e->graph_nodes;
+        CUDA_TRY(e, cudaMemcpyAsync(e->h_done, &e->st->done, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(e, cudaStreamSynchronize(s));
+        if (*e->h_done) break;
+    }
+    DecState hs{};
+    CUDA_TRY(e, cudaMemcpyAsync(&hs, e->st, sizeof(DecState), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(e, cudaStreamSynchronize(s));
+    e->last_steps = hs.steps_run;
+    e->last_B = B; e->last_S = S;
+    return MNX_OK;
+}
+
+extern "C" int mnx_decode_greedy(mnx_engine* e, const float* features, int32_t B, int32_t S, int32_t* ids,
+                                 int32_t* lens, float* token_logp, float* hidden, void* cuda_stream) {
+    if (!e || !features) return fail(e, MNX_ERR_INVALID, "mnx_decode_greedy: null argument");
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    int rc = decode_internal(e, features, B, S, s);
+    if (rc != MNX_OK) return rc;
+    const size_t T = e->cfg.max_len;
+    if (ids) CUDA_TRY(e, cudaMemcpyAsync(ids, e->ids, sizeof(int) * B * T, cudaMemcpyDeviceToDevice, s));
+    if (lens) CUDA_TRY(e, cudaMemcpyAsync(lens, e->lens, sizeof(int) * B, cudaMemcpyDeviceToDevice, s));
+    if (token_logp) CUDA_TRY(e, cudaMemcpyAsync(token_logp, e->logp, sizeof(float) * B * T, cudaMemcpyDeviceToDevice, s));
+    if (hidden) CUDA_TRY(e, cudaMemcpyAsync(hidden, e->hidden, sizeof(float) * B * T * 256, cudaMemcpyDeviceToDevice, s));
+    return MNX_OK;
+}
+
+extern "C" int mnx_atom_indices(mnx_engine* e, const int32_t* ids, const int32_t* lens, int32_t B, int32_t* atom_idx,
+                                int32_t* n_atoms, void* cuda_stream) {
+    if (!e || !ids || !lens || !atom_idx || !n_atoms) return fail(e, MNX_ERR_INVALID, "mnx_atom_indices: null argument");
+    if (!e->finalized) return fail(e, MNX_ERR_INVALID, "weights not finalized");
+    if (B < 1 || B > e->cfg.max_batch) return fail(e, MNX_ERR_CAPACITY, "batch %d exceeds max_batch %d", B, e->cfg.max_batch);
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    CUDA_TRY(e, dec_atom_scan(ids, lens, B, e->cfg.max_len, e->d_cls, e->g, e->cfg.max_atoms, atom_idx, n_atoms,
+                              (cudaStream_t)cuda_stream));
+    e->launches += 1;
+    return MNX_OK;
+}
+
+extern "C" int mnx_edges(mnx_engine* e, const float* hidden, const int32_t* atom_idx, const int32_t* n_atoms, int32_t B,
+                         uint8_t* edges, float* edge_score, void* cuda_stream) {
+    if (!e || !atom_idx || !n_atoms || !edges) return fail(e, MNX_ERR_INVALID, "mnx_edges: null argument");
+    if (!e->finalized) return fail(e, MNX_ERR_INVALID, "weights not finalized");
+    if (B < 1 || B > e->cfg.max_batch) return fail(e, MNX_ERR_CAPACITY, "batch %d exceeds max_batch %d", B, e->cfg.max_batch);
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    int nl = 0;
+    CUDA_TRY(e, dec_edges(hidden ? hidden : e->hidden, atom_idx, n_atoms, B, e->cfg.max_len, e->cfg.max_atoms, e->dw,
+                          e->hg, e->AB, e->prob, edges, edge_score, (cudaStream_t)cuda_stream, &nl));
+    e->launches += nl;
+    return MNX_OK;
+}
+
+extern "C" int mnx_encode(mnx_engine* e, const float* images, int32_t B, int32_t H, int32_t W, float* features,
+                          void* cuda_stream) {
+    if (!e || !images || !features) return fail(e, MNX_ERR_INVALID, "mnx_encode: null argument");
+    if (!e->finalized) return fail(e, MNX_ERR_INVALID, "weights not finalized");
+    if (e->cfg.encoder_kind == MNX_ENCODER_NONE) return fail(e, MNX_ERR_INVALID, "this handle was created without an encoder");
+    if (B < 1 || B > e->cfg.max_batch) return fail(e, MNX_ERR_CAPACITY, "batch %d exceeds max_batch %d", B, e->cfg.max_batch);
+    if (H < 32 || W < 32 || H > e->cfg.max_height || W > e->cfg.max_width)
+        return fail(e, MNX_ERR_CAPACITY, "image %dx%d outside [32, %dx%d]", H, W, e->cfg.max_height, e->cfg.max_width);
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    int nl = 0;
+    int rc = encoder_forward(e, e->enc, images, B, H, W, features, (cudaStream_t)cuda_stream, &nl);
+    e->launches += nl;
+    return rc;
+}
+
+extern "C" int mnx_predict(mnx_engine* e, const float* images, int32_t B, int32_t H, int32_t W, int32_t* ids,
+                           int32_t* lens, float* token_logp, int32_t* atom_idx, int32_t* n_atoms, uint8_t* edges,
+                           void* cuda_stream) {
+    if (!e) return MNX_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    int rc = mnx_encode(e, images, B, H, W, e->features, s);
+    if (rc != MNX_OK) return rc;
+    const int S = encoder_seq_len(e->cfg.encoder_kind, H, W);
+    rc = decode_internal(e, e->features, B, S, s);
+    if (rc != MNX_OK) return rc;
+    rc = mnx_atom_indices(e, e->ids, e->lens, B, e->atom_idx, e->n_atoms, s);
+    if (rc != MNX_OK) return rc;
+    rc = mnx_edges(e, nullptr, e->atom_idx, e->n_atoms, B, e->edges, nullptr, s);
+    if (rc != MNX_OK) return rc;
+    const size_t T = e->cfg.max_len, KA = e->cfg.max_atoms;
+    if (ids) CUDA_TRY(e, cudaMemcpyAsync(ids, e->ids, sizeof(int) * B * T, cudaMemcpyDefault, s));
+    if (lens) CUDA_TRY(e, cudaMemcpyAsync(lens, e->lens, sizeof(int) * B, cudaMemcpyDefault, s));
+    if (token_logp) CUDA_TRY(e, cudaMemcpyAsync(token_logp, e->logp, sizeof(float) * B * T, cudaMemcpyDefault, s));
+    if (atom_idx) CUDA_TRY(e, cudaMemcpyAsync(atom_idx, e->atom_idx, sizeof(int) * B * KA, cudaMemcpyDefault, s));
+    if (n_atoms) CUDA_TRY(e, cudaMemcpyAsync(n_atoms, e->n_atoms, sizeof(int) * B, cudaMemcpyDefault, s));
+    if (edges) CUDA_TRY(e, cudaMemcpyAsync(edges, e->edges, B * KA * KA, cudaMemcpyDefault, s));
+    return MNX_OK;
+}
+
+extern "C" int mnx_predict_host(mnx_engine* e, const float* images_host, int32_t B, int32_t H, int32_t W,
+                                int32_t* ids_host, int32_t* lens_host, float* token_logp_host, int32_t* atom_idx_host,
+                                int32_t* n_atoms_host, uint8_t* edges_host) {
+    if (!e || !images_host) return fail(e, MNX_ERR_INVALID, "mnx_predict_host: null argument");
+    if (!e->finalized) return fail(e, MNX_ERR_INVALID, "weights not finalized");
+    if (e->cfg.encoder_kind == MNX_ENCODER_NONE) return fail(e, MNX_ERR_INVALID, "this handle was created without an encoder");
+    if (B < 1 || B > e->cfg.max_batch || H > e->cfg.max_height || W > e->cfg.max_width)
+        return fail(e, MNX_ERR_CAPACITY, "request (%d,%d,%d) exceeds the sizes given at create", B, H, W);
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    cudaStream_t s = nullptr;   // legacy default stream
+    CUDA_TRY(e, cudaMemcpyAsync(e->images, images_host, sizeof(float) * (size_t)B * 3 * H * W, cudaMemcpyHostToDevice, s));
+    int rc = mnx_predict(e, e->images, B, H, W, ids_host, lens_host, token_logp_host, atom_idx_host, n_atoms_host,
+                         edges_host, s);
+    if (rc != MNX_OK) return rc;
+    CUDA_TRY(e, cudaStreamSynchronize(s));
+    return MNX_OK;
+}
+
+extern "C" int64_t mnx_launch_count(const mnx_engine* e) { return e ? e->launches : 0; }
+extern "C" int32_t mnx_last_decode_steps(const mnx_engine* e) { return e ? e->last_steps : 0; }
+
+extern "C" int mnx_time_kernel(mnx_engine* e, int32_t which, int32_t iters, float* ms, void* cuda_stream) {
+    if (!e || !ms || iters < 1) return fail(e, MNX_ERR_INVALID, "mnx_time_kernel: bad argument");
+    if (!e->finalized || e->last_B == 0) return fail(e, MNX_ERR_INVALID, "run a decode first: timing uses its shapes and caches");
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    if (which >= 100) return encoder_time_kernel(e, e->enc, which, iters, ms, s);
+    DecBuffers b = make_buffers(e, e->last_B, e->last_S);
+    cudaError_t c = dec_time_kernel(which, iters, b, e->dw, e->g, e->cfg.max_len / 2, ms, s);
+    if (c == cudaErrorInvalidValue) return fail(e, MNX_ERR_INVALID, "unknown kernel id %d", which);
+    CUDA_TRY(e, c);
+    return MNX_OK;
+}

@@ -1,0 +1,218 @@
+"""Python handle over the C ABI.  torch tensors are containers only: every call passes
+`data_ptr()`, shapes and the current CUDA stream to libmolnextr_b200.so."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .tokenization import CharTokenizer
+
+MAX_LEN = 480          # FORMAT_INFO['chartok_coords']['max_len'], MolNexTR/utils.py:25
+MAX_ATOMS = 160        # an atom needs >= 3 tokens
+
+
+def token_class_table(tok: CharTokenizer) -> np.ndarray:
+    """Per-id class bits consumed by the device-side atom scan (see include/molnextr_b200.h)."""
+    tab = np.zeros(len(tok), np.uint8)
+    for i in range(tok.offset):
+        bits = 0
+        if tok.is_symbol(i):
+            bits |= 1
+            ch = tok.itos[i]
+            if tok.is_atom_token(ch):
+                bits |= 2
+            for bit, c in ((4, "["), (8, "]"), (16, "C"), (32, "l"), (64, "B"), (128, "r")):
+                if ch == c:
+                    bits |= bit
+        tab[i] = bits
+    return tab
+
+
+def encoder_kind_of(enc_state: Optional[Dict[str, torch.Tensor]]) -> int:
+    if not enc_state:
+        return _cabi.ENCODER_NONE
+    key = next(iter(enc_state)).replace("module.", "")
+    if key.startswith("transformer."):
+        return _cabi.ENCODER_SWIN_B
+    if key.startswith("cnn."):
+        return _cabi.ENCODER_CONVNEXT_B
+    raise ValueError(f"unrecognised encoder state-dict (first key {key!r})")
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class Engine:
+    """One engine per GPU.  `checkpoint` is a dict in the reference schema
+    ({'encoder': sd, 'decoder': sd, 'args': {...}}, main.py:389-398); pass encoder=None for a
+    decoder-only handle."""
+
+    def __init__(self, checkpoint: dict, tokenizer: Optional[CharTokenizer] = None, device: int = 0,
+                 max_batch: int = 32, max_height: int = 384, max_width: int = 384, encoder_dim: int = 1024):
+        if not torch.cuda.is_available():
+            raise EngineError("no CUDA device: molnextr_b200 has no CPU fallback")
+        self.lib = _cabi.load()
+        self.tok = tokenizer or CharTokenizer(64)
+        self.device = torch.device("cuda", device)
+        self.max_batch, self.max_height, self.max_width = max_batch, max_height, max_width
+        self.encoder_dim = encoder_dim
+        enc_sd = checkpoint.get("encoder")
+        self.encoder_kind = encoder_kind_of(enc_sd)
+        offset, maxx, maxy = self.tok.grammar_rule()
+        cls = token_class_table(self.tok)
+        self._cls = cls   # keep alive during create
+        cfg = _cabi.MnxConfig(device=device, encoder_kind=self.encoder_kind, max_batch=max_batch,
+                              max_height=max_height, max_width=max_width, max_len=MAX_LEN, vocab=len(self.tok),
+                              tok_offset=offset, max_x=maxx, max_y=maxy, max_atoms=MAX_ATOMS,
+                              encoder_dim=encoder_dim,
+                              token_class=cls.ctypes.data_as(C.POINTER(C.c_uint8)))
+        h = C.c_void_p()
+        rc = self.lib.mnx_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise EngineError(f"mnx_create failed ({rc}): {self.lib.mnx_last_error(None).decode()}")
+        self.h = h
+        try:
+            if enc_sd:
+                self._load("encoder.", enc_sd)
+            self._load("decoder.", checkpoint["decoder"])
+            self._check(self.lib.mnx_finalize_weights(self.h), "mnx_finalize_weights")
+        except Exception:
+            self.close()
+            raise
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise EngineError(f"{what} failed ({rc}): {self.lib.mnx_last_error(self.h).decode()}")
+
+    def _load(self, scope: str, sd: Dict[str, torch.Tensor]):
+        for k, v in sd.items():
+            t = v.detach().cpu().contiguous()
+            is_i64 = t.dtype == torch.int64
+            if not is_i64:
+                t = t.float().contiguous()
+            shape = (C.c_int64 * t.dim())(*t.shape)
+            self._check(self.lib.mnx_load_tensor(self.h, (scope + k).encode(), C.c_void_p(t.data_ptr()), shape,
+                                                 t.dim(), int(is_i64)), f"mnx_load_tensor({k})")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mnx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self) -> C.c_void_p:
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _p(t: Optional[torch.Tensor]) -> C.c_void_p:
+        return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+    # ------------------------------------------------------------------ hot path
+    def seq_len(self, H: int, W: int) -> int:
+        if self.encoder_kind == _cabi.ENCODER_SWIN_B:
+            h, w = (H + 3) // 4, (W + 3) // 4
+            for _ in range(3):
+                h, w = (h + 1) // 2, (w + 1) // 2
+            return h * w
+        return (H // 32) * (W // 32)
+
+    def encode(self, images: torch.Tensor) -> torch.Tensor:
+        """Encoder.forward (components.py:162-174): fp32 NCHW cuda tensor -> (B,S,1024)."""
+        assert images.is_cuda and images.dtype == torch.float32 and images.dim() == 4 and images.size(1) == 3
+        images = images.contiguous()
+        B, _, H, W = images.shape
+        feats = torch.empty((B, self.seq_len(H, W), self.encoder_dim), device=images.device, dtype=torch.float32)
+        self._check(self.lib.mnx_encode(self.h, self._p(images), B, H, W, self._p(feats), self._stream()), "mnx_encode")
+        return feats
+
+    def decode_greedy(self, features: torch.Tensor, return_hidden: bool = False):
+        """TransformerDecoderAR.decode with GreedySearch (components.py:253-334)."""
+        assert features.is_cuda and features.dtype == torch.float32
+        features = features.contiguous().view(features.size(0), -1, features.size(-1))
+        B, S, _ = features.shape
+        dev = features.device
+        ids = torch.empty((B, MAX_LEN), device=dev, dtype=torch.int32)
+        lens = torch.empty((B,), device=dev, dtype=torch.int32)
+        logp = torch.empty((B, MAX_LEN), device=dev, dtype=torch.float32)
+        hidden = torch.empty((B, MAX_LEN, 256), device=dev, dtype=torch.float32) if return_hidden else None
+        self._check(self.lib.mnx_decode_greedy(self.h, self._p(features), B, S, self._p(ids), self._p(lens),
+                                               self._p(logp), self._p(hidden), self._stream()), "mnx_decode_greedy")
+        out = {"ids": ids, "lens": lens, "logp": logp}
+        if return_hidden:
+            out["hidden"] = hidden
+        return out
+
+    def atom_indices(self, ids: torch.Tensor, lens: torch.Tensor):
+        B = ids.size(0)
+        atom_idx = torch.full((B, MAX_ATOMS), -1, device=ids.device, dtype=torch.int32)
+        n_atoms = torch.empty((B,), device=ids.device, dtype=torch.int32)
+        self._check(self.lib.mnx_atom_indices(self.h, self._p(ids), self._p(lens), B, self._p(atom_idx),
+                                              self._p(n_atoms), self._stream()), "mnx_atom_indices")
+        return atom_idx, n_atoms
+
+    def edges(self, atom_idx: torch.Tensor, n_atoms: torch.Tensor, hidden: Optional[torch.Tensor] = None,
+              return_scores: bool = False):
+        """GraphPredictor + get_edge_prediction (components.py:365-400) for every image of the batch."""
+        B = atom_idx.size(0)
+        edges = torch.zeros((B, MAX_ATOMS, MAX_ATOMS), device=atom_idx.device, dtype=torch.uint8)
+        score = torch.zeros((B, MAX_ATOMS, MAX_ATOMS), device=atom_idx.device, dtype=torch.float32) if return_scores else None
+        self._check(self.lib.mnx_edges(self.h, self._p(hidden), self._p(atom_idx), self._p(n_atoms), B,
+                                       self._p(edges), self._p(score), self._stream()), "mnx_edges")
+        return (edges, score) if return_scores else edges
+
+    def predict(self, images: torch.Tensor):
+        """encoder -> greedy decode -> atom scan -> bond head, device tensors in and out."""
+        assert images.is_cuda and images.dtype == torch.float32
+        images = images.contiguous()
+        B, _, H, W = images.shape
+        dev = images.device
+        ids = torch.empty((B, MAX_LEN), device=dev, dtype=torch.int32)
+        lens = torch.empty((B,), device=dev, dtype=torch.int32)
+        logp = torch.empty((B, MAX_LEN), device=dev, dtype=torch.float32)
+        atom_idx = torch.empty((B, MAX_ATOMS), device=dev, dtype=torch.int32)
+        n_atoms = torch.empty((B,), device=dev, dtype=torch.int32)
+        edges = torch.empty((B, MAX_ATOMS, MAX_ATOMS), device=dev, dtype=torch.uint8)
+        self._check(self.lib.mnx_predict(self.h, self._p(images), B, H, W, self._p(ids), self._p(lens), self._p(logp),
+                                         self._p(atom_idx), self._p(n_atoms), self._p(edges), self._stream()),
+                    "mnx_predict")
+        return {"ids": ids, "lens": lens, "logp": logp, "atom_idx": atom_idx, "n_atoms": n_atoms, "edges": edges}
+
+    def predict_host(self, images: torch.Tensor):
+        """Same through host buffers: H2D of the images and D2H of every result inside the call."""
+        assert not images.is_cuda and images.dtype == torch.float32
+        images = images.contiguous()
+        B, _, H, W = images.shape
+        pin = dict(pin_memory=True)
+        ids = torch.empty((B, MAX_LEN), dtype=torch.int32, **pin)
+        lens = torch.empty((B,), dtype=torch.int32, **pin)
+        logp = torch.empty((B, MAX_LEN), dtype=torch.float32, **pin)
+        atom_idx = torch.empty((B, MAX_ATOMS), dtype=torch.int32, **pin)
+        n_atoms = torch.empty((B,), dtype=torch.int32, **pin)
+        edges = torch.empty((B, MAX_ATOMS, MAX_ATOMS), dtype=torch.uint8, **pin)
+        self._check(self.lib.mnx_predict_host(self.h, self._p(images), B, H, W, self._p(ids), self._p(lens),
+                                              self._p(logp), self._p(atom_idx), self._p(n_atoms), self._p(edges)),
+                    "mnx_predict_host")
+        return {"ids": ids, "lens": lens, "logp": logp, "atom_idx": atom_idx, "n_atoms": n_atoms, "edges": edges}
+
+    # ------------------------------------------------------------------ introspection
+    def launch_count(self) -> int:
+        return int(self.lib.mnx_launch_count(self.h))
+
+    def last_decode_steps(self) -> int:
+        return int(self.lib.mnx_last_decode_steps(self.h))
+
+    def time_kernel(self, which: int, iters: int = 20) -> float:
+        ms = C.c_float(0.0)
+        self._check(self.lib.mnx_time_kernel(self.h, which, iters, C.byref(ms), self._stream()), "mnx_time_kernel")
+        return float(ms.value)
