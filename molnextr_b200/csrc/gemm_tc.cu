@@ -1,0 +1,315 @@
+// bf16 GEMM on the 5th-generation tensor cores of sm_100a, hand-written:
+//   * operands staged by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) into a 3-stage ring,
+//   * one elected thread issues tcgen05.mma (UMMA 128 x 128 x 16, kind::f16, bf16 in / fp32 out),
+//   * the accumulator lives in TMEM (128 lanes x 128 columns) and is read back with tcgen05.ld,
+//   * four epilogue warps apply bias / GELU / layer-scale / residual-add (optionally through a
+//     row map that undoes Swin's window partition + cyclic shift) and write straight to HBM.
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+// One 128 x 128 output tile per CTA; two CTAs are co-resident per SM (96 KB of shared memory and
+// 128 TMEM columns each) so one CTA's epilogue overlaps the other's main loop.
+#include "gemm_tc.cuh"
+
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace mnx {
+
+static constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
+static constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
+static constexpr int B_STAGE_BYTES = BN * BK * 2;   // 16 KB
+static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+static constexpr int GEMM_THREADS = 192;
+static constexpr uint32_t TMEM_COLS = 128;
+
+// ---- PTX wrappers --------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] * B[smem]; both operands K-major, described by 64-bit shared-memory descriptors
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte-swizzled operand tile whose rows are 128 bytes (64 bf16): 8-row groups are
+// 1024 bytes apart (SBO), LBO is unused for swizzled K-major layouts, descriptor version 1.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);   // start address, 16-byte units     bits [0,14)
+    d |= (uint64_t)1 << 16;                          // leading byte offset (ignored)    bits [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset = 1024 B      bits [32,46)
+    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)   bits [46,48)
+    d |= (uint64_t)2 << 61;                          // layout type: SWIZZLE_128B        bits [61,64)
+    return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M x N tile
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct GemmKernelArgs {
+    int M, N, K;
+    int epilogue;
+    const float* bias;
+    const float* gamma;
+    const int* row_map;
+    void* out;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, GemmKernelArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    // 128B-swizzled TMA / UMMA tiles need 1024-byte aligned bases
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* acc_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+    const int num_kb = g.K / BK;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w)) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(acc_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);     // slot free (first lap passes immediately)
+                mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + B_STAGE_BYTES);
+                tma_load_2d(smem_a + s * A_STAGE_BYTES, &tmap_a, &full_bar[s], kb * BK, m_tile * BM);
+                tma_load_2d(smem_b + s * B_STAGE_BYTES, &tmap_w, &full_bar[s], kb * BK, n_tile * BN);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(BM, BN);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + s * A_STAGE_BYTES));
+                const uint64_t b_desc = make_smem_desc(smem_u32(smem_b + s * B_STAGE_BYTES));
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    // advancing 16 bf16 (32 bytes) along K inside the swizzle atom = +2 in 16-byte units
+                    umma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                              (kb | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);            // frees the smem slot when these MMAs retire
+            }
+            umma_commit(acc_bar);                      // accumulator complete
+        }
+    } else {
+        // ===================== epilogue: TMEM -> registers -> HBM =====================
+        const int q = warp & 3;                        // TMEM lane quarter this warp may access
+        const int row_in_tile = q * 32 + lane;
+        const int m = m_tile * BM + row_in_tile;
+        mbar_wait(acc_bar, 0);
+        tc_fence_after();
+        int dst_row = m;
+        if (g.row_map != nullptr && m < g.M) dst_row = g.row_map[m];
+        const bool live = (m < g.M) && (dst_row >= 0);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+            if (!live) continue;
+            const int n0 = n_tile * BN + c * 32;
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            if (g.bias != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(g.bias + n0 + i);
+                    v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                }
+            }
+            if (g.epilogue == GEMM_EPI_BF16 || g.epilogue == GEMM_EPI_GELU_BF16) {
+                if (g.epilogue == GEMM_EPI_GELU_BF16) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+                }
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)dst_row * g.N + n0;
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    uint4 pk;
+                    pk.x = pack_bf16(v[i], v[i + 1]); pk.y = pack_bf16(v[i + 2], v[i + 3]);
+                    pk.z = pack_bf16(v[i + 4], v[i + 5]); pk.w = pack_bf16(v[i + 6], v[i + 7]);
+                    *reinterpret_cast<uint4*>(o + i) = pk;
+                }
+            } else if (g.epilogue == GEMM_EPI_RESADD_F32) {
+                float* o = reinterpret_cast<float*>(g.out) + (size_t)dst_row * g.N + n0;
+                if (g.gamma != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 g4 = *reinterpret_cast<const float4*>(g.gamma + n0 + i);
+                        v[i] *= g4.x; v[i + 1] *= g4.y; v[i + 2] *= g4.z; v[i + 3] *= g4.w;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    float4 x4 = *reinterpret_cast<float4*>(o + i);
+                    x4.x += v[i]; x4.y += v[i + 1]; x4.z += v[i + 2]; x4.w += v[i + 3];
+                    *reinterpret_cast<float4*>(o + i) = x4;
+                }
+            } else {
+                float* o = reinterpret_cast<float*>(g.out) + (size_t)dst_row * g.N + n0;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+        }
+    }
+    // ---- teardown: every role is done with TMEM before it is released ----
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+
+cudaError_t gemm_tc_configure() {
+    if (g_encode == nullptr) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess) return e;
+        if (qres != cudaDriverEntryPointSuccess || fn == nullptr) return cudaErrorNotSupported;
+        g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    }
+    return cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+}
+
+// 2-D bf16 row-major [rows][cols] tensor, box = [box_rows][64 cols], 128-byte swizzle, zero OOB fill
+static bool make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+cudaError_t gemm_tc_launch(const GemmParams& p, cudaStream_t s) {
+    if (g_encode == nullptr) return cudaErrorNotReady;
+    if (p.M < 1 || p.N % BN != 0 || p.K % BK != 0 || p.K < BK) return cudaErrorInvalidValue;
+    if ((reinterpret_cast<uintptr_t>(p.A) & 15) || (reinterpret_cast<uintptr_t>(p.W) & 15)) return cudaErrorInvalidValue;
+    CUtensorMap ma, mw;
+    if (!make_map(&ma, p.A, (uint64_t)p.M, (uint64_t)p.K, BM)) return cudaErrorInvalidValue;
+    if (!make_map(&mw, p.W, (uint64_t)p.N, (uint64_t)p.K, BN)) return cudaErrorInvalidValue;
+    GemmKernelArgs g{p.M, p.N, p.K, p.epilogue, p.bias, p.gamma, p.row_map, p.out};
+    dim3 grid(p.N / BN, (p.M + BM - 1) / BM);
+    gemm_tc_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, s>>>(ma, mw, g);
+    return cudaGetLastError();
+}
+
+// ---- stand-alone test entry (include/molnextr_b200.h: mnx_test_gemm_bf16) ---------------------
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __bfloat162float(in[i]);
+}
+
+}  // namespace mnx
+
+extern "C" int mnx_test_gemm_bf16(const float* A, const float* W, const float* bias, float* C, int32_t M, int32_t N,
+                                  int32_t K, int32_t epilogue, void* cuda_stream) {
+    using namespace mnx;
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    if (gemm_tc_configure() != cudaSuccess) return -2;
+    __nv_bfloat16 *a = nullptr, *w = nullptr, *o = nullptr;
+    const size_t na = (size_t)M * K, nw = (size_t)N * K, nc = (size_t)M * N;
+    if (cudaMalloc(&a, na * 2) != cudaSuccess || cudaMalloc(&w, nw * 2) != cudaSuccess || cudaMalloc(&o, nc * 2) != cudaSuccess) return -2;
+    f32_to_bf16_kernel<<<(unsigned)((na + 255) / 256), 256, 0, s>>>(A, a, na);
+    f32_to_bf16_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, s>>>(W, w, nw);
+    GemmParams p{};
+    p.A = a; p.W = w; p.M = M; p.N = N; p.K = K; p.epilogue = epilogue; p.bias = bias;
+    const bool bf16_out = (epilogue == GEMM_EPI_BF16 || epilogue == GEMM_EPI_GELU_BF16);
+    p.out = bf16_out ? (void*)o : (void*)C;
+    cudaError_t e = gemm_tc_launch(p, s);
+    if (e == cudaSuccess && bf16_out) bf16_to_f32_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, s>>>(o, C, nc);
+    cudaError_t e2 = cudaStreamSynchronize(s);
+    cudaFree(a); cudaFree(w); cudaFree(o);
+    if (e != cudaSuccess) return e == cudaErrorInvalidValue ? -1 : -2;
+    return e2 == cudaSuccess ? 0 : -2;
+}

@@ -1,0 +1,34 @@
+// tcgen05 / TMEM / TMA GEMM used by both encoders (every Linear of Swin-B and every 1x1 /
+// patchify convolution of ConvNeXt-B):   D[M][N] = A[M][K](bf16) * W[N][K]^T(bf16), fp32 accumulate,
+// with the consumer's elementwise work fused into the epilogue.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace mnx {
+
+enum GemmEpilogue {
+    GEMM_EPI_BF16 = 0,        // out_bf16[m][n] = acc + bias[n]
+    GEMM_EPI_GELU_BF16 = 1,   // out_bf16[m][n] = gelu_erf(acc + bias[n])
+    GEMM_EPI_RESADD_F32 = 2,  // resid[row_map ? row_map[m] : m][n] += (gamma ? gamma[n] : 1) * (acc + bias[n])
+    GEMM_EPI_F32 = 3,         // out_f32[m][n] = acc + (bias ? bias[n] : 0)
+};
+
+struct GemmParams {
+    const __nv_bfloat16* A;   // [M][K] row-major (K contiguous)
+    const __nv_bfloat16* W;   // [N][K] row-major (torch Linear layout)
+    int M, N, K;              // N % 128 == 0, K % 64 == 0
+    int epilogue;
+    const float* bias;        // [N] or nullptr (GEMM_EPI_F32 only)
+    const float* gamma;       // [N] or nullptr
+    const int* row_map;       // [M] destination row (or -1 = drop) or nullptr
+    void* out;                // bf16 [M][N] / fp32 [M][N] / fp32 residual stream [*][N]
+};
+
+// Launches the kernel on `s`.  Returns cudaErrorInvalidValue for unsupported shapes.
+cudaError_t gemm_tc_launch(const GemmParams& p, cudaStream_t s);
+// one-time per-device setup (driver entry point for tensor maps, smem opt-in)
+cudaError_t gemm_tc_configure();
+
+}  // namespace mnx

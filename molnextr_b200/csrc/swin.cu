@@ -1,10 +1,570 @@
-// placeholder until the Swin-B kernels land (replaced in the next commit)
+// Swin-B encoder (patch4 / window12 / dims 128-256-512-1024 / depths 2-2-18-2 / heads 4-8-16-32)
+// on sm_100a -- the encoder the reference actually executes (MolNexTR/models/transformers.py:
+// PatchEmbed :405-419, SwinTransformerBlock :245-292, WindowAttention :147-178, PatchMerging
+// :310-336, Vision_Transformer.forward :504-515).
+//
+// Data layout: the residual stream x is fp32 [B*H*W][C] (token-major, NHWC); every Linear runs on
+// the tcgen05 GEMM (gemm_tc.cu) with bf16 operands that the LayerNorm kernels emit directly in the
+// order the GEMM wants (window-partitioned and cyclically shifted for attention), so the
+// reference's pad / roll / window_partition / permute / contiguous copies never materialise;
+// window_reverse + un-roll + crop + residual add happen in the proj GEMM's epilogue via a row map.
+#include <cuda_bf16.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
 #include "encoder.cuh"
+#include "gemm_tc.cuh"
+
 namespace mnx {
-struct SwinState { int dummy; };
-int swin_finalize(mnx_engine* e, SwinState**, const mnx_config&) { mnx_set_error(e, "swin encoder not built yet"); return MNX_ERR_INVALID; }
-int swin_forward(mnx_engine* e, SwinState*, const float*, int, int, int, float*, cudaStream_t, int*) { mnx_set_error(e, "swin encoder not built yet"); return MNX_ERR_INVALID; }
-int swin_time_kernel(mnx_engine* e, SwinState*, int, int, float*, cudaStream_t) { mnx_set_error(e, "swin encoder not built yet"); return MNX_ERR_INVALID; }
-void swin_destroy(SwinState*) {}
+
+static constexpr int WS = 12, WIN = 144;
+static const int SW_DEPTH[4] = {2, 2, 18, 2};
+static const int SW_HEADS[4] = {4, 8, 16, 32};
+
+struct SwinBlockW {
+    const float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+    const __nv_bfloat16 *qkv_w, *proj_w, *fc1_w, *fc2_w;
+    const float *qkv_b, *proj_b, *fc1_b, *fc2_b;
+    const float* rpb_t;   // [nH][529] relative position bias table, head-major
+};
+struct SwinMergeW {
+    const float *ln_w, *ln_b;
+    const __nv_bfloat16* red_w;   // [2C][4C]
+};
+
+struct SwinState {
+    const float *pe_w, *pe_b, *pe_ln_w, *pe_ln_b;   // patch embed: [128][48], [128]
+    std::vector<SwinBlockW> blocks[4];
+    SwinMergeW merge[3];
+    const float *norm_w, *norm_b;
+    // workspaces
+    float *x0 = nullptr, *x1 = nullptr;             // residual stream ping-pong (merging switches)
+    __nv_bfloat16 *abuf = nullptr, *qkv = nullptr, *attn = nullptr, *hbuf = nullptr;
+    int* row_map = nullptr;                          // [2][max Mw]
+    size_t max_tokens = 0;
+    int last_B = 0, last_H = 0, last_W = 0;
+};
+
+// ------------------------------------------------------------------------------------------
+// patch embed: conv 4x4 stride 4 (3 -> 128) + LayerNorm(128, eps 1e-5); 8 tokens per CTA
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) patch_embed_kernel(const float* __restrict__ img, int B, int H, int W, int Hp,
+                                                          int Wp, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, const float* __restrict__ ln_w,
+                                                          const float* __restrict__ ln_b, float eps,
+                                                          float* __restrict__ x) {
+    __shared__ float patch[8][48];
+    __shared__ float red[8][4][2];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long tok0 = (long long)blockIdx.x * 8;
+    const long long ntok = (long long)B * Hp * Wp;
+    float wr[48];
+#pragma unroll
+    for (int k = 0; k < 48; ++k) wr[k] = w[tid * 48 + k];
+    for (int i = tid; i < 8 * 48; i += 128) {
+        const int t = i / 48, k = i % 48;
+        const long long tok = tok0 + t;
+        float v = 0.f;
+        if (tok < ntok) {
+            const int b = (int)(tok / ((long long)Hp * Wp));
+            const int r = (int)(tok % ((long long)Hp * Wp));
+            const int py = r / Wp, px = r % Wp;
+            const int c = k >> 4, dy = (k >> 2) & 3, dx = k & 3;
+            const int yy = py * 4 + dy, xx = px * 4 + dx;
+            if (yy < H && xx < W) v = img[(((size_t)b * 3 + c) * H + yy) * W + xx];
+        }
+        patch[t][k] = v;
+    }
+    __syncthreads();
+    float acc[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        float a = bias[tid];
+#pragma unroll
+        for (int k = 0; k < 48; ++k) a = fmaf(patch[t][k], wr[k], a);
+        acc[t] = a;
+    }
+    // LayerNorm over the 128 channels of each token (two-pass)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const float s = warp_sum(acc[t]);
+        if (lane == 0) red[t][wid][0] = s;
+    }
+    __syncthreads();
+    float mean[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) mean[t] = ((red[t][0][0] + red[t][1][0]) + (red[t][2][0] + red[t][3][0])) * (1.0f / 128.0f);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const float d = acc[t] - mean[t];
+        const float s = warp_sum(d * d);
+        if (lane == 0) red[t][wid][1] = s;
+    }
+    __syncthreads();
+    const float g = ln_w[tid], be = ln_b[tid];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const float var = ((red[t][0][1] + red[t][1][1]) + (red[t][2][1] + red[t][3][1])) * (1.0f / 128.0f);
+        const float rstd = 1.0f / sqrtf(var + eps);
+        if (tok0 + t < ntok) x[(size_t)(tok0 + t) * 128 + tid] = (acc[t] - mean[t]) * rstd * g + be;
+    }
 }
-extern "C" int mnx_test_gemm_bf16(const float*, const float*, const float*, float*, int32_t, int32_t, int32_t, int32_t, void*) { return MNX_ERR_INVALID; }
+
+// ------------------------------------------------------------------------------------------
+// row map of one attention block: window-order row -> token row of x (or -1 for a padded position)
+// window order = (b, wh, ww, ph, pw) over the padded, cyclically shifted map (transformers.py:252-266)
+// ------------------------------------------------------------------------------------------
+__global__ void swin_row_map_kernel(int B, int H, int W, int Hp, int Wp, int shift, int* __restrict__ map) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)B * Hp * Wp;
+    if (idx >= total) return;
+    const int nww = Wp / WS;
+    const int pos = (int)(idx % WIN);
+    const long long win = idx / WIN;
+    const int nwin = (Hp / WS) * nww;
+    const int b = (int)(win / nwin), wi = (int)(win % nwin);
+    const int wh = wi / nww, ww = wi % nww;
+    const int hs = wh * WS + pos / WS, wsx = ww * WS + pos % WS;
+    const int hp = (hs + shift) % Hp, wp = (wsx + shift) % Wp;
+    map[idx] = (hp < H && wp < W) ? (int)(((long long)b * H + hp) * W + wp) : -1;
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm of C-wide rows -> bf16 (GEMM A operand) or fp32; one warp per output row, optional
+// gather through a row map (-1 -> zeros: the reference pads AFTER norm1).
+// ------------------------------------------------------------------------------------------
+template <bool OUT_BF16>
+__global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ x, const int* __restrict__ map,
+                                                      long long rows, int C, const float* __restrict__ w,
+                                                      const float* __restrict__ b, float eps, void* __restrict__ out) {
+    const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const long long src = map ? (long long)map[r] : r;
+    const int n4 = C >> 2;
+    if (src < 0) {
+        if (OUT_BF16) {
+            uint2* o = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + (size_t)r * C);
+            for (int i = lane; i < n4; i += 32) o[i] = make_uint2(0u, 0u);
+        } else {
+            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (size_t)r * C);
+            for (int i = lane; i < n4; i += 32) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        return;
+    }
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)src * C);
+    float s = 0.f;
+    for (int i = lane; i < n4; i += 32) { const float4 v = xr[i]; s += (v.x + v.y) + (v.z + v.w); }
+    const float mean = warp_sum(s) / (float)C;
+    float sq = 0.f;
+    for (int i = lane; i < n4; i += 32) {
+        const float4 v = xr[i];
+        const float a = v.x - mean, bb = v.y - mean, c = v.z - mean, d = v.w - mean;
+        sq += (a * a + bb * bb) + (c * c + d * d);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)C + eps);
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+    for (int i = lane; i < n4; i += 32) {
+        const float4 v = xr[i], g = w4[i], be = b4[i];
+        const float y0 = (v.x - mean) * rstd * g.x + be.x, y1 = (v.y - mean) * rstd * g.y + be.y;
+        const float y2 = (v.z - mean) * rstd * g.z + be.z, y3 = (v.w - mean) * rstd * g.w + be.w;
+        if (OUT_BF16) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(y0, y1), hi = __floats2bfloat162_rn(y2, y3);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + (size_t)r * C)[i] = pk;
+        } else {
+            reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (size_t)r * C)[i] = make_float4(y0, y1, y2, y3);
+        }
+    }
+}
+
+// PatchMerging gather + LayerNorm(4C): out row (b,h2,w2) = LN(cat[x(2h2,2w2), x(2h2+1,2w2), x(2h2,2w2+1),
+// x(2h2+1,2w2+1)]) with zero padding of odd maps (transformers.py:318-333); one warp per output row.
+__global__ void __launch_bounds__(256) merge_ln_kernel(const float* __restrict__ x, int B, int H, int W, int C,
+                                                       const float* __restrict__ w, const float* __restrict__ b,
+                                                       float eps, __nv_bfloat16* __restrict__ out) {
+    const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
+    const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= (long long)B * H2 * W2) return;
+    const int lane = threadIdx.x & 31;
+    const int bb = (int)(r / ((long long)H2 * W2));
+    const int rem = (int)(r % ((long long)H2 * W2));
+    const int h2 = rem / W2, w2 = rem % W2;
+    const int n4 = C >> 2;
+    const float4* src[4];
+    const int dh[4] = {0, 1, 0, 1}, dw[4] = {0, 0, 1, 1};
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int hh = 2 * h2 + dh[p], ww = 2 * w2 + dw[p];
+        src[p] = (hh < H && ww < W) ? reinterpret_cast<const float4*>(x + (((size_t)bb * H + hh) * W + ww) * C) : nullptr;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+        if (src[p]) for (int i = lane; i < n4; i += 32) { const float4 v = src[p][i]; s += (v.x + v.y) + (v.z + v.w); }
+    const float inv = 1.0f / (float)(4 * C);
+    const float mean = warp_sum(s) * inv;
+    float sq = 0.f;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        for (int i = lane; i < n4; i += 32) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (src[p]) v = src[p][i];
+            const float a = v.x - mean, b2 = v.y - mean, c = v.z - mean, d = v.w - mean;
+            sq += (a * a + b2 * b2) + (c * c + d * d);
+        }
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(sq) * inv + eps);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const float4* w4 = reinterpret_cast<const float4*>(w + p * C);
+        const float4* b4 = reinterpret_cast<const float4*>(b + p * C);
+        uint2* o = reinterpret_cast<uint2*>(out + (size_t)r * 4 * C + p * C);
+        for (int i = lane; i < n4; i += 32) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (src[p]) v = src[p][i];
+            const float4 g = w4[i], be = b4[i];
+            __nv_bfloat162 lo = __floats2bfloat162_rn((v.x - mean) * rstd * g.x + be.x, (v.y - mean) * rstd * g.y + be.y);
+            __nv_bfloat162 hi = __floats2bfloat162_rn((v.z - mean) * rstd * g.z + be.z, (v.w - mean) * rstd * g.w + be.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            o[i] = pk;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// window attention: one CTA per (window, head); 9 warps x 16 query rows; QK^T and PV on
+// mma.sync m16n8k16 (bf16 in, fp32 accumulate); bias-table gather, shift mask (-100) and softmax
+// in fp32 registers.  144 x 144 x 32 per tile is too small to amortise a tcgen05/TMEM round trip.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(288) window_attn_kernel(const __nv_bfloat16* __restrict__ qkv, int C, int nH,
+                                                          const float* __restrict__ rpb_t, int Hp, int Wp, int shift,
+                                                          __nv_bfloat16* __restrict__ out) {
+    __shared__ __align__(16) __nv_bfloat16 Ks[WIN][40];       // [key][dim], row stride 80 B
+    __shared__ __align__(16) __nv_bfloat16 Vt[32][WIN + 8];   // [dim][key]
+    __shared__ float tab[529];
+    __shared__ uint8_t region[WIN];
+    const int win = blockIdx.x, h = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t row0 = (size_t)win * WIN;
+    const int ld = 3 * C;
+    // stage K, V^T, bias table, mask regions
+    for (int i = tid; i < WIN * 4; i += 288) {
+        const int key = i >> 2, c8 = i & 3;
+        const uint4 kv = *reinterpret_cast<const uint4*>(qkv + (row0 + key) * ld + C + h * 32 + c8 * 8);
+        *reinterpret_cast<uint4*>(&Ks[key][c8 * 8]) = kv;
+        const uint4 vv = *reinterpret_cast<const uint4*>(qkv + (row0 + key) * ld + 2 * C + h * 32 + c8 * 8);
+        const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) Vt[c8 * 8 + e][key] = ve[e];
+    }
+    for (int i = tid; i < 529; i += 288) tab[i] = rpb_t[h * 529 + i];
+    if (tid < WIN) {
+        int reg = 0;
+        if (shift > 0) {
+            const int nww = Wp / WS;
+            const int wi = win % ((Hp / WS) * nww);
+            const int hs = (wi / nww) * WS + tid / WS, wsx = (wi % nww) * WS + tid % WS;
+            const int hid = hs < Hp - WS ? 0 : (hs < Hp - shift ? 1 : 2);
+            const int wid = wsx < Wp - WS ? 0 : (wsx < Wp - shift ? 1 : 2);
+            reg = hid * 3 + wid;
+        }
+        region[tid] = (uint8_t)reg;
+    }
+    __syncthreads();
+
+    const int qr = lane >> 2, qc = (lane & 3) * 2;
+    const int i0 = warp * 16 + qr, i1 = i0 + 8;             // the two query rows this thread owns
+    // Q fragments (2 k-steps of 16 dims)
+    uint32_t qa[2][4];
+    {
+        const __nv_bfloat16* q0 = qkv + (row0 + i0) * ld + h * 32;
+        const __nv_bfloat16* q1 = qkv + (row0 + i1) * ld + h * 32;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            qa[ks][0] = *reinterpret_cast<const uint32_t*>(q0 + ks * 16 + qc);
+            qa[ks][1] = *reinterpret_cast<const uint32_t*>(q1 + ks * 16 + qc);
+            qa[ks][2] = *reinterpret_cast<const uint32_t*>(q0 + ks * 16 + qc + 8);
+            qa[ks][3] = *reinterpret_cast<const uint32_t*>(q1 + ks * 16 + qc + 8);
+        }
+    }
+    float s[18][4];
+#pragma unroll
+    for (int nt = 0; nt < 18; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Ks[nt * 8 + qr][ks * 16 + qc]);
+            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Ks[nt * 8 + qr][ks * 16 + qc + 8]);
+            mma_bf16_16816(s[nt], qa[ks], b0, b1);
+        }
+    }
+    // scale, relative position bias, shift mask, softmax (fp32)
+    const float scale = 0.17677669529663687f;   // 32 ** -0.5
+    const int yi0 = i0 / WS, xi0 = i0 % WS, yi1 = i1 / WS, xi1 = i1 % WS;
+    const int r0 = region[i0], r1 = region[i1];
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 18; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int j = nt * 8 + qc + e;
+            const int yj = j / WS, xj = j % WS;
+            const int rj = region[j];
+            float v0 = s[nt][e] * scale + tab[(yi0 - yj + WS - 1) * (2 * WS - 1) + (xi0 - xj + WS - 1)];
+            float v1 = s[nt][2 + e] * scale + tab[(yi1 - yj + WS - 1) * (2 * WS - 1) + (xi1 - xj + WS - 1)];
+            if (rj != r0) v0 += -100.0f;
+            if (rj != r1) v1 += -100.0f;
+            s[nt][e] = v0;
+            s[nt][2 + e] = v1;
+            m0 = fmaxf(m0, v0);
+            m1 = fmaxf(m1, v1);
+        }
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 18; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const float p0 = expf(s[nt][e] - m0), p1 = expf(s[nt][2 + e] - m1);
+            s[nt][e] = p0; s[nt][2 + e] = p1;
+            l0 += p0; l1 += p1;
+        }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+    // O = P V : 9 k-steps of 16 keys, 4 n-tiles of 8 dims
+    float o[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 9; ++kk) {
+        uint32_t pa[4];
+        {
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(s[2 * kk][0] * inv0, s[2 * kk][1] * inv0);
+            __nv_bfloat162 t1 = __floats2bfloat162_rn(s[2 * kk][2] * inv1, s[2 * kk][3] * inv1);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(s[2 * kk + 1][0] * inv0, s[2 * kk + 1][1] * inv0);
+            __nv_bfloat162 t3 = __floats2bfloat162_rn(s[2 * kk + 1][2] * inv1, s[2 * kk + 1][3] * inv1);
+            pa[0] = *reinterpret_cast<uint32_t*>(&t0); pa[1] = *reinterpret_cast<uint32_t*>(&t1);
+            pa[2] = *reinterpret_cast<uint32_t*>(&t2); pa[3] = *reinterpret_cast<uint32_t*>(&t3);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Vt[nt * 8 + qr][kk * 16 + qc]);
+            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Vt[nt * 8 + qr][kk * 16 + qc + 8]);
+            mma_bf16_16816(o[nt], pa, b0, b1);
+        }
+    }
+    __nv_bfloat16* o0 = out + (row0 + i0) * C + h * 32;
+    __nv_bfloat16* o1 = out + (row0 + i1) * C + h * 32;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(o[nt][0], o[nt][1]);
+        __nv_bfloat162 b = __floats2bfloat162_rn(o[nt][2], o[nt][3]);
+        *reinterpret_cast<__nv_bfloat162*>(o0 + nt * 8 + qc) = a;
+        *reinterpret_cast<__nv_bfloat162*>(o1 + nt * 8 + qc) = b;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static std::vector<__nv_bfloat16> to_bf16(const std::vector<float>& v) {
+    std::vector<__nv_bfloat16> o(v.size());
+    for (size_t i = 0; i < v.size(); ++i) o[i] = __float2bfloat16_rn(v[i]);
+    return o;
+}
+
+#define SW_CUDA(e, x)                                                                                     \
+    do {                                                                                                  \
+        cudaError_t _c = (x);                                                                             \
+        if (_c != cudaSuccess) {                                                                          \
+            std::string m = std::string(#x) + " failed: " + cudaGetErrorString(_c);                       \
+            mnx_set_error(e, m.c_str());                                                                  \
+            return MNX_ERR_CUDA;                                                                          \
+        }                                                                                                 \
+    } while (0)
+
+static int up_f32(mnx_engine* e, const std::string& key, std::initializer_list<int64_t> shape, const float** out) {
+    const std::vector<float>* v = mnx_need(e, key, shape);
+    if (!v) return MNX_ERR_WEIGHTS;
+    SW_CUDA(e, mnx_upload(e, *v, out));
+    return MNX_OK;
+}
+static int up_bf16(mnx_engine* e, const std::string& key, std::initializer_list<int64_t> shape, const __nv_bfloat16** out) {
+    const std::vector<float>* v = mnx_need(e, key, shape);
+    if (!v) return MNX_ERR_WEIGHTS;
+    std::vector<__nv_bfloat16> h = to_bf16(*v);
+    void* d = nullptr;
+    SW_CUDA(e, mnx_upload_raw(e, h.data(), h.size() * sizeof(__nv_bfloat16), &d));
+    *out = reinterpret_cast<const __nv_bfloat16*>(d);
+    return MNX_OK;
+}
+#define SW_TRY(x) do { int _r = (x); if (_r != MNX_OK) return _r; } while (0)
+
+int swin_finalize(mnx_engine* e, SwinState** out, const mnx_config& cfg) {
+    SW_CUDA(e, gemm_tc_configure());
+    SwinState* st = new SwinState();
+    *out = st;
+    const std::string P = "encoder.transformer.";
+    SW_TRY(up_f32(e, P + "patch_embed.proj.weight", {128, 3, 4, 4}, &st->pe_w));
+    SW_TRY(up_f32(e, P + "patch_embed.proj.bias", {128}, &st->pe_b));
+    SW_TRY(up_f32(e, P + "patch_embed.norm.weight", {128}, &st->pe_ln_w));
+    SW_TRY(up_f32(e, P + "patch_embed.norm.bias", {128}, &st->pe_ln_b));
+    // the index buffer is recomputed on the fly in the attention kernel; verify the checkpoint agrees
+    std::vector<int64_t> ref_idx(WIN * WIN);
+    for (int i = 0; i < WIN; ++i)
+        for (int j = 0; j < WIN; ++j)
+            ref_idx[i * WIN + j] = (i / WS - j / WS + WS - 1) * (2 * WS - 1) + (i % WS - j % WS + WS - 1);
+    for (int s = 0; s < 4; ++s) {
+        const int64_t C = 128 << s, nH = SW_HEADS[s];
+        st->blocks[s].resize(SW_DEPTH[s]);
+        for (int j = 0; j < SW_DEPTH[s]; ++j) {
+            const std::string B = P + "layers." + std::to_string(s) + ".blocks." + std::to_string(j) + ".";
+            SwinBlockW& w = st->blocks[s][j];
+            SW_TRY(up_f32(e, B + "norm1.weight", {C}, &w.ln1_w));
+            SW_TRY(up_f32(e, B + "norm1.bias", {C}, &w.ln1_b));
+            SW_TRY(up_f32(e, B + "norm2.weight", {C}, &w.ln2_w));
+            SW_TRY(up_f32(e, B + "norm2.bias", {C}, &w.ln2_b));
+            SW_TRY(up_bf16(e, B + "attn.qkv.weight", {3 * C, C}, &w.qkv_w));
+            SW_TRY(up_f32(e, B + "attn.qkv.bias", {3 * C}, &w.qkv_b));
+            SW_TRY(up_bf16(e, B + "attn.proj.weight", {C, C}, &w.proj_w));
+            SW_TRY(up_f32(e, B + "attn.proj.bias", {C}, &w.proj_b));
+            SW_TRY(up_bf16(e, B + "mlp.fc1.weight", {4 * C, C}, &w.fc1_w));
+            SW_TRY(up_f32(e, B + "mlp.fc1.bias", {4 * C}, &w.fc1_b));
+            SW_TRY(up_bf16(e, B + "mlp.fc2.weight", {C, 4 * C}, &w.fc2_w));
+            SW_TRY(up_f32(e, B + "mlp.fc2.bias", {C}, &w.fc2_b));
+            const std::vector<float>* tab = mnx_need(e, B + "attn.relative_position_bias_table", {529, nH});
+            if (!tab) return MNX_ERR_WEIGHTS;
+            std::vector<float> tt((size_t)nH * 529);
+            for (int i = 0; i < 529; ++i)
+                for (int hh = 0; hh < nH; ++hh) tt[(size_t)hh * 529 + i] = (*tab)[(size_t)i * nH + hh];
+            SW_CUDA(e, mnx_upload(e, tt, &w.rpb_t));
+            const std::vector<int64_t>* idx = mnx_need_i64(e, B + "attn.relative_position_index", {WIN, WIN});
+            if (!idx) return MNX_ERR_WEIGHTS;
+            if (*idx != ref_idx) {
+                mnx_set_error(e, (B + "attn.relative_position_index differs from the window-12 table the kernels assume").c_str());
+                return MNX_ERR_WEIGHTS;
+            }
+        }
+        if (s < 3) {
+            const std::string D = P + "layers." + std::to_string(s) + ".downsample.";
+            SW_TRY(up_f32(e, D + "norm.weight", {4 * C}, &st->merge[s].ln_w));
+            SW_TRY(up_f32(e, D + "norm.bias", {4 * C}, &st->merge[s].ln_b));
+            SW_TRY(up_bf16(e, D + "reduction.weight", {2 * C, 4 * C}, &st->merge[s].red_w));
+        }
+    }
+    SW_TRY(up_f32(e, P + "norm.weight", {1024}, &st->norm_w));
+    SW_TRY(up_f32(e, P + "norm.bias", {1024}, &st->norm_b));
+    // workspaces for the largest request: stage-0 map padded to window multiples
+    const size_t Hq = (cfg.max_height + 3) / 4, Wq = (cfg.max_width + 3) / 4;
+    const size_t Hp = (Hq + WS - 1) / WS * WS, Wp = (Wq + WS - 1) / WS * WS;
+    const size_t tok = (size_t)cfg.max_batch * Hp * Wp;      // >= tokens (and padded tokens) of every stage
+    st->max_tokens = tok;
+    void* p = nullptr;
+    SW_CUDA(e, mnx_dev_alloc_bytes(e, &p, tok * 128 * sizeof(float))); st->x0 = (float*)p;
+    SW_CUDA(e, mnx_dev_alloc_bytes(e, &p, tok * 128 * sizeof(float) / 2 + 1024)); st->x1 = (float*)p;
+    SW_CUDA(e, mnx_dev_alloc_bytes(e, &p, tok * 128 * 2)); st->abuf = (__nv_bfloat16*)p;
+    SW_CUDA(e, mnx_dev_alloc_bytes(e, &p, tok * 384 * 2)); st->qkv = (__nv_bfloat16*)p;
+    SW_CUDA(e, mnx_dev_alloc_bytes(e, &p, tok * 128 * 2)); st->attn = (__nv_bfloat16*)p;
+    SW_CUDA(e, mnx_dev_alloc_bytes(e, &p, tok * 512 * 2)); st->hbuf = (__nv_bfloat16*)p;
+    SW_CUDA(e, mnx_dev_alloc_bytes(e, &p, tok * sizeof(int))); st->row_map = (int*)p;
+    return MNX_OK;
+}
+
+void swin_destroy(SwinState* st) { delete st; }
+
+static cudaError_t gemm(const __nv_bfloat16* A, const __nv_bfloat16* W, long long M, int N, int K, int epi,
+                        const float* bias, const int* row_map, void* out, cudaStream_t s) {
+    GemmParams p{};
+    p.A = A; p.W = W; p.M = (int)M; p.N = N; p.K = K; p.epilogue = epi; p.bias = bias; p.row_map = row_map; p.out = out;
+    return gemm_tc_launch(p, s);
+}
+
+int swin_forward(mnx_engine* e, SwinState* st, const float* images, int B, int H, int W, float* features,
+                 cudaStream_t s, int* launches) {
+    int nl = 0;
+    int Hc = (H + 3) / 4, Wc = (W + 3) / 4;
+    {
+        const long long ntok = (long long)B * Hc * Wc;
+        patch_embed_kernel<<<(unsigned)((ntok + 7) / 8), 128, 0, s>>>(images, B, H, W, Hc, Wc, st->pe_w, st->pe_b,
+                                                                      st->pe_ln_w, st->pe_ln_b, 1e-5f, st->x0);
+        SW_CUDA(e, cudaGetLastError()); ++nl;
+    }
+    float* x = st->x0;
+    float* x_other = st->x1;
+    for (int stage = 0; stage < 4; ++stage) {
+        const int C = 128 << stage, nH = SW_HEADS[stage];
+        const int Hp = (Hc + WS - 1) / WS * WS, Wp = (Wc + WS - 1) / WS * WS;
+        const long long M = (long long)B * Hc * Wc, Mw = (long long)B * Hp * Wp;
+        if ((size_t)Mw * C > st->max_tokens * 128) {
+            mnx_set_error(e, "swin workspace too small for this request");
+            return MNX_ERR_CAPACITY;
+        }
+        // one map live at a time; it is recomputed when the shift changes (one cheap launch)
+        int* map0 = st->row_map;
+        int cur_shift = -1;
+        for (int j = 0; j < SW_DEPTH[stage]; ++j) {
+            const SwinBlockW& w = st->blocks[stage][j];
+            const int shift = (j % 2 == 0) ? 0 : WS / 2;
+            if (shift != cur_shift) {
+                swin_row_map_kernel<<<(unsigned)((Mw + 255) / 256), 256, 0, s>>>(B, Hc, Wc, Hp, Wp, shift, map0);
+                SW_CUDA(e, cudaGetLastError()); ++nl;
+                cur_shift = shift;
+            }
+            // norm1 -> (pad, roll, window partition) -> bf16
+            ln_rows_kernel<true><<<(unsigned)((Mw + 7) / 8), 256, 0, s>>>(x, map0, Mw, C, w.ln1_w, w.ln1_b, 1e-5f, st->abuf);
+            SW_CUDA(e, cudaGetLastError()); ++nl;
+            SW_CUDA(e, gemm(st->abuf, w.qkv_w, Mw, 3 * C, C, GEMM_EPI_BF16, w.qkv_b, nullptr, st->qkv, s)); ++nl;
+            window_attn_kernel<<<dim3((unsigned)(Mw / WIN), nH), 288, 0, s>>>(st->qkv, C, nH, w.rpb_t, Hp, Wp, shift, st->attn);
+            SW_CUDA(e, cudaGetLastError()); ++nl;
+            // proj + window_reverse + un-roll + crop + residual
+            SW_CUDA(e, gemm(st->attn, w.proj_w, Mw, C, C, GEMM_EPI_RESADD_F32, w.proj_b, map0, x, s)); ++nl;
+            // norm2 -> fc1 (GELU) -> fc2 + residual
+            ln_rows_kernel<true><<<(unsigned)((M + 7) / 8), 256, 0, s>>>(x, nullptr, M, C, w.ln2_w, w.ln2_b, 1e-5f, st->abuf);
+            SW_CUDA(e, cudaGetLastError()); ++nl;
+            SW_CUDA(e, gemm(st->abuf, w.fc1_w, M, 4 * C, C, GEMM_EPI_GELU_BF16, w.fc1_b, nullptr, st->hbuf, s)); ++nl;
+            SW_CUDA(e, gemm(st->hbuf, w.fc2_w, M, C, 4 * C, GEMM_EPI_RESADD_F32, w.fc2_b, nullptr, x, s)); ++nl;
+        }
+        if (stage < 3) {
+            const int H2 = (Hc + 1) / 2, W2 = (Wc + 1) / 2;
+            const long long M2 = (long long)B * H2 * W2;
+            merge_ln_kernel<<<(unsigned)((M2 + 7) / 8), 256, 0, s>>>(x, B, Hc, Wc, C, st->merge[stage].ln_w,
+                                                                    st->merge[stage].ln_b, 1e-5f, st->abuf);
+            SW_CUDA(e, cudaGetLastError()); ++nl;
+            SW_CUDA(e, gemm(st->abuf, st->merge[stage].red_w, M2, 2 * C, 4 * C, GEMM_EPI_F32, nullptr, nullptr, x_other, s)); ++nl;
+            float* t = x; x = x_other; x_other = t;
+            Hc = H2; Wc = W2;
+        }
+    }
+    const long long M = (long long)B * Hc * Wc;
+    ln_rows_kernel<false><<<(unsigned)((M + 7) / 8), 256, 0, s>>>(x, nullptr, M, 1024, st->norm_w, st->norm_b, 1e-5f, features);
+    SW_CUDA(e, cudaGetLastError()); ++nl;
+    st->last_B = B; st->last_H = H; st->last_W = W;
+    *launches += nl;
+    return MNX_OK;
+}
+
+int swin_time_kernel(mnx_engine* e, SwinState*, int, int, float*, cudaStream_t) {
+    mnx_set_error(e, "swin kernel timing ids are not wired up yet");
+    return MNX_ERR_INVALID;
+}
+
+}  // namespace mnx
