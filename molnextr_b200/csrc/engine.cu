@@ -16,6 +16,7 @@
 
 #include "decoder.cuh"
 #include "encoder.cuh"
+#include "mega.cuh"
 
 namespace mnx {
 // decoder.cu
@@ -66,6 +67,12 @@ struct mnx_engine {
     float *selfK = nullptr, *selfV = nullptr, *crossK = nullptr, *crossV = nullptr, *membank = nullptr;
     int *ids = nullptr, *lens = nullptr;
     float *logp = nullptr, *hidden = nullptr;
+    // persistent cluster decode kernel (mega.cu)
+    const float *wpack = nullptr, *ppack = nullptr, *finalp = nullptr;
+    unsigned int* row_state = nullptr;
+    int* steps_run_dev = nullptr;
+    int max_clusters = 0;
+    int decode_path = 0;   // 0 auto, 1 force multi-kernel graph path, 2 force cluster kernel
     // bond head
     float *hg = nullptr, *AB = nullptr, *prob = nullptr;
     // predict-path staging
@@ -172,6 +179,11 @@ extern "C" int mnx_create(const mnx_config* cfg, mnx_engine** out) {
     }
     cudaError_t c = cudaSetDevice(cfg->device);
     if (c == cudaSuccess) c = dec_configure();
+    if (c == cudaSuccess) c = mega_configure(&e->max_clusters);
+    if (const char* env = getenv("MNX_DECODE_PATH")) {
+        if (!strcmp(env, "graph")) e->decode_path = 1;
+        else if (!strcmp(env, "cluster")) e->decode_path = 2;
+    }
     if (c == cudaSuccess) c = cudaMallocHost(&e->h_done, sizeof(int));
     if (c == cudaSuccess) c = cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking);
     if (c != cudaSuccess) {
@@ -259,6 +271,15 @@ static int finalize_decoder(mnx_engine* e) {
     if (!var) return MNX_ERR_WEIGHTS
 #define UP(dst, vec) CUDA_TRY(e, mnx_upload(e, vec, &(dst)))
     std::vector<float> wkv((size_t)D * MNX_DEC_L * 512), bkv((size_t)MNX_DEC_L * 512);
+    // per-head tile stream of the persistent cluster kernel: [8][L*14 + 1][256 k][32 cols]
+    const size_t TILE = MG_TILE_FLOATS_H, TPL = MG_TILES_PER_LAYER_H, NTILE = MNX_DEC_L * TPL + 1;
+    std::vector<float> wpack((size_t)8 * NTILE * TILE, 0.f), ppack((size_t)8 * MNX_DEC_L * MG_PARAM_FLOATS_H, 0.f);
+    // tile[k][c] = W[row0 + c][k0 + k] for a torch Linear weight W [out][in]
+    auto put_tile = [&](int h, int l, int t, const std::vector<float>& Wm, int in_dim, int row0, int k0) {
+        float* dst = wpack.data() + ((size_t)h * NTILE + (size_t)l * TPL + t) * TILE;
+        for (int k = 0; k < 256; ++k)
+            for (int c = 0; c < 32; ++c) dst[k * 32 + c] = Wm[(size_t)(row0 + c) * in_dim + k0 + k];
+    };
     for (int l = 0; l < MNX_DEC_L; ++l) {
         const std::string L = P + "decoder.transformer_layers." + std::to_string(l) + ".";
         DecLayerW& w = e->dw.layer[l];
@@ -300,6 +321,26 @@ static int finalize_decoder(mnx_engine* e) {
         put_transposed(w1t, MNX_DEC_FF, 0, w1->f, MNX_DEC_FF, D);
         put_transposed(w2t, D, 0, w2->f, D, MNX_DEC_FF);
         UP(w.w1_t, w1t); UP(w.b1, b1->f); UP(w.w2_t, w2t); UP(w.b2, b2->f);
+        for (int h = 0; h < 8; ++h) {
+            put_tile(h, l, 0, sq->f, D, h * 32, 0);
+            put_tile(h, l, 1, sk->f, D, h * 32, 0);
+            put_tile(h, l, 2, sv->f, D, h * 32, 0);
+            put_tile(h, l, 3, so->f, D, h * 32, 0);
+            put_tile(h, l, 4, cq->f, D, h * 32, 0);
+            put_tile(h, l, 5, co->f, D, h * 32, 0);
+            for (int j = 0; j < 4; ++j) put_tile(h, l, 6 + j, w1->f, D, h * 128 + j * 32, 0);
+            for (int j = 0; j < 4; ++j) put_tile(h, l, 10 + j, w2->f, MNX_DEC_FF, h * 32, 256 * j);
+            float* pp = ppack.data() + ((size_t)h * MNX_DEC_L + l) * MG_PARAM_FLOATS_H;
+            std::copy(ln1w->f.begin(), ln1w->f.end(), pp + 0);    std::copy(ln1b->f.begin(), ln1b->f.end(), pp + 256);
+            std::copy(ln2w->f.begin(), ln2w->f.end(), pp + 512);  std::copy(ln2b->f.begin(), ln2b->f.end(), pp + 768);
+            std::copy(lnfw->f.begin(), lnfw->f.end(), pp + 1024); std::copy(lnfb->f.begin(), lnfb->f.end(), pp + 1280);
+            for (int c = 0; c < 32; ++c) {
+                pp[1536 + c] = sqb->f[h * 32 + c]; pp[1568 + c] = skb->f[h * 32 + c]; pp[1600 + c] = svb->f[h * 32 + c];
+                pp[1632 + c] = sob->f[h * 32 + c]; pp[1664 + c] = cqb->f[h * 32 + c]; pp[1696 + c] = cob->f[h * 32 + c];
+                pp[1856 + c] = b2->f[h * 32 + c];
+            }
+            for (int c = 0; c < 128; ++c) pp[1728 + c] = b1->f[h * 128 + c];
+        }
     }
     UP(e->dw.wkv_c_t, wkv); UP(e->dw.bkv_c, bkv);
     NEED(lnw, P + "decoder.layer_norm.weight", D); NEED(lnb, P + "decoder.layer_norm.bias", D);
@@ -309,6 +350,18 @@ static int finalize_decoder(mnx_engine* e) {
     put_transposed(wout, 256, 0, ow->f, V, D);
     std::copy(ob->f.begin(), ob->f.end(), bout.begin());
     UP(e->dw.wout_t, wout); UP(e->dw.bout, bout);
+    {
+        std::vector<float> fin(768, 0.f);
+        std::copy(lnw->f.begin(), lnw->f.end(), fin.begin());
+        std::copy(lnb->f.begin(), lnb->f.end(), fin.begin() + 256);
+        std::copy(ob->f.begin(), ob->f.end(), fin.begin() + 512);
+        for (int h = 0; h < 8; ++h) {
+            float* dst = wpack.data() + ((size_t)h * NTILE + (size_t)MNX_DEC_L * TPL) * TILE;
+            for (int k = 0; k < 256; ++k)
+                for (int c = 0; c < 32; ++c) dst[k * 32 + c] = (h * 32 + c < V) ? ow->f[(size_t)(h * 32 + c) * D + k] : 0.f;
+        }
+        UP(e->wpack, wpack); UP(e->ppack, ppack); UP(e->finalp, fin);
+    }
     NEED(emb, P + "embeddings.make_embedding.emb_luts.0.weight", V, D);
     UP(e->dw.emb, emb->f);
     NEED(pe, P + "embeddings.make_embedding.pe.pe", 5000, 1, D);
@@ -353,6 +406,8 @@ static int alloc_workspaces(mnx_engine* e) {
     CUDA_TRY(e, dev_alloc(e, &e->lens, B));
     CUDA_TRY(e, dev_alloc(e, &e->logp, B * T));
     CUDA_TRY(e, dev_alloc(e, &e->hidden, B * T * 256));
+    CUDA_TRY(e, dev_alloc(e, &e->row_state, B));
+    CUDA_TRY(e, dev_alloc(e, &e->steps_run_dev, 1));
     CUDA_TRY(e, dev_alloc(e, &e->hg, B * KA * 256));
     CUDA_TRY(e, dev_alloc(e, &e->AB, B * KA * 512));
     CUDA_TRY(e, dev_alloc(e, &e->prob, B * KA * KA * 8));
@@ -435,6 +490,31 @@ static int decode_internal(mnx_engine* e, const float* features, int B, int S, c
     int nl = 0;
     CUDA_TRY(e, dec_precompute(b, e->dw, features, e->cfg.encoder_dim, s, &nl));
     e->launches += nl;
+    // persistent cluster kernel when every cluster (<= 4 rows each) can be co-resident
+    const int usable = e->max_clusters < 16 ? e->max_clusters : 16;
+    const bool fits = usable > 0 && B <= usable * MG_GMAX_H;
+    if (e->decode_path == 2 && !fits)
+        return fail(e, MNX_ERR_CAPACITY, "cluster decode path forced but %d rows need more than %d co-resident clusters", B, usable);
+    if (fits && e->decode_path != 1) {
+        const int G = (B + usable - 1) / usable;
+        const int clusters = (B + G - 1) / G;
+        CUDA_TRY(e, cudaMemsetAsync(e->row_state, 0, sizeof(unsigned) * B, s));
+        CUDA_TRY(e, cudaMemsetAsync(e->steps_run_dev, 0, sizeof(int), s));
+        MegaArgs a{};
+        a.wpack = e->wpack; a.ppack = e->ppack; a.finalp = e->finalp; a.emb = e->dw.emb; a.pe = e->dw.pe;
+        a.selfK = e->selfK; a.selfV = e->selfV; a.crossK = e->crossK; a.crossV = e->crossV;
+        a.B = B; a.S = S; a.T = T; a.G = G;
+        a.ids = e->ids; a.logp = e->logp; a.hidden = e->hidden; a.lens = e->lens;
+        a.row_state = e->row_state; a.steps_run = e->steps_run_dev; a.g = e->g;
+        CUDA_TRY(e, mega_launch(a, clusters, s));
+        e->launches += 1;
+        int steps = 0;
+        CUDA_TRY(e, cudaMemcpyAsync(&steps, e->steps_run_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(e, cudaStreamSynchronize(s));
+        e->last_steps = steps;
+        e->last_B = B; e->last_S = S;
+        return MNX_OK;
+    }
     int rc = ensure_graph(e, b);
     if (rc != MNX_OK) return rc;
     for (int chunk = 0; chunk < T / STEPS_PER_GRAPH; ++chunk) {

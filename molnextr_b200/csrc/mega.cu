@@ -1,0 +1,629 @@
+// Persistent cluster decode kernel: the WHOLE greedy decode (all <= 480 steps, 6 layers each) in one
+// launch, with no grid-wide synchronisation.
+//
+// A thread-block cluster of 8 CTAs owns G <= 4 rows (images) for the entire decode; CTA h of the
+// cluster is attention head h and owns a 1/8 column slice of every linear layer:
+//   * every weight the CTA needs is a contiguous 32 KB tile [256 k][32 cols] (repacked once at load
+//     time); a producer warp streams the tiles L2 -> shared memory with 1-D bulk async copies (TMA
+//     engine) through a 3-deep mbarrier ring, running ahead of the math across phase boundaries;
+//   * activations (residual stream, attention context, FFN hidden, logits) are replicated in every
+//     CTA's shared memory and re-assembled after each sliced GEMM by writing the slice into all 8
+//     CTAs through distributed shared memory (st.shared::cluster) + a cluster-scope mbarrier;
+//   * K/V tiles of the row are staged with bulk copies exactly like the multi-kernel path;
+//   * greedy bookkeeping (log-softmax, grammar mask, argmax, <eos>, max length) is done redundantly
+//     in every CTA; the only inter-cluster traffic is one word per row per step (`row_state`), which
+//     later clusters read to reproduce the reference's "positional encoding indexed by the rank of
+//     the row among alive rows" rule (models/embedding.py:52-59).
+// Arithmetic is fp32 and mirrors decoder.cu operation for operation (same reference citations).
+#include "mega.cuh"
+
+namespace mnx {
+
+#define MG_COMPUTE_THREADS 256
+#define MG_THREADS 288            // + 1 producer warp
+#define MG_GMAX 4
+#define MG_TILE_FLOATS (256 * 32)
+#define MG_TILE_BYTES (MG_TILE_FLOATS * 4)
+#define MG_RING 3
+#define MG_TILES_PER_LAYER 14
+#define MG_PARAM_FLOATS 1920      // 1888 used, padded to a multiple of 32 floats
+#define MG_TK 160                 // keys per staged K/V tile
+#define MG_QSCALE 5.656854152679443f
+
+// tile ids inside a layer
+enum { TQ = 0, TK_ = 1, TV = 2, TOS = 3, TQC = 4, TOC = 5, TW1 = 6, TW2 = 10 };
+// parameter block offsets (floats)
+enum { P_LN1W = 0, P_LN1B = 256, P_LN2W = 512, P_LN2B = 768, P_LNFW = 1024, P_LNFB = 1280,
+       P_BQ = 1536, P_BK = 1568, P_BV = 1600, P_BO = 1632, P_BQC = 1664, P_BOC = 1696, P_B1 = 1728, P_B2 = 1856 };
+
+// ---- shared memory carve-up (bytes) ----------------------------------------------------------
+struct MegaSmem {
+    static constexpr int ring = 0;
+    static constexpr int kv = ring + MG_RING * MG_TILE_BYTES;                 // 98304
+    static constexpr int params = kv + 2 * MG_TK * 128;                        // +40960
+    static constexpr int finalp = params + 2 * MG_PARAM_FLOATS * 4;            // +15360
+    static constexpr int xbuf = finalp + 768 * 4;
+    static constexpr int nbuf = xbuf + MG_GMAX * 256 * 4;
+    static constexpr int ctxbuf = nbuf + MG_GMAX * 256 * 4;
+    static constexpr int hbuf = ctxbuf + MG_GMAX * 256 * 4;
+    static constexpr int lgbuf = hbuf + MG_GMAX * 1024 * 4;
+    static constexpr int qkv = lgbuf + MG_GMAX * 256 * 4;                      // q,k,v [G][32] each
+    static constexpr int scores = qkv + 3 * MG_GMAX * 32 * 4;
+    static constexpr int red = scores + 1024 * 4;                              // [8][G][32]
+    static constexpr int misc = red + 8 * MG_GMAX * 32 * 4;
+    static constexpr int total = misc + 512;
+};
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP_C:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_C;\n"
+        "bra WAIT_LOOP_C;\n"
+        "DONE_C:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// all threads of all CTAs of the cluster (non-.aligned form: callers need not be warp-converged)
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+struct MegaCtx {
+    uint8_t* sm;
+    int h;              // cluster rank = head
+    int tid, lane, warp;
+    int G;
+    uint64_t *full, *empty, *kvbar, *pbar, *xbar, *stepbar;
+    uint32_t tile_seq;  // consumer-side running tile counter
+    uint32_t kv_seq;    // running K/V staging counter
+    uint32_t x_seq;     // running exchange counter
+    uint32_t xbar_remote[8];
+};
+
+// ---- weight-tile ring (consumer side) ---------------------------------------------------------
+__device__ __forceinline__ const float* tile_acquire(MegaCtx& c) {
+    const uint32_t slot = c.tile_seq % MG_RING, ph = (c.tile_seq / MG_RING) & 1u;
+    mbar_wait(&c.full[slot], ph);
+    return reinterpret_cast<const float*>(c.sm + MegaSmem::ring + slot * MG_TILE_BYTES);
+}
+// call after every compute thread has finished reading the tile (i.e. after a compute_sync)
+__device__ __forceinline__ void tile_release(MegaCtx& c) {
+    const uint32_t slot = c.tile_seq % MG_RING;
+    if (c.tid == 0) mbar_arrive(&c.empty[slot]);
+    ++c.tile_seq;
+}
+
+// acc[g] += sum over this warp's 32 k of Xs[g][koff + 32*warp + k] * tile[32*warp + k][lane]
+__device__ __forceinline__ void tile_fma(const MegaCtx& c, const float* tile, const float* Xs, int ldx, int koff,
+                                         float (&acc)[MG_GMAX]) {
+    const int kb = 32 * c.warp;
+#pragma unroll
+    for (int kk = 0; kk < 32; kk += 4) {
+        const float w0 = tile[(kb + kk + 0) * 32 + c.lane];
+        const float w1 = tile[(kb + kk + 1) * 32 + c.lane];
+        const float w2 = tile[(kb + kk + 2) * 32 + c.lane];
+        const float w3 = tile[(kb + kk + 3) * 32 + c.lane];
+#pragma unroll
+        for (int g = 0; g < MG_GMAX; ++g) {
+            if (g < c.G) {
+                const float4 x = *reinterpret_cast<const float4*>(Xs + g * ldx + koff + kb + kk);
+                acc[g] = fmaf(x.x, w0, acc[g]);
+                acc[g] = fmaf(x.y, w1, acc[g]);
+                acc[g] = fmaf(x.z, w2, acc[g]);
+                acc[g] = fmaf(x.w, w3, acc[g]);
+            }
+        }
+    }
+}
+// cross-warp reduction of the 8 k-splits; afterwards thread (g = warp, col = lane) of the first G warps
+// holds the full dot product.  Contains two compute_syncs (the second protects `red` for reuse).
+__device__ __forceinline__ float tile_reduce(const MegaCtx& c, const float (&acc)[MG_GMAX]) {
+    float* red = reinterpret_cast<float*>(c.sm + MegaSmem::red);
+#pragma unroll
+    for (int g = 0; g < MG_GMAX; ++g)
+        if (g < c.G) red[(c.warp * MG_GMAX + g) * 32 + c.lane] = acc[g];
+    compute_sync();
+    float v = 0.f;
+    if (c.warp < c.G) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[(w * MG_GMAX + c.warp) * 32 + c.lane];
+    }
+    compute_sync();
+    return v;
+}
+
+// write one float into the same shared-memory location of all 8 CTAs of the cluster
+__device__ __forceinline__ void bcast_store(const MegaCtx& c, int byte_off, float v) {
+    const uint32_t local = smem_u32(c.sm + byte_off);
+#pragma unroll
+    for (uint32_t d = 0; d < 8; ++d) st_cluster_f32(mapa_u32(local, d), v);
+}
+// complete an all-gather: everybody's slices are visible in everybody's shared memory afterwards
+__device__ __forceinline__ void exchange_sync(MegaCtx& c) {
+    compute_sync();                       // all remote stores of this CTA issued
+    if (c.tid == 0) {
+        asm volatile("fence.acq_rel.cluster;" ::: "memory");
+#pragma unroll
+        for (int d = 0; d < 8; ++d) mbar_arrive_remote(c.xbar_remote[d]);
+    }
+    mbar_wait_cluster(c.xbar, c.x_seq & 1u);
+    ++c.x_seq;
+}
+
+// LayerNorm (eps 1e-6) of rows xbuf[g] -> nbuf[g]; warp g handles row g
+__device__ __forceinline__ void layer_norm_rows(const MegaCtx& c, const float* w, const float* b) {
+    if (c.warp < c.G) {
+        const float* x = reinterpret_cast<const float*>(c.sm + MegaSmem::xbuf) + c.warp * 256;
+        float* n = reinterpret_cast<float*>(c.sm + MegaSmem::nbuf) + c.warp * 256;
+        float4 v0 = reinterpret_cast<const float4*>(x)[c.lane];
+        float4 v1 = reinterpret_cast<const float4*>(x)[c.lane + 32];
+        const float sum = ((v0.x + v0.y) + (v0.z + v0.w)) + ((v1.x + v1.y) + (v1.z + v1.w));
+        const float mean = warp_sum(sum) * (1.0f / 256.0f);
+        v0.x -= mean; v0.y -= mean; v0.z -= mean; v0.w -= mean;
+        v1.x -= mean; v1.y -= mean; v1.z -= mean; v1.w -= mean;
+        const float sq = ((v0.x * v0.x + v0.y * v0.y) + (v0.z * v0.z + v0.w * v0.w)) +
+                         ((v1.x * v1.x + v1.y * v1.y) + (v1.z * v1.z + v1.w * v1.w));
+        const float rstd = 1.0f / sqrtf(warp_sum(sq) * (1.0f / 256.0f) + 1e-6f);
+        const float4 g0 = reinterpret_cast<const float4*>(w)[c.lane], g1 = reinterpret_cast<const float4*>(w)[c.lane + 32];
+        const float4 c0 = reinterpret_cast<const float4*>(b)[c.lane], c1 = reinterpret_cast<const float4*>(b)[c.lane + 32];
+        v0.x = v0.x * rstd * g0.x + c0.x; v0.y = v0.y * rstd * g0.y + c0.y;
+        v0.z = v0.z * rstd * g0.z + c0.z; v0.w = v0.w * rstd * g0.w + c0.w;
+        v1.x = v1.x * rstd * g1.x + c1.x; v1.y = v1.y * rstd * g1.y + c1.y;
+        v1.z = v1.z * rstd * g1.z + c1.z; v1.w = v1.w * rstd * g1.w + c1.w;
+        reinterpret_cast<float4*>(n)[c.lane] = v0;
+        reinterpret_cast<float4*>(n)[c.lane + 32] = v1;
+    }
+    compute_sync();
+}
+
+// single-query attention of head c.h for local row g; q in qkv smem; writes ctx slice to all CTAs.
+// nglobal keys come from Kb/Vb in global memory; if `extra` the row's new key/value (smem k/v) is
+// appended as key index nglobal (self-attention of the current position).
+__device__ void attend(MegaCtx& c, int g, const float* Kb, const float* Vb, int nglobal, bool extra) {
+    float* scores = reinterpret_cast<float*>(c.sm + MegaSmem::scores);
+    float* red = reinterpret_cast<float*>(c.sm + MegaSmem::red);
+    const float* qs = reinterpret_cast<const float*>(c.sm + MegaSmem::qkv) + g * 32;
+    const float* ks = reinterpret_cast<const float*>(c.sm + MegaSmem::qkv) + (MG_GMAX + g) * 32;
+    const float* vs = reinterpret_cast<const float*>(c.sm + MegaSmem::qkv) + (2 * MG_GMAX + g) * 32;
+    const int nkeys = nglobal + (extra ? 1 : 0);
+    const int ntiles = (nkeys + MG_TK - 1) / MG_TK;
+
+    auto issue = [&](int i, uint32_t seq) {
+        const int tile = (i < ntiles) ? i : i - ntiles;
+        const float* src = ((i < ntiles) ? Kb : Vb) + (size_t)tile * MG_TK * 32;
+        const int rows = min(MG_TK, nglobal - tile * MG_TK);
+        if (rows > 0) {
+            fence_proxy_async();
+            mbar_arrive_expect_tx(&c.kvbar[seq & 1u], (uint32_t)rows * 128u);
+            bulk_g2s(c.sm + MegaSmem::kv + (seq & 1u) * MG_TK * 128, src, (uint32_t)rows * 128u, &c.kvbar[seq & 1u]);
+        } else {
+            mbar_arrive(&c.kvbar[seq & 1u]);   // nothing to copy: complete the phase by hand
+        }
+    };
+    if (c.tid == 0) issue(0, c.kv_seq);
+    float acc = 0.f;
+    for (int i = 0; i < 2 * ntiles; ++i) {
+        const uint32_t seq = c.kv_seq + (uint32_t)i;
+        if (c.tid == 0 && i + 1 < 2 * ntiles) issue(i + 1, seq + 1);
+        mbar_wait(&c.kvbar[seq & 1u], (seq >> 1) & 1u);
+        float* tb = reinterpret_cast<float*>(c.sm + MegaSmem::kv + (seq & 1u) * MG_TK * 128);
+        const int tile = (i < ntiles) ? i : i - ntiles;
+        const int nk = min(MG_TK, nkeys - tile * MG_TK);
+        // the freshly computed key/value of this position lives only in shared memory: drop it in place
+        if (extra && tile == ntiles - 1) {
+            if (c.tid < 32) tb[(nkeys - 1 - tile * MG_TK) * 32 + c.tid] = (i < ntiles) ? ks[c.tid] : vs[c.tid];
+            compute_sync();
+        }
+        if (i < ntiles) {
+            for (int j = c.tid; j < nk; j += MG_COMPUTE_THREADS) {
+                const float4* kr = reinterpret_cast<const float4*>(tb + j * 32);
+                float s = 0.f;
+#pragma unroll
+                for (int cc0 = 0; cc0 < 8; ++cc0) {
+                    const int cc = (cc0 + j) & 7;
+                    const float4 kv = kr[cc];
+                    const float4 qv = reinterpret_cast<const float4*>(qs)[cc];
+                    s = fmaf(qv.x, kv.x, s); s = fmaf(qv.y, kv.y, s);
+                    s = fmaf(qv.z, kv.z, s); s = fmaf(qv.w, kv.w, s);
+                }
+                scores[tile * MG_TK + j] = s;
+            }
+        } else {
+            if (i == ntiles) {
+                compute_sync();
+                float m = -INFINITY;
+                for (int j = c.tid; j < nkeys; j += MG_COMPUTE_THREADS) m = fmaxf(m, scores[j]);
+                m = warp_max(m);
+                if (c.lane == 0) red[c.warp] = m;
+                compute_sync();
+                m = red[0];
+#pragma unroll
+                for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+                compute_sync();
+                float sum = 0.f;
+                for (int j = c.tid; j < nkeys; j += MG_COMPUTE_THREADS) {
+                    const float e = expf(scores[j] - m);
+                    scores[j] = e;
+                    sum += e;
+                }
+                sum = warp_sum(sum);
+                if (c.lane == 0) red[c.warp] = sum;
+                compute_sync();
+                sum = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
+                for (int j = c.tid; j < nkeys; j += MG_COMPUTE_THREADS) scores[j] = scores[j] / sum;
+                compute_sync();
+            }
+            const float* ps = scores + tile * MG_TK;
+            for (int j = c.warp; j < nk; j += 8) acc = fmaf(ps[j], tb[j * 32 + c.lane], acc);
+        }
+        compute_sync();   // tile consumed
+    }
+    c.kv_seq += (uint32_t)(2 * ntiles);
+    red[c.warp * 32 + c.lane] = acc;
+    compute_sync();
+    if (c.warp == 0) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[w * 32 + c.lane];
+        bcast_store(c, MegaSmem::ctxbuf + (g * 256 + c.h * 32 + c.lane) * 4, v);
+    }
+    compute_sync();
+}
+
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    MegaCtx c;
+    c.sm = sm;
+    c.tid = threadIdx.x; c.lane = c.tid & 31; c.warp = c.tid >> 5;
+    {
+        uint32_t r;
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+        c.h = (int)r;
+    }
+    const int cluster = blockIdx.x >> 3;
+    const int row0 = cluster * a.G;
+    c.G = min(a.G, a.B - row0);
+    c.tile_seq = 0; c.kv_seq = 0; c.x_seq = 0;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + MegaSmem::misc);
+    c.full = bars; c.empty = bars + MG_RING; c.kvbar = bars + 2 * MG_RING; c.pbar = c.kvbar + 2;
+    c.xbar = c.pbar + 2; c.stepbar = c.xbar + 1;
+    int* s_tok = reinterpret_cast<int*>(c.stepbar + 1);      // [G]
+    int* s_fin = s_tok + MG_GMAX;                             // [G]
+    int* s_rank = s_fin + MG_GMAX;                            // [G]
+    int* s_go = s_rank + MG_GMAX;                             // producer: continue flag
+
+    if (c.tid == 0) {
+        for (int i = 0; i < MG_RING; ++i) { mbar_init(&c.full[i], 1); mbar_init(&c.empty[i], 1); }
+        mbar_init(&c.kvbar[0], 1); mbar_init(&c.kvbar[1], 1);
+        mbar_init(&c.pbar[0], 1); mbar_init(&c.pbar[1], 1);
+        mbar_init(c.xbar, 8);
+        mbar_init(c.stepbar, 1);
+        fence_barrier_init();
+        for (int g = 0; g < MG_GMAX; ++g) { s_tok[g] = a.g.sos; s_fin[g] = (g < c.G) ? 0 : 1; s_rank[g] = 0; }
+        *s_go = 1;
+    }
+    for (int i = c.tid; i < 768; i += MG_THREADS) reinterpret_cast<float*>(sm + MegaSmem::finalp)[i] = a.finalp[i];
+#pragma unroll
+    for (uint32_t d = 0; d < 8; ++d) c.xbar_remote[d] = mapa_u32(smem_u32(c.xbar), d);
+    // every CTA's barriers must be initialised before anyone arrives remotely
+    cluster_sync_all();
+
+    const size_t kv_layer = (size_t)a.B * 8 * a.T * 32;
+    const float* wbase = a.wpack + (size_t)c.h * (MNX_DEC_L * MG_TILES_PER_LAYER + 1) * MG_TILE_FLOATS;
+    const float* pbase = a.ppack + (size_t)c.h * MNX_DEC_L * MG_PARAM_FLOATS;
+
+    if (c.warp == 8) {
+        // =========================== producer warp: weight tiles + parameter blocks ===========================
+        if (c.lane == 0) {
+            uint32_t seq = 0, pseq = 0, step = 0;
+            for (;;) {
+                // wait until the consumers decided that step `step` runs
+                mbar_wait(c.stepbar, step & 1u);
+                if (*reinterpret_cast<volatile int*>(s_go) == 0) break;
+                for (int l = 0; l < MNX_DEC_L; ++l) {
+                    {   // parameter block of layer l (double buffered)
+                        const uint32_t pb = pseq & 1u;
+                        // slot reuse is safe: block pseq-2 was consumed two layers ago (consumers sync every tile)
+                        mbar_arrive_expect_tx(&c.pbar[pb], MG_PARAM_FLOATS * 4);
+                        bulk_g2s(sm + MegaSmem::params + pb * MG_PARAM_FLOATS * 4, pbase + (size_t)l * MG_PARAM_FLOATS,
+                                 MG_PARAM_FLOATS * 4, &c.pbar[pb]);
+                        ++pseq;
+                    }
+                    for (int tI = 0; tI < MG_TILES_PER_LAYER; ++tI, ++seq) {
+                        const uint32_t slot = seq % MG_RING, ph = (seq / MG_RING) & 1u;
+                        mbar_wait(&c.empty[slot], ph ^ 1u);
+                        mbar_arrive_expect_tx(&c.full[slot], MG_TILE_BYTES);
+                        bulk_g2s(sm + MegaSmem::ring + slot * MG_TILE_BYTES,
+                                 wbase + (size_t)(l * MG_TILES_PER_LAYER + tI) * MG_TILE_FLOATS, MG_TILE_BYTES, &c.full[slot]);
+                    }
+                }
+                {   // vocabulary tile
+                    const uint32_t slot = seq % MG_RING, ph = (seq / MG_RING) & 1u;
+                    mbar_wait(&c.empty[slot], ph ^ 1u);
+                    mbar_arrive_expect_tx(&c.full[slot], MG_TILE_BYTES);
+                    bulk_g2s(sm + MegaSmem::ring + slot * MG_TILE_BYTES,
+                             wbase + (size_t)(MNX_DEC_L * MG_TILES_PER_LAYER) * MG_TILE_FLOATS, MG_TILE_BYTES, &c.full[slot]);
+                    ++seq;
+                }
+                ++step;
+            }
+        }
+        __syncwarp();
+    } else {
+        // =========================== 8 compute warps ===========================
+        float* xbuf = reinterpret_cast<float*>(sm + MegaSmem::xbuf);
+        float* nbuf = reinterpret_cast<float*>(sm + MegaSmem::nbuf);
+        float* ctxbuf = reinterpret_cast<float*>(sm + MegaSmem::ctxbuf);
+        float* hbuf = reinterpret_cast<float*>(sm + MegaSmem::hbuf);
+        float* lgbuf = reinterpret_cast<float*>(sm + MegaSmem::lgbuf);
+        float* qkv = reinterpret_cast<float*>(sm + MegaSmem::qkv);
+        const float* fp = reinterpret_cast<const float*>(sm + MegaSmem::finalp);
+        uint32_t pseq = 0;
+        int t = 0;
+        for (;; ++t) {
+            // ---- is there anything left to do in this cluster? ----
+            bool any = false;
+            for (int g = 0; g < c.G; ++g) any = any || (s_fin[g] == 0);
+            if (c.tid == 0) {
+                *reinterpret_cast<volatile int*>(s_go) = any ? 1 : 0;
+                __threadfence_block();
+                mbar_arrive(c.stepbar);
+            }
+            if (!any) break;
+            // ---- rank of each alive row among all alive rows of the batch (row-rank PE rule) ----
+            if (c.warp == 0) {
+                int finished_before = 0;
+                for (int r = c.lane; r < row0; r += 32) {
+                    unsigned s;
+                    do { s = ld_acquire_u32(a.row_state + r); } while ((s >> 1) < (unsigned)t && (s & 1u) == 0u);
+                    if ((s & 1u) && (s >> 1) <= (unsigned)t) ++finished_before;
+                }
+                finished_before = (int)warp_sum((float)finished_before);
+                if (c.lane == 0) {
+                    int alive_lower = row0 - finished_before;
+                    for (int g = 0; g < c.G; ++g) {
+                        s_rank[g] = alive_lower;
+                        if (s_fin[g] == 0) ++alive_lower;
+                    }
+                }
+            }
+            compute_sync();
+            // ---- embedding: x = emb[tok] * 16 + pe[rank]  (Embeddings / PositionalEncoding) ----
+            for (int i = c.tid; i < c.G * 256; i += MG_COMPUTE_THREADS) {
+                const int g = i >> 8, d = i & 255;
+                xbuf[i] = (s_fin[g] == 0) ? a.emb[s_tok[g] * 256 + d] * 16.0f + a.pe[(size_t)s_rank[g] * 256 + d] : 0.f;
+            }
+            compute_sync();
+
+            for (int l = 0; l < MNX_DEC_L; ++l) {
+                mbar_wait(&c.pbar[pseq & 1u], (pseq >> 1) & 1u);
+                const float* P = reinterpret_cast<const float*>(sm + MegaSmem::params + (pseq & 1u) * MG_PARAM_FLOATS * 4);
+                ++pseq;
+                float* Kc = a.selfK + l * kv_layer;
+                float* Vc = a.selfV + l * kv_layer;
+                // ---------- self attention ----------
+                layer_norm_rows(c, P + P_LN1W, P + P_LN1B);
+#pragma unroll 1
+                for (int which = 0; which < 3; ++which) {
+                    float acc[MG_GMAX] = {0.f, 0.f, 0.f, 0.f};
+                    const float* tile = tile_acquire(c);
+                    tile_fma(c, tile, nbuf, 256, 0, acc);
+                    const float v = tile_reduce(c, acc);
+                    tile_release(c);
+                    if (c.warp < c.G) {
+                        const int g = c.warp;
+                        const float o = v + P[P_BQ + which * 32 + c.lane];
+                        if (which == 0) {
+                            qkv[g * 32 + c.lane] = o / MG_QSCALE;
+                        } else {
+                            qkv[(which * MG_GMAX + g) * 32 + c.lane] = o;
+                            if (s_fin[g] == 0) {
+                                float* dst = (which == 1) ? Kc : Vc;
+                                dst[(((size_t)(row0 + g) * 8 + c.h) * a.T + t) * 32 + c.lane] = o;
+                            }
+                        }
+                    }
+                }
+                compute_sync();
+                for (int g = 0; g < c.G; ++g) {
+                    if (s_fin[g]) continue;                        // uniform across the cluster
+                    attend(c, g, Kc + ((size_t)(row0 + g) * 8 + c.h) * a.T * 32, Vc + ((size_t)(row0 + g) * 8 + c.h) * a.T * 32, t, true);
+                }
+                exchange_sync(c);                                  // ctx complete everywhere
+                {   // final_linear slice + residual -> x1
+                    float acc[MG_GMAX] = {0.f, 0.f, 0.f, 0.f};
+                    const float* tile = tile_acquire(c);
+                    tile_fma(c, tile, ctxbuf, 256, 0, acc);
+                    const float v = tile_reduce(c, acc);
+                    tile_release(c);
+                    if (c.warp < c.G) {
+                        const int col = c.h * 32 + c.lane;
+                        bcast_store(c, MegaSmem::xbuf + (c.warp * 256 + col) * 4, (v + P[P_BO + c.lane]) + xbuf[c.warp * 256 + col]);
+                    }
+                }
+                exchange_sync(c);                                  // x1 complete everywhere
+                // ---------- context attention ----------
+                layer_norm_rows(c, P + P_LN2W, P + P_LN2B);
+                {
+                    float acc[MG_GMAX] = {0.f, 0.f, 0.f, 0.f};
+                    const float* tile = tile_acquire(c);
+                    tile_fma(c, tile, nbuf, 256, 0, acc);
+                    const float v = tile_reduce(c, acc);
+                    tile_release(c);
+                    if (c.warp < c.G) qkv[c.warp * 32 + c.lane] = (v + P[P_BQC + c.lane]) / MG_QSCALE;
+                }
+                compute_sync();
+                for (int g = 0; g < c.G; ++g) {
+                    if (s_fin[g]) continue;
+                    const size_t off = (((size_t)l * a.B + row0 + g) * 8 + c.h) * (size_t)a.S * 32;
+                    attend(c, g, a.crossK + off, a.crossV + off, a.S, false);
+                }
+                exchange_sync(c);
+                {
+                    float acc[MG_GMAX] = {0.f, 0.f, 0.f, 0.f};
+                    const float* tile = tile_acquire(c);
+                    tile_fma(c, tile, ctxbuf, 256, 0, acc);
+                    const float v = tile_reduce(c, acc);
+                    tile_release(c);
+                    if (c.warp < c.G) {
+                        const int col = c.h * 32 + c.lane;
+                        bcast_store(c, MegaSmem::xbuf + (c.warp * 256 + col) * 4, (v + P[P_BOC + c.lane]) + xbuf[c.warp * 256 + col]);
+                    }
+                }
+                exchange_sync(c);                                  // x2
+                // ---------- feed forward ----------
+                layer_norm_rows(c, P + P_LNFW, P + P_LNFB);
+#pragma unroll 1
+                for (int j = 0; j < 4; ++j) {
+                    float acc[MG_GMAX] = {0.f, 0.f, 0.f, 0.f};
+                    const float* tile = tile_acquire(c);
+                    tile_fma(c, tile, nbuf, 256, 0, acc);
+                    const float v = tile_reduce(c, acc);
+                    tile_release(c);
+                    if (c.warp < c.G)
+                        bcast_store(c, MegaSmem::hbuf + (c.warp * 1024 + c.h * 128 + j * 32 + c.lane) * 4,
+                                    gelu_erf(v + P[P_B1 + j * 32 + c.lane]));
+                }
+                exchange_sync(c);                                  // FFN hidden complete
+                {
+                    float acc[MG_GMAX] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+                    for (int j = 0; j < 4; ++j) {
+                        const float* tile = tile_acquire(c);
+                        tile_fma(c, tile, hbuf, 1024, 256 * j, acc);
+                        compute_sync();
+                        tile_release(c);
+                    }
+                    const float v = tile_reduce(c, acc);
+                    if (c.warp < c.G) {
+                        const int col = c.h * 32 + c.lane;
+                        bcast_store(c, MegaSmem::xbuf + (c.warp * 256 + col) * 4, (v + P[P_B2 + c.lane]) + xbuf[c.warp * 256 + col]);
+                    }
+                }
+                exchange_sync(c);                                  // x3 = layer output
+            }
+            // ---------- final LayerNorm, vocabulary slice, all-gather of the logits ----------
+            layer_norm_rows(c, fp, fp + 256);
+            {
+                float acc[MG_GMAX] = {0.f, 0.f, 0.f, 0.f};
+                const float* tile = tile_acquire(c);
+                tile_fma(c, tile, nbuf, 256, 0, acc);
+                const float v = tile_reduce(c, acc);
+                tile_release(c);
+                if (c.warp < c.G)
+                    bcast_store(c, MegaSmem::lgbuf + (c.warp * 256 + c.h * 32 + c.lane) * 4, v + fp[512 + c.h * 32 + c.lane]);
+            }
+            exchange_sync(c);
+            // ---------- log_softmax, grammar mask, argmax: warp g decides row g (identically in every CTA) ----------
+            if (c.warp < c.G && s_fin[c.warp] == 0) {
+                const int g = c.warp, row = row0 + g;
+                float lg[8];
+                float m = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int v = i * 32 + c.lane;
+                    lg[i] = (v < a.g.vocab) ? lgbuf[g * 256 + v] : -INFINITY;
+                    m = fmaxf(m, lg[i]);
+                }
+                m = warp_max(m);
+                float se = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) se += (i * 32 + c.lane < a.g.vocab) ? expf(lg[i] - m) : 0.f;
+                se = warp_sum(se);
+                const float lse = logf(se);
+                const int tok_in = s_tok[g];
+                const bool in_x = tok_in >= a.g.offset && tok_in < a.g.offset + a.g.maxx;
+                const bool in_y = tok_in >= a.g.offset + a.g.maxx;
+                float bv = -INFINITY;
+                int bi = 1 << 30;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int v = i * 32 + c.lane;
+                    float lp = (lg[i] - m) - lse;
+                    if (in_x && v < a.g.offset + a.g.maxx) lp = -10000.0f;
+                    if (in_y && v >= a.g.offset) lp = -10000.0f;
+                    if (t == 0 && v == a.g.eos) lp = -1e20f;
+                    if (v >= a.g.vocab) lp = -INFINITY;
+                    if (lp > bv) { bv = lp; bi = v; }      // ascending v: first maximum kept
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                }
+                const int fin = (bi == a.g.eos) || (t == a.g.max_len - 1);
+                if (c.h == 0) {
+                    // hidden state of this step = final LayerNorm output (greedy_search.py:93-97)
+                    float* hd = a.hidden + ((size_t)row * a.T + t) * 256;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) hd[i * 32 + c.lane] = nbuf[g * 256 + i * 32 + c.lane];
+                    if (c.lane == 0) {
+                        a.ids[(size_t)row * a.T + t] = bi;
+                        a.logp[(size_t)row * a.T + t] = bv;
+                        if (fin) { a.lens[row] = t + 1; atomicMax(a.steps_run, t + 1); }
+                        st_release_u32(a.row_state + row, ((unsigned)(t + 1) << 1) | (fin ? 1u : 0u));
+                    }
+                }
+                __syncwarp();
+                if (c.lane == 0) { s_tok[g] = bi; s_fin[g] = fin; }
+            }
+            compute_sync();
+        }
+    }
+    // nobody may exit while peers can still write into its shared memory or arrive on its barriers
+    cluster_sync_all();
+}
+
+// ---- host side --------------------------------------------------------------------------------
+size_t mega_smem_bytes() { return (size_t)MegaSmem::total; }
+
+cudaError_t mega_configure(int* max_clusters) {
+    cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MegaSmem::total);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(8 * 16);
+    cfg.blockDim = dim3(MG_THREADS);
+    cfg.dynamicSmemBytes = MegaSmem::total;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 8; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    e = cudaOccupancyMaxActiveClusters(&n, decode_mega_kernel, &cfg);
+    if (e != cudaSuccess) return e;
+    *max_clusters = n;
+    return cudaSuccess;
+}
+
+cudaError_t mega_launch(const MegaArgs& a, int clusters, cudaStream_t s) {
+    decode_mega_kernel<<<dim3(8 * clusters), MG_THREADS, MegaSmem::total, s>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace mnx

@@ -1,0 +1,35 @@
+// Persistent cluster decode kernel (mega.cu): host-visible interface.
+#pragma once
+#include "decoder.cuh"
+
+namespace mnx {
+
+#define MG_TILE_FLOATS_H (256 * 32)
+#define MG_TILES_PER_LAYER_H 14
+#define MG_PARAM_FLOATS_H 1920
+#define MG_GMAX_H 4
+
+struct MegaArgs {
+    const float* wpack;
+    const float* ppack;
+    const float* finalp;
+    const float* emb;
+    const float* pe;
+    float* selfK;
+    float* selfV;
+    const float* crossK;
+    const float* crossV;
+    int B, S, T, G;
+    int* ids;
+    float* logp;
+    float* hidden;
+    int* lens;
+    unsigned int* row_state;
+    int* steps_run;
+    Grammar g;
+};
+
+cudaError_t mega_configure(int* max_clusters);
+cudaError_t mega_launch(const MegaArgs& a, int clusters, cudaStream_t s);
+
+}  // namespace mnx

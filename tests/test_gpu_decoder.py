@@ -14,10 +14,14 @@ from tests.helpers import load_golden, seeded_features
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def engines():
+@pytest.fixture(scope="module", params=["cluster", "graph"])
+def engines(request):
+    """Both decode paths are exercised: the persistent cluster kernel (mega.cu) and the
+    multi-kernel CUDA-graph path (decoder.cu) used for batches that do not fit in 16 clusters."""
+    import os
     from molnextr_b200.engine import Engine
     cache = {}
+    os.environ["MNX_DECODE_PATH"] = request.param
 
     def get(seed):
         if seed not in cache:
@@ -28,6 +32,7 @@ def engines():
     yield get
     for e in cache.values():
         e.close()
+    os.environ.pop("MNX_DECODE_PATH", None)
 
 
 def _compare(out, atom_idx, n_atoms, edges, ref_ids, ref_lens, ref_tokp, ref_hsub, ref_natoms, ref_aidx, ref_edges):
