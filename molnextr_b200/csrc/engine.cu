@@ -71,6 +71,7 @@ struct mnx_engine {
     const float *wpack = nullptr, *ppack = nullptr, *finalp = nullptr;
     unsigned int* row_state = nullptr;
     int* steps_run_dev = nullptr;
+    long long* prof_dev = nullptr;
     int max_clusters = 0;
     int decode_path = 0;   // 0 auto, 1 force multi-kernel graph path, 2 force cluster kernel
     // bond head
@@ -408,6 +409,8 @@ static int alloc_workspaces(mnx_engine* e) {
     CUDA_TRY(e, dev_alloc(e, &e->hidden, B * T * 256));
     CUDA_TRY(e, dev_alloc(e, &e->row_state, B));
     CUDA_TRY(e, dev_alloc(e, &e->steps_run_dev, 1));
+    CUDA_TRY(e, dev_alloc(e, &e->prof_dev, 64));
+    CUDA_TRY(e, cudaMemset(e->prof_dev, 0, 64 * sizeof(long long)));
     CUDA_TRY(e, dev_alloc(e, &e->hg, B * KA * 256));
     CUDA_TRY(e, dev_alloc(e, &e->AB, B * KA * 512));
     CUDA_TRY(e, dev_alloc(e, &e->prob, B * KA * KA * 8));
@@ -506,6 +509,7 @@ static int decode_internal(mnx_engine* e, const float* features, int B, int S, c
         a.B = B; a.S = S; a.T = T; a.G = G;
         a.ids = e->ids; a.logp = e->logp; a.hidden = e->hidden; a.lens = e->lens;
         a.row_state = e->row_state; a.steps_run = e->steps_run_dev; a.g = e->g;
+        a.prof = getenv("MNX_DECODE_PROFILE") ? e->prof_dev : nullptr;
         CUDA_TRY(e, mega_launch(a, clusters, s));
         e->launches += 1;
         int steps = 0;
@@ -633,6 +637,14 @@ extern "C" int32_t mnx_last_decode_steps(const mnx_engine* e) { return e ? e->la
 
 extern "C" int mnx_time_kernel(mnx_engine* e, int32_t which, int32_t iters, float* ms, void* cuda_stream) {
     if (!e || !ms || iters < 1) return fail(e, MNX_ERR_INVALID, "mnx_time_kernel: bad argument");
+    if (which == 1000) { *ms = (float)e->max_clusters; return MNX_OK; }   // introspection: co-resident 8-CTA clusters
+    if (which == 1001) {   // dump the cycle stamps recorded by the last profiled cluster decode (MNX_DECODE_PROFILE=1)
+        long long h[64];
+        CUDA_TRY(e, cudaMemcpy(h, e->prof_dev, sizeof(h), cudaMemcpyDeviceToHost));
+        for (int i = 1; i < 64 && h[i] != 0; ++i) fprintf(stderr, "mark %2d: +%lld cycles (total %lld)\n", i, h[i] - h[i - 1], h[i] - h[0]);
+        *ms = 0.f;
+        return MNX_OK;
+    }
     if (!e->finalized || e->last_B == 0) return fail(e, MNX_ERR_INVALID, "run a decode first: timing uses its shapes and caches");
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
     cudaStream_t s = (cudaStream_t)cuda_stream;

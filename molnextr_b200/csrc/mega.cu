@@ -21,13 +21,13 @@ namespace mnx {
 
 #define MG_COMPUTE_THREADS 256
 #define MG_THREADS 288            // + 1 producer warp
-#define MG_GMAX 4
+#define MG_GMAX 2
 #define MG_TILE_FLOATS (256 * 32)
 #define MG_TILE_BYTES (MG_TILE_FLOATS * 4)
 #define MG_RING 3
 #define MG_TILES_PER_LAYER 14
 #define MG_PARAM_FLOATS 1920      // 1888 used, padded to a multiple of 32 floats
-#define MG_TK 160                 // keys per staged K/V tile
+#define MG_TK 144                 // keys per staged K/V tile (= S at 384x384)
 #define MG_QSCALE 5.656854152679443f
 
 // tile ids inside a layer
@@ -40,7 +40,7 @@ enum { P_LN1W = 0, P_LN1B = 256, P_LN2W = 512, P_LN2B = 768, P_LNFW = 1024, P_LN
 struct MegaSmem {
     static constexpr int ring = 0;
     static constexpr int kv = ring + MG_RING * MG_TILE_BYTES;                 // 98304
-    static constexpr int params = kv + 2 * MG_TK * 128;                        // +40960
+    static constexpr int params = kv + 4 * MG_TK * 128;                        // 2 row groups x 2 buffers
     static constexpr int finalp = params + 2 * MG_PARAM_FLOATS * 4;            // +15360
     static constexpr int xbuf = finalp + 768 * 4;
     static constexpr int nbuf = xbuf + MG_GMAX * 256 * 4;
@@ -49,8 +49,8 @@ struct MegaSmem {
     static constexpr int lgbuf = hbuf + MG_GMAX * 1024 * 4;
     static constexpr int qkv = lgbuf + MG_GMAX * 256 * 4;                      // q,k,v [G][32] each
     static constexpr int scores = qkv + 3 * MG_GMAX * 32 * 4;
-    static constexpr int red = scores + 1024 * 4;                              // [8][G][32]
-    static constexpr int misc = red + 8 * MG_GMAX * 32 * 4;
+    static constexpr int red = scores + 2 * 1024 * 4;                          // scores: one row per group
+    static constexpr int misc = red + 4 * 8 * MG_GMAX * 32 * 4;               // red: [4 sets][8 warps][G][32]
     static constexpr int total = misc + 512;
 };
 
@@ -100,9 +100,10 @@ struct MegaCtx {
     int G;
     uint64_t *full, *empty, *kvbar, *pbar, *xbar, *stepbar;
     uint32_t tile_seq;  // consumer-side running tile counter
-    uint32_t kv_seq;    // running K/V staging counter
+    uint32_t kv_seq;    // running K/V staging counter of this thread's row group
     uint32_t x_seq;     // running exchange counter
-    uint32_t xbar_remote[8];
+    int grp, gtid, gwarp;   // attention row group (0/1), thread and warp index inside it
+    uint32_t xbar_remote[8];      // exchange barrier 0 of every CTA (barrier 1 is 8 bytes further)
 };
 
 // ---- weight-tile ring (consumer side) ---------------------------------------------------------
@@ -111,10 +112,11 @@ __device__ __forceinline__ const float* tile_acquire(MegaCtx& c) {
     mbar_wait(&c.full[slot], ph);
     return reinterpret_cast<const float*>(c.sm + MegaSmem::ring + slot * MG_TILE_BYTES);
 }
-// call after every compute thread has finished reading the tile (i.e. after a compute_sync)
+// each warp releases the slot as soon as IT has finished reading the tile (empty barrier counts 8)
 __device__ __forceinline__ void tile_release(MegaCtx& c) {
     const uint32_t slot = c.tile_seq % MG_RING;
-    if (c.tid == 0) mbar_arrive(&c.empty[slot]);
+    __syncwarp();
+    if (c.lane == 0) mbar_arrive(&c.empty[slot]);
     ++c.tile_seq;
 }
 
@@ -140,38 +142,46 @@ __device__ __forceinline__ void tile_fma(const MegaCtx& c, const float* tile, co
         }
     }
 }
-// cross-warp reduction of the 8 k-splits; afterwards thread (g = warp, col = lane) of the first G warps
-// holds the full dot product.  Contains two compute_syncs (the second protects `red` for reuse).
-__device__ __forceinline__ float tile_reduce(const MegaCtx& c, const float (&acc)[MG_GMAX]) {
+// cross-warp reduction of the 8 k-splits of NS accumulator sets at once.  Warp w < NS*G then holds,
+// in lane c, the complete dot product of set (w / G), row (w % G), column c.  Two compute_syncs.
+template <int NS>
+__device__ __forceinline__ float tile_reduce(const MegaCtx& c, const float (&acc)[NS][MG_GMAX]) {
     float* red = reinterpret_cast<float*>(c.sm + MegaSmem::red);
 #pragma unroll
-    for (int g = 0; g < MG_GMAX; ++g)
-        if (g < c.G) red[(c.warp * MG_GMAX + g) * 32 + c.lane] = acc[g];
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int g = 0; g < MG_GMAX; ++g)
+            if (g < c.G) red[((s * 8 + c.warp) * MG_GMAX + g) * 32 + c.lane] = acc[s][g];
     compute_sync();
     float v = 0.f;
-    if (c.warp < c.G) {
+    if (c.warp < NS * c.G) {
+        const int s = c.warp / c.G, g = c.warp % c.G;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) v += red[(w * MG_GMAX + c.warp) * 32 + c.lane];
+        for (int w = 0; w < 8; ++w) v += red[((s * 8 + w) * MG_GMAX + g) * 32 + c.lane];
     }
     compute_sync();
     return v;
 }
 
-// write one float into the same shared-memory location of all 8 CTAs of the cluster
+// write one float into the same shared-memory location of all 8 CTAs of the cluster.  The store is
+// asynchronous and signals the destination CTA's exchange mbarrier with its byte count
+// (st.async ... mbarrier::complete_tx), so no fence / arrive round trip is needed afterwards.
 __device__ __forceinline__ void bcast_store(const MegaCtx& c, int byte_off, float v) {
     const uint32_t local = smem_u32(c.sm + byte_off);
 #pragma unroll
-    for (uint32_t d = 0; d < 8; ++d) st_cluster_f32(mapa_u32(local, d), v);
-}
-// complete an all-gather: everybody's slices are visible in everybody's shared memory afterwards
-__device__ __forceinline__ void exchange_sync(MegaCtx& c) {
-    compute_sync();                       // all remote stores of this CTA issued
-    if (c.tid == 0) {
-        asm volatile("fence.acq_rel.cluster;" ::: "memory");
-#pragma unroll
-        for (int d = 0; d < 8; ++d) mbar_arrive_remote(c.xbar_remote[d]);
+    for (uint32_t d = 0; d < 8; ++d) {
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(mapa_u32(local, d)),
+                     "r"(__float_as_uint(v)), "r"(c.xbar_remote[d] + 8u * (c.x_seq & 1u))
+                     : "memory");
     }
-    mbar_wait_cluster(c.xbar, c.x_seq & 1u);
+}
+// complete an all-gather in which every CTA of the cluster sent `bytes_per_cta` bytes to every CTA.
+// Two barriers alternate between consecutive exchanges so a fast peer's next exchange can never be
+// counted into the current phase.
+__device__ __forceinline__ void exchange_sync(MegaCtx& c, uint32_t bytes_per_cta) {
+    uint64_t* bar = c.xbar + (c.x_seq & 1u);
+    if (c.tid == 0) mbar_arrive_expect_tx(bar, 8u * bytes_per_cta);
+    mbar_wait_cluster(bar, (c.x_seq >> 1) & 1u);
     ++c.x_seq;
 }
 
@@ -201,46 +211,58 @@ __device__ __forceinline__ void layer_norm_rows(const MegaCtx& c, const float* w
     compute_sync();
 }
 
-// single-query attention of head c.h for local row g; q in qkv smem; writes ctx slice to all CTAs.
-// nglobal keys come from Kb/Vb in global memory; if `extra` the row's new key/value (smem k/v) is
-// appended as key index nglobal (self-attention of the current position).
-__device__ void attend(MegaCtx& c, int g, const float* Kb, const float* Vb, int nglobal, bool extra) {
-    float* scores = reinterpret_cast<float*>(c.sm + MegaSmem::scores);
-    float* red = reinterpret_cast<float*>(c.sm + MegaSmem::red);
+// ---- attention: row g of the cluster is handled by thread group g (128 threads = 4 warps) ----------
+__device__ __forceinline__ void group_sync(const MegaCtx& c) {
+    asm volatile("bar.sync %0, 128;" ::"r"(2 + c.grp) : "memory");
+}
+// stage tile i of the sequence K0..K(n-1), V0..V(n-1) of this group's row into buffer (seq & 1)
+__device__ __forceinline__ void kv_issue(const MegaCtx& c, const float* Kb, const float* Vb, int nglobal, int ntiles,
+                                         int i, uint32_t seq) {
+    const int tile = (i < ntiles) ? i : i - ntiles;
+    const float* src = ((i < ntiles) ? Kb : Vb) + (size_t)tile * MG_TK * 32;
+    const int rows = min(MG_TK, nglobal - tile * MG_TK);
+    uint64_t* bar = &c.kvbar[c.grp * 2 + (seq & 1u)];
+    if (rows > 0) {
+        asm volatile("fence.proxy.async;" ::: "memory");
+        mbar_arrive_expect_tx(bar, (uint32_t)rows * 128u);
+        bulk_g2s(c.sm + MegaSmem::kv + (c.grp * 2 + (seq & 1u)) * MG_TK * 128, src, (uint32_t)rows * 128u, bar);
+    } else {
+        mbar_arrive(bar);   // nothing to copy: complete the phase by hand
+    }
+}
+// prefetch the first two tiles; call (by every thread of the group) well before attend_run
+__device__ __forceinline__ void attend_arm(const MegaCtx& c, const float* Kb, const float* Vb, int nglobal, bool extra) {
+    const int nkeys = nglobal + (extra ? 1 : 0);
+    const int ntiles = (nkeys + MG_TK - 1) / MG_TK;
+    if (c.gtid == 0) {
+        kv_issue(c, Kb, Vb, nglobal, ntiles, 0, c.kv_seq);
+        kv_issue(c, Kb, Vb, nglobal, ntiles, 1, c.kv_seq + 1);
+    }
+}
+// single-query attention of head c.h for the group's row g (q/k/v of the row in qkv smem); the context
+// slice is written into every CTA of the cluster.  nglobal keys come from global memory; with `extra`
+// the row's freshly computed key/value is appended as key index nglobal.
+__device__ void attend_run(MegaCtx& c, int g, const float* Kb, const float* Vb, int nglobal, bool extra) {
+    float* scores = reinterpret_cast<float*>(c.sm + MegaSmem::scores) + c.grp * 1024;
+    float* red = reinterpret_cast<float*>(c.sm + MegaSmem::red) + c.grp * 256;
     const float* qs = reinterpret_cast<const float*>(c.sm + MegaSmem::qkv) + g * 32;
     const float* ks = reinterpret_cast<const float*>(c.sm + MegaSmem::qkv) + (MG_GMAX + g) * 32;
     const float* vs = reinterpret_cast<const float*>(c.sm + MegaSmem::qkv) + (2 * MG_GMAX + g) * 32;
     const int nkeys = nglobal + (extra ? 1 : 0);
     const int ntiles = (nkeys + MG_TK - 1) / MG_TK;
-
-    auto issue = [&](int i, uint32_t seq) {
-        const int tile = (i < ntiles) ? i : i - ntiles;
-        const float* src = ((i < ntiles) ? Kb : Vb) + (size_t)tile * MG_TK * 32;
-        const int rows = min(MG_TK, nglobal - tile * MG_TK);
-        if (rows > 0) {
-            fence_proxy_async();
-            mbar_arrive_expect_tx(&c.kvbar[seq & 1u], (uint32_t)rows * 128u);
-            bulk_g2s(c.sm + MegaSmem::kv + (seq & 1u) * MG_TK * 128, src, (uint32_t)rows * 128u, &c.kvbar[seq & 1u]);
-        } else {
-            mbar_arrive(&c.kvbar[seq & 1u]);   // nothing to copy: complete the phase by hand
-        }
-    };
-    if (c.tid == 0) issue(0, c.kv_seq);
     float acc = 0.f;
     for (int i = 0; i < 2 * ntiles; ++i) {
         const uint32_t seq = c.kv_seq + (uint32_t)i;
-        if (c.tid == 0 && i + 1 < 2 * ntiles) issue(i + 1, seq + 1);
-        mbar_wait(&c.kvbar[seq & 1u], (seq >> 1) & 1u);
-        float* tb = reinterpret_cast<float*>(c.sm + MegaSmem::kv + (seq & 1u) * MG_TK * 128);
+        mbar_wait(&c.kvbar[c.grp * 2 + (seq & 1u)], (seq >> 1) & 1u);
+        float* tb = reinterpret_cast<float*>(c.sm + MegaSmem::kv + (c.grp * 2 + (seq & 1u)) * MG_TK * 128);
         const int tile = (i < ntiles) ? i : i - ntiles;
         const int nk = min(MG_TK, nkeys - tile * MG_TK);
-        // the freshly computed key/value of this position lives only in shared memory: drop it in place
         if (extra && tile == ntiles - 1) {
-            if (c.tid < 32) tb[(nkeys - 1 - tile * MG_TK) * 32 + c.tid] = (i < ntiles) ? ks[c.tid] : vs[c.tid];
-            compute_sync();
+            if (c.gtid < 32) tb[(nkeys - 1 - tile * MG_TK) * 32 + c.gtid] = (i < ntiles) ? ks[c.gtid] : vs[c.gtid];
+            group_sync(c);
         }
         if (i < ntiles) {
-            for (int j = c.tid; j < nk; j += MG_COMPUTE_THREADS) {
+            for (int j = c.gtid; j < nk; j += 128) {
                 const float4* kr = reinterpret_cast<const float4*>(tb + j * 32);
                 float s = 0.f;
 #pragma unroll
@@ -255,44 +277,40 @@ __device__ void attend(MegaCtx& c, int g, const float* Kb, const float* Vb, int 
             }
         } else {
             if (i == ntiles) {
-                compute_sync();
+                group_sync(c);
                 float m = -INFINITY;
-                for (int j = c.tid; j < nkeys; j += MG_COMPUTE_THREADS) m = fmaxf(m, scores[j]);
+                for (int j = c.gtid; j < nkeys; j += 128) m = fmaxf(m, scores[j]);
                 m = warp_max(m);
-                if (c.lane == 0) red[c.warp] = m;
-                compute_sync();
-                m = red[0];
-#pragma unroll
-                for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
-                compute_sync();
+                if (c.lane == 0) red[c.gwarp] = m;
+                group_sync(c);
+                m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+                group_sync(c);
                 float sum = 0.f;
-                for (int j = c.tid; j < nkeys; j += MG_COMPUTE_THREADS) {
+                for (int j = c.gtid; j < nkeys; j += 128) {
                     const float e = expf(scores[j] - m);
                     scores[j] = e;
                     sum += e;
                 }
                 sum = warp_sum(sum);
-                if (c.lane == 0) red[c.warp] = sum;
-                compute_sync();
-                sum = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
-                for (int j = c.tid; j < nkeys; j += MG_COMPUTE_THREADS) scores[j] = scores[j] / sum;
-                compute_sync();
+                if (c.lane == 0) red[c.gwarp] = sum;
+                group_sync(c);
+                sum = (red[0] + red[1]) + (red[2] + red[3]);
+                for (int j = c.gtid; j < nkeys; j += 128) scores[j] = scores[j] / sum;
+                group_sync(c);
             }
             const float* ps = scores + tile * MG_TK;
-            for (int j = c.warp; j < nk; j += 8) acc = fmaf(ps[j], tb[j * 32 + c.lane], acc);
+            for (int j = c.gwarp; j < nk; j += 4) acc = fmaf(ps[j], tb[j * 32 + c.lane], acc);
         }
-        compute_sync();   // tile consumed
+        group_sync(c);   // tile consumed: refill its buffer with tile i + 2
+        if (c.gtid == 0 && i + 2 < 2 * ntiles) kv_issue(c, Kb, Vb, nglobal, ntiles, i + 2, seq + 2);
     }
     c.kv_seq += (uint32_t)(2 * ntiles);
-    red[c.warp * 32 + c.lane] = acc;
-    compute_sync();
-    if (c.warp == 0) {
-        float v = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) v += red[w * 32 + c.lane];
+    red[c.gwarp * 32 + c.lane] = acc;
+    group_sync(c);
+    if (c.gwarp == 0) {
+        const float v = (red[c.lane] + red[32 + c.lane]) + (red[64 + c.lane] + red[96 + c.lane]);
         bcast_store(c, MegaSmem::ctxbuf + (g * 256 + c.h * 32 + c.lane) * 4, v);
     }
-    compute_sync();
 }
 
 __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) {
@@ -309,19 +327,21 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(MG_THREADS, 1) decod
     const int row0 = cluster * a.G;
     c.G = min(a.G, a.B - row0);
     c.tile_seq = 0; c.kv_seq = 0; c.x_seq = 0;
+    c.grp = (c.warp >> 2) & 1; c.gtid = c.tid & 127; c.gwarp = c.warp & 3;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + MegaSmem::misc);
-    c.full = bars; c.empty = bars + MG_RING; c.kvbar = bars + 2 * MG_RING; c.pbar = c.kvbar + 2;
-    c.xbar = c.pbar + 2; c.stepbar = c.xbar + 1;
+    c.full = bars; c.empty = bars + MG_RING; c.kvbar = bars + 2 * MG_RING; c.pbar = c.kvbar + 4;
+    c.xbar = c.pbar + 2; c.stepbar = c.xbar + 2;
     int* s_tok = reinterpret_cast<int*>(c.stepbar + 1);      // [G]
     int* s_fin = s_tok + MG_GMAX;                             // [G]
     int* s_rank = s_fin + MG_GMAX;                            // [G]
     int* s_go = s_rank + MG_GMAX;                             // producer: continue flag
 
     if (c.tid == 0) {
-        for (int i = 0; i < MG_RING; ++i) { mbar_init(&c.full[i], 1); mbar_init(&c.empty[i], 1); }
-        mbar_init(&c.kvbar[0], 1); mbar_init(&c.kvbar[1], 1);
+        for (int i = 0; i < MG_RING; ++i) { mbar_init(&c.full[i], 1); mbar_init(&c.empty[i], 8); }
+        for (int i = 0; i < 4; ++i) mbar_init(&c.kvbar[i], 1);
         mbar_init(&c.pbar[0], 1); mbar_init(&c.pbar[1], 1);
-        mbar_init(c.xbar, 8);
+        mbar_init(&c.xbar[0], 1);
+        mbar_init(&c.xbar[1], 1);
         mbar_init(c.stepbar, 1);
         fence_barrier_init();
         for (int g = 0; g < MG_GMAX; ++g) { s_tok[g] = a.g.sos; s_fin[g] = (g < c.G) ? 0 : 1; s_rank[g] = 0; }
@@ -329,7 +349,7 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(MG_THREADS, 1) decod
     }
     for (int i = c.tid; i < 768; i += MG_THREADS) reinterpret_cast<float*>(sm + MegaSmem::finalp)[i] = a.finalp[i];
 #pragma unroll
-    for (uint32_t d = 0; d < 8; ++d) c.xbar_remote[d] = mapa_u32(smem_u32(c.xbar), d);
+    for (uint32_t d = 0; d < 8; ++d) c.xbar_remote[d] = mapa_u32(smem_u32(&c.xbar[0]), d);
     // every CTA's barriers must be initialised before anyone arrives remotely
     cluster_sync_all();
 
@@ -385,10 +405,14 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(MG_THREADS, 1) decod
         const float* fp = reinterpret_cast<const float*>(sm + MegaSmem::finalp);
         uint32_t pseq = 0;
         int t = 0;
+        int pm = 0;
+#define MG_MARK() do { if (a.prof && t == 100 && blockIdx.x == 0 && c.tid == 0 && pm < 64) a.prof[pm++] = clock64(); } while (0)
         for (;; ++t) {
+            MG_MARK();
             // ---- is there anything left to do in this cluster? ----
-            bool any = false;
-            for (int g = 0; g < c.G; ++g) any = any || (s_fin[g] == 0);
+            int n_alive = 0;
+            for (int g = 0; g < c.G; ++g) n_alive += (s_fin[g] == 0) ? 1 : 0;
+            const bool any = n_alive > 0;
             if (c.tid == 0) {
                 *reinterpret_cast<volatile int*>(s_go) = any ? 1 : 0;
                 __threadfence_block();
@@ -413,6 +437,7 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(MG_THREADS, 1) decod
                 }
             }
             compute_sync();
+            MG_MARK();
             // ---- embedding: x = emb[tok] * 16 + pe[rank]  (Embeddings / PositionalEncoding) ----
             for (int i = c.tid; i < c.G * 256; i += MG_COMPUTE_THREADS) {
                 const int g = i >> 8, d = i & 255;
@@ -420,23 +445,33 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(MG_THREADS, 1) decod
             }
             compute_sync();
 
+            MG_MARK();
             for (int l = 0; l < MNX_DEC_L; ++l) {
+                if (l == 1) MG_MARK();
                 mbar_wait(&c.pbar[pseq & 1u], (pseq >> 1) & 1u);
                 const float* P = reinterpret_cast<const float*>(sm + MegaSmem::params + (pseq & 1u) * MG_PARAM_FLOATS * 4);
                 ++pseq;
                 float* Kc = a.selfK + l * kv_layer;
                 float* Vc = a.selfV + l * kv_layer;
                 // ---------- self attention ----------
+                // K/V tiles of positions < t are final: start staging them now, they land during LN1 + QKV
+                const bool my_row = (c.grp < c.G) && (s_fin[c.grp] == 0);
+                const float* sKb = Kc + ((size_t)(row0 + c.grp) * 8 + c.h) * a.T * 32;
+                const float* sVb = Vc + ((size_t)(row0 + c.grp) * 8 + c.h) * a.T * 32;
+                if (my_row) attend_arm(c, sKb, sVb, t, true);
                 layer_norm_rows(c, P + P_LN1W, P + P_LN1B);
-#pragma unroll 1
-                for (int which = 0; which < 3; ++which) {
-                    float acc[MG_GMAX] = {0.f, 0.f, 0.f, 0.f};
-                    const float* tile = tile_acquire(c);
-                    tile_fma(c, tile, nbuf, 256, 0, acc);
-                    const float v = tile_reduce(c, acc);
-                    tile_release(c);
-                    if (c.warp < c.G) {
-                        const int g = c.warp;
+                if (l == 1) MG_MARK();
+                {
+                    float acc[3][MG_GMAX] = {};
+#pragma unroll
+                    for (int which = 0; which < 3; ++which) {
+                        const float* tile = tile_acquire(c);
+                        tile_fma(c, tile, nbuf, 256, 0, acc[which]);
+                        tile_release(c);
+                    }
+                    const float v = tile_reduce<3>(c, acc);
+                    if (c.warp < 3 * c.G) {
+                        const int which = c.warp / c.G, g = c.warp % c.G;
                         const float o = v + P[P_BQ + which * 32 + c.lane];
                         if (which == 0) {
                             qkv[g * 32 + c.lane] = o / MG_QSCALE;
@@ -450,95 +485,114 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(MG_THREADS, 1) decod
                     }
                 }
                 compute_sync();
-                for (int g = 0; g < c.G; ++g) {
-                    if (s_fin[g]) continue;                        // uniform across the cluster
-                    attend(c, g, Kc + ((size_t)(row0 + g) * 8 + c.h) * a.T * 32, Vc + ((size_t)(row0 + g) * 8 + c.h) * a.T * 32, t, true);
+                if (l == 1) MG_MARK();
+                const size_t coff = (((size_t)l * a.B + row0 + c.grp) * 8 + c.h) * (size_t)a.S * 32;
+                if (my_row) {
+                    attend_run(c, c.grp, sKb, sVb, t, true);
+                    // buffers are free again: stage the memory-bank K/V for the context attention right away
+                    group_sync(c);
+                    attend_arm(c, a.crossK + coff, a.crossV + coff, a.S, false);
                 }
-                exchange_sync(c);                                  // ctx complete everywhere
+                if (l == 1) MG_MARK();
+                exchange_sync(c, (uint32_t)n_alive * 128u);         // ctx complete everywhere
+                if (l == 1) MG_MARK();
                 {   // final_linear slice + residual -> x1
-                    float acc[MG_GMAX] = {0.f, 0.f, 0.f, 0.f};
+                    float acc[1][MG_GMAX] = {};
                     const float* tile = tile_acquire(c);
-                    tile_fma(c, tile, ctxbuf, 256, 0, acc);
-                    const float v = tile_reduce(c, acc);
+                    tile_fma(c, tile, ctxbuf, 256, 0, acc[0]);
                     tile_release(c);
+                    const float v = tile_reduce<1>(c, acc);
                     if (c.warp < c.G) {
                         const int col = c.h * 32 + c.lane;
                         bcast_store(c, MegaSmem::xbuf + (c.warp * 256 + col) * 4, (v + P[P_BO + c.lane]) + xbuf[c.warp * 256 + col]);
                     }
                 }
-                exchange_sync(c);                                  // x1 complete everywhere
+                if (l == 1) MG_MARK();
+                exchange_sync(c, (uint32_t)c.G * 128u);             // x1 complete everywhere
+                if (l == 1) MG_MARK();
                 // ---------- context attention ----------
                 layer_norm_rows(c, P + P_LN2W, P + P_LN2B);
                 {
-                    float acc[MG_GMAX] = {0.f, 0.f, 0.f, 0.f};
+                    float acc[1][MG_GMAX] = {};
                     const float* tile = tile_acquire(c);
-                    tile_fma(c, tile, nbuf, 256, 0, acc);
-                    const float v = tile_reduce(c, acc);
+                    tile_fma(c, tile, nbuf, 256, 0, acc[0]);
                     tile_release(c);
+                    const float v = tile_reduce<1>(c, acc);
                     if (c.warp < c.G) qkv[c.warp * 32 + c.lane] = (v + P[P_BQC + c.lane]) / MG_QSCALE;
                 }
                 compute_sync();
-                for (int g = 0; g < c.G; ++g) {
-                    if (s_fin[g]) continue;
-                    const size_t off = (((size_t)l * a.B + row0 + g) * 8 + c.h) * (size_t)a.S * 32;
-                    attend(c, g, a.crossK + off, a.crossV + off, a.S, false);
-                }
-                exchange_sync(c);
+                if (l == 1) MG_MARK();
+                if (my_row) attend_run(c, c.grp, a.crossK + coff, a.crossV + coff, a.S, false);
+                if (l == 1) MG_MARK();
+                exchange_sync(c, (uint32_t)n_alive * 128u);
+                if (l == 1) MG_MARK();
                 {
-                    float acc[MG_GMAX] = {0.f, 0.f, 0.f, 0.f};
+                    float acc[1][MG_GMAX] = {};
                     const float* tile = tile_acquire(c);
-                    tile_fma(c, tile, ctxbuf, 256, 0, acc);
-                    const float v = tile_reduce(c, acc);
+                    tile_fma(c, tile, ctxbuf, 256, 0, acc[0]);
                     tile_release(c);
+                    const float v = tile_reduce<1>(c, acc);
                     if (c.warp < c.G) {
                         const int col = c.h * 32 + c.lane;
                         bcast_store(c, MegaSmem::xbuf + (c.warp * 256 + col) * 4, (v + P[P_BOC + c.lane]) + xbuf[c.warp * 256 + col]);
                     }
                 }
-                exchange_sync(c);                                  // x2
+                if (l == 1) MG_MARK();
+                exchange_sync(c, (uint32_t)c.G * 128u);             // x2
+                if (l == 1) MG_MARK();
                 // ---------- feed forward ----------
                 layer_norm_rows(c, P + P_LNFW, P + P_LNFB);
-#pragma unroll 1
-                for (int j = 0; j < 4; ++j) {
-                    float acc[MG_GMAX] = {0.f, 0.f, 0.f, 0.f};
-                    const float* tile = tile_acquire(c);
-                    tile_fma(c, tile, nbuf, 256, 0, acc);
-                    const float v = tile_reduce(c, acc);
-                    tile_release(c);
-                    if (c.warp < c.G)
-                        bcast_store(c, MegaSmem::hbuf + (c.warp * 1024 + c.h * 128 + j * 32 + c.lane) * 4,
-                                    gelu_erf(v + P[P_B1 + j * 32 + c.lane]));
-                }
-                exchange_sync(c);                                  // FFN hidden complete
                 {
-                    float acc[MG_GMAX] = {0.f, 0.f, 0.f, 0.f};
+                    float acc[4][MG_GMAX] = {};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float* tile = tile_acquire(c);
+                        tile_fma(c, tile, nbuf, 256, 0, acc[j]);
+                        tile_release(c);
+                    }
+                    const float v = tile_reduce<4>(c, acc);
+                    if (c.warp < 4 * c.G) {
+                        const int j = c.warp / c.G, g = c.warp % c.G;
+                        bcast_store(c, MegaSmem::hbuf + (g * 1024 + c.h * 128 + j * 32 + c.lane) * 4,
+                                    gelu_erf(v + P[P_B1 + j * 32 + c.lane]));
+                    }
+                }
+                if (l == 1) MG_MARK();
+                exchange_sync(c, (uint32_t)c.G * 512u);             // FFN hidden complete
+                if (l == 1) MG_MARK();
+                {
+                    float acc[1][MG_GMAX] = {};
 #pragma unroll 1
                     for (int j = 0; j < 4; ++j) {
                         const float* tile = tile_acquire(c);
-                        tile_fma(c, tile, hbuf, 1024, 256 * j, acc);
-                        compute_sync();
+                        tile_fma(c, tile, hbuf, 1024, 256 * j, acc[0]);
                         tile_release(c);
                     }
-                    const float v = tile_reduce(c, acc);
+                    const float v = tile_reduce<1>(c, acc);
                     if (c.warp < c.G) {
                         const int col = c.h * 32 + c.lane;
                         bcast_store(c, MegaSmem::xbuf + (c.warp * 256 + col) * 4, (v + P[P_B2 + c.lane]) + xbuf[c.warp * 256 + col]);
                     }
                 }
-                exchange_sync(c);                                  // x3 = layer output
+                if (l == 1) MG_MARK();
+                exchange_sync(c, (uint32_t)c.G * 128u);             // x3 = layer output
+                if (l == 1) MG_MARK();
             }
+            MG_MARK();
             // ---------- final LayerNorm, vocabulary slice, all-gather of the logits ----------
             layer_norm_rows(c, fp, fp + 256);
             {
-                float acc[MG_GMAX] = {0.f, 0.f, 0.f, 0.f};
+                float acc[1][MG_GMAX] = {};
                 const float* tile = tile_acquire(c);
-                tile_fma(c, tile, nbuf, 256, 0, acc);
-                const float v = tile_reduce(c, acc);
+                tile_fma(c, tile, nbuf, 256, 0, acc[0]);
                 tile_release(c);
+                const float v = tile_reduce<1>(c, acc);
                 if (c.warp < c.G)
                     bcast_store(c, MegaSmem::lgbuf + (c.warp * 256 + c.h * 32 + c.lane) * 4, v + fp[512 + c.h * 32 + c.lane]);
             }
-            exchange_sync(c);
+            MG_MARK();
+            exchange_sync(c, (uint32_t)c.G * 128u);
+            MG_MARK();
             // ---------- log_softmax, grammar mask, argmax: warp g decides row g (identically in every CTA) ----------
             if (c.warp < c.G && s_fin[c.warp] == 0) {
                 const int g = c.warp, row = row0 + g;

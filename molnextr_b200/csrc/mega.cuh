@@ -7,7 +7,7 @@ namespace mnx {
 #define MG_TILE_FLOATS_H (256 * 32)
 #define MG_TILES_PER_LAYER_H 14
 #define MG_PARAM_FLOATS_H 1920
-#define MG_GMAX_H 4
+#define MG_GMAX_H 2
 
 struct MegaArgs {
     const float* wpack;
@@ -26,6 +26,7 @@ struct MegaArgs {
     int* lens;
     unsigned int* row_state;
     int* steps_run;
+    long long* prof;        // optional [64] cycle stamps of cluster 0 / CTA 0 at step 100 (nullptr = off)
     Grammar g;
 };
 
