@@ -21,13 +21,13 @@ namespace mnx {
 
 #define MG_COMPUTE_THREADS 256
 #define MG_THREADS 288            // + 1 producer warp
-#define MG_GMAX 2
+#define MG_GMAX 4
 #define MG_TILE_FLOATS (256 * 32)
 #define MG_TILE_BYTES (MG_TILE_FLOATS * 4)
 #define MG_RING 3
 #define MG_TILES_PER_LAYER 14
 #define MG_PARAM_FLOATS 1920      // 1888 used, padded to a multiple of 32 floats
-#define MG_TK 144                 // keys per staged K/V tile (= S at 384x384)
+#define MG_TK 72                  // keys per staged K/V tile (two tiles cover S = 144 at 384x384)
 #define MG_QSCALE 5.656854152679443f
 
 // tile ids inside a layer
@@ -40,19 +40,26 @@ enum { P_LN1W = 0, P_LN1B = 256, P_LN2W = 512, P_LN2B = 768, P_LNFW = 1024, P_LN
 struct MegaSmem {
     static constexpr int ring = 0;
     static constexpr int kv = ring + MG_RING * MG_TILE_BYTES;                 // 98304
-    static constexpr int params = kv + 4 * MG_TK * 128;                        // 2 row groups x 2 buffers
+    // K/V staging: 4 row groups x 2 buffers x 72 keys.  The FFN hidden activations alias this area
+    // (no attention tile is in flight between the x2 and x3 exchanges of a layer).
+    static constexpr int hbuf = kv;
+    static constexpr int params = kv + 8 * MG_TK * 128;                        // +73728
     static constexpr int finalp = params + 2 * MG_PARAM_FLOATS * 4;            // +15360
     static constexpr int xbuf = finalp + 768 * 4;
     static constexpr int nbuf = xbuf + MG_GMAX * 256 * 4;
     static constexpr int ctxbuf = nbuf + MG_GMAX * 256 * 4;
-    static constexpr int hbuf = ctxbuf + MG_GMAX * 256 * 4;
-    static constexpr int lgbuf = hbuf + MG_GMAX * 1024 * 4;
+    static constexpr int lgbuf = ctxbuf + MG_GMAX * 256 * 4;
     static constexpr int qkv = lgbuf + MG_GMAX * 256 * 4;                      // q,k,v [G][32] each
-    static constexpr int scores = qkv + 3 * MG_GMAX * 32 * 4;
-    static constexpr int red = scores + 2 * 1024 * 4;                          // scores: one row per group
-    static constexpr int misc = red + 4 * 8 * MG_GMAX * 32 * 4;               // red: [4 sets][8 warps][G][32]
+    // GEMM cross-warp reduction scratch [4 sets][8 warps][G][32]; the attention scores (one 1024-float
+    // row per group) alias it -- the two are never live at the same time.
+    static constexpr int red = qkv + 3 * MG_GMAX * 32 * 4;
+    static constexpr int scores = red;
+    static constexpr int ared = red + 4 * 8 * MG_GMAX * 32 * 4;               // attention scratch [4 groups][64]
+    static constexpr int misc = ared + 4 * 64 * 4;
     static constexpr int total = misc + 512;
 };
+static_assert(MegaSmem::total <= 232448, "shared memory budget exceeded");
+static_assert(MG_GMAX * 1024 * 4 <= 8 * MG_TK * 128, "FFN hidden does not fit in the K/V staging area");
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t cta) {
     uint32_t r;
@@ -142,10 +149,10 @@ __device__ __forceinline__ void tile_fma(const MegaCtx& c, const float* tile, co
         }
     }
 }
-// cross-warp reduction of the 8 k-splits of NS accumulator sets at once.  Warp w < NS*G then holds,
-// in lane c, the complete dot product of set (w / G), row (w % G), column c.  Two compute_syncs.
-template <int NS>
-__device__ __forceinline__ float tile_reduce(const MegaCtx& c, const float (&acc)[NS][MG_GMAX]) {
+// cross-warp reduction of the 8 k-splits of NS accumulator sets at once, then f(set, row, value) is
+// called by one warp per (set, row) pair with lane = output column.  Two compute_syncs.
+template <int NS, class F>
+__device__ __forceinline__ void reduce_apply(const MegaCtx& c, const float (&acc)[NS][MG_GMAX], F f) {
     float* red = reinterpret_cast<float*>(c.sm + MegaSmem::red);
 #pragma unroll
     for (int s = 0; s < NS; ++s)
@@ -153,14 +160,14 @@ __device__ __forceinline__ float tile_reduce(const MegaCtx& c, const float (&acc
         for (int g = 0; g < MG_GMAX; ++g)
             if (g < c.G) red[((s * 8 + c.warp) * MG_GMAX + g) * 32 + c.lane] = acc[s][g];
     compute_sync();
-    float v = 0.f;
-    if (c.warp < NS * c.G) {
-        const int s = c.warp / c.G, g = c.warp % c.G;
+    for (int idx = c.warp; idx < NS * c.G; idx += 8) {
+        const int s = idx / c.G, g = idx - s * c.G;
+        float v = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) v += red[((s * 8 + w) * MG_GMAX + g) * 32 + c.lane];
+        f(s, g, v);
     }
     compute_sync();
-    return v;
 }
 
 // write one float into the same shared-memory location of all 8 CTAs of the cluster.  The store is
@@ -211,9 +218,9 @@ __device__ __forceinline__ void layer_norm_rows(const MegaCtx& c, const float* w
     compute_sync();
 }
 
-// ---- attention: row g of the cluster is handled by thread group g (128 threads = 4 warps) ----------
+// ---- attention: row g of the cluster is handled by thread group g (64 threads = 2 warps) ------------
 __device__ __forceinline__ void group_sync(const MegaCtx& c) {
-    asm volatile("bar.sync %0, 128;" ::"r"(2 + c.grp) : "memory");
+    asm volatile("bar.sync %0, 64;" ::"r"(2 + c.grp) : "memory");
 }
 // stage tile i of the sequence K0..K(n-1), V0..V(n-1) of this group's row into buffer (seq & 1)
 __device__ __forceinline__ void kv_issue(const MegaCtx& c, const float* Kb, const float* Vb, int nglobal, int ntiles,
@@ -244,7 +251,7 @@ __device__ __forceinline__ void attend_arm(const MegaCtx& c, const float* Kb, co
 // the row's freshly computed key/value is appended as key index nglobal.
 __device__ void attend_run(MegaCtx& c, int g, const float* Kb, const float* Vb, int nglobal, bool extra) {
     float* scores = reinterpret_cast<float*>(c.sm + MegaSmem::scores) + c.grp * 1024;
-    float* red = reinterpret_cast<float*>(c.sm + MegaSmem::red) + c.grp * 256;
+    float* ared = reinterpret_cast<float*>(c.sm + MegaSmem::ared) + c.grp * 64;
     const float* qs = reinterpret_cast<const float*>(c.sm + MegaSmem::qkv) + g * 32;
     const float* ks = reinterpret_cast<const float*>(c.sm + MegaSmem::qkv) + (MG_GMAX + g) * 32;
     const float* vs = reinterpret_cast<const float*>(c.sm + MegaSmem::qkv) + (2 * MG_GMAX + g) * 32;
@@ -262,7 +269,7 @@ __device__ void attend_run(MegaCtx& c, int g, const float* Kb, const float* Vb, 
             group_sync(c);
         }
         if (i < ntiles) {
-            for (int j = c.gtid; j < nk; j += 128) {
+            for (int j = c.gtid; j < nk; j += 64) {
                 const float4* kr = reinterpret_cast<const float4*>(tb + j * 32);
                 float s = 0.f;
 #pragma unroll
@@ -277,40 +284,33 @@ __device__ void attend_run(MegaCtx& c, int g, const float* Kb, const float* Vb, 
             }
         } else {
             if (i == ntiles) {
+                // softmax over all keys by the group's first warp (shuffles only), p = exp(s - max) / sum
                 group_sync(c);
-                float m = -INFINITY;
-                for (int j = c.gtid; j < nkeys; j += 128) m = fmaxf(m, scores[j]);
-                m = warp_max(m);
-                if (c.lane == 0) red[c.gwarp] = m;
-                group_sync(c);
-                m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-                group_sync(c);
-                float sum = 0.f;
-                for (int j = c.gtid; j < nkeys; j += 128) {
-                    const float e = expf(scores[j] - m);
-                    scores[j] = e;
-                    sum += e;
+                if (c.gwarp == 0) {
+                    float m = -INFINITY;
+                    for (int j = c.lane; j < nkeys; j += 32) m = fmaxf(m, scores[j]);
+                    m = warp_max(m);
+                    float sum = 0.f;
+                    for (int j = c.lane; j < nkeys; j += 32) {
+                        const float e = expf(scores[j] - m);
+                        scores[j] = e;
+                        sum += e;
+                    }
+                    sum = warp_sum(sum);
+                    for (int j = c.lane; j < nkeys; j += 32) scores[j] = scores[j] / sum;
                 }
-                sum = warp_sum(sum);
-                if (c.lane == 0) red[c.gwarp] = sum;
-                group_sync(c);
-                sum = (red[0] + red[1]) + (red[2] + red[3]);
-                for (int j = c.gtid; j < nkeys; j += 128) scores[j] = scores[j] / sum;
                 group_sync(c);
             }
             const float* ps = scores + tile * MG_TK;
-            for (int j = c.gwarp; j < nk; j += 4) acc = fmaf(ps[j], tb[j * 32 + c.lane], acc);
+            for (int j = c.gwarp; j < nk; j += 2) acc = fmaf(ps[j], tb[j * 32 + c.lane], acc);
         }
         group_sync(c);   // tile consumed: refill its buffer with tile i + 2
         if (c.gtid == 0 && i + 2 < 2 * ntiles) kv_issue(c, Kb, Vb, nglobal, ntiles, i + 2, seq + 2);
     }
     c.kv_seq += (uint32_t)(2 * ntiles);
-    red[c.gwarp * 32 + c.lane] = acc;
+    ared[c.gwarp * 32 + c.lane] = acc;
     group_sync(c);
-    if (c.gwarp == 0) {
-        const float v = (red[c.lane] + red[32 + c.lane]) + (red[64 + c.lane] + red[96 + c.lane]);
-        bcast_store(c, MegaSmem::ctxbuf + (g * 256 + c.h * 32 + c.lane) * 4, v);
-    }
+    if (c.gwarp == 0) bcast_store(c, MegaSmem::ctxbuf + (g * 256 + c.h * 32 + c.lane) * 4, ared[c.lane] + ared[32 + c.lane]);
 }
 
 __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) {
@@ -327,9 +327,9 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(MG_THREADS, 1) decod
     const int row0 = cluster * a.G;
     c.G = min(a.G, a.B - row0);
     c.tile_seq = 0; c.kv_seq = 0; c.x_seq = 0;
-    c.grp = (c.warp >> 2) & 1; c.gtid = c.tid & 127; c.gwarp = c.warp & 3;
+    c.grp = (c.warp >> 1) & 3; c.gtid = c.tid & 63; c.gwarp = c.warp & 1;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + MegaSmem::misc);
-    c.full = bars; c.empty = bars + MG_RING; c.kvbar = bars + 2 * MG_RING; c.pbar = c.kvbar + 4;
+    c.full = bars; c.empty = bars + MG_RING; c.kvbar = bars + 2 * MG_RING; c.pbar = c.kvbar + 8;
     c.xbar = c.pbar + 2; c.stepbar = c.xbar + 2;
     int* s_tok = reinterpret_cast<int*>(c.stepbar + 1);      // [G]
     int* s_fin = s_tok + MG_GMAX;                             // [G]
@@ -338,7 +338,7 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(MG_THREADS, 1) decod
 
     if (c.tid == 0) {
         for (int i = 0; i < MG_RING; ++i) { mbar_init(&c.full[i], 1); mbar_init(&c.empty[i], 8); }
-        for (int i = 0; i < 4; ++i) mbar_init(&c.kvbar[i], 1);
+        for (int i = 0; i < 8; ++i) mbar_init(&c.kvbar[i], 1);
         mbar_init(&c.pbar[0], 1); mbar_init(&c.pbar[1], 1);
         mbar_init(&c.xbar[0], 1);
         mbar_init(&c.xbar[1], 1);
@@ -469,9 +469,7 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(MG_THREADS, 1) decod
                         tile_fma(c, tile, nbuf, 256, 0, acc[which]);
                         tile_release(c);
                     }
-                    const float v = tile_reduce<3>(c, acc);
-                    if (c.warp < 3 * c.G) {
-                        const int which = c.warp / c.G, g = c.warp % c.G;
+                    reduce_apply<3>(c, acc, [&](int which, int g, float v) {
                         const float o = v + P[P_BQ + which * 32 + c.lane];
                         if (which == 0) {
                             qkv[g * 32 + c.lane] = o / MG_QSCALE;
@@ -482,7 +480,7 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(MG_THREADS, 1) decod
                                 dst[(((size_t)(row0 + g) * 8 + c.h) * a.T + t) * 32 + c.lane] = o;
                             }
                         }
-                    }
+                    });
                 }
                 compute_sync();
                 if (l == 1) MG_MARK();
@@ -501,11 +499,10 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(MG_THREADS, 1) decod
                     const float* tile = tile_acquire(c);
                     tile_fma(c, tile, ctxbuf, 256, 0, acc[0]);
                     tile_release(c);
-                    const float v = tile_reduce<1>(c, acc);
-                    if (c.warp < c.G) {
+                    reduce_apply<1>(c, acc, [&](int, int g, float v) {
                         const int col = c.h * 32 + c.lane;
-                        bcast_store(c, MegaSmem::xbuf + (c.warp * 256 + col) * 4, (v + P[P_BO + c.lane]) + xbuf[c.warp * 256 + col]);
-                    }
+                        bcast_store(c, MegaSmem::xbuf + (g * 256 + col) * 4, (v + P[P_BO + c.lane]) + xbuf[g * 256 + col]);
+                    });
                 }
                 if (l == 1) MG_MARK();
                 exchange_sync(c, (uint32_t)c.G * 128u);             // x1 complete everywhere
@@ -517,8 +514,7 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(MG_THREADS, 1) decod
                     const float* tile = tile_acquire(c);
                     tile_fma(c, tile, nbuf, 256, 0, acc[0]);
                     tile_release(c);
-                    const float v = tile_reduce<1>(c, acc);
-                    if (c.warp < c.G) qkv[c.warp * 32 + c.lane] = (v + P[P_BQC + c.lane]) / MG_QSCALE;
+                    reduce_apply<1>(c, acc, [&](int, int g, float v) { qkv[g * 32 + c.lane] = (v + P[P_BQC + c.lane]) / MG_QSCALE; });
                 }
                 compute_sync();
                 if (l == 1) MG_MARK();
@@ -531,11 +527,10 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(MG_THREADS, 1) decod
                     const float* tile = tile_acquire(c);
                     tile_fma(c, tile, ctxbuf, 256, 0, acc[0]);
                     tile_release(c);
-                    const float v = tile_reduce<1>(c, acc);
-                    if (c.warp < c.G) {
+                    reduce_apply<1>(c, acc, [&](int, int g, float v) {
                         const int col = c.h * 32 + c.lane;
-                        bcast_store(c, MegaSmem::xbuf + (c.warp * 256 + col) * 4, (v + P[P_BOC + c.lane]) + xbuf[c.warp * 256 + col]);
-                    }
+                        bcast_store(c, MegaSmem::xbuf + (g * 256 + col) * 4, (v + P[P_BOC + c.lane]) + xbuf[g * 256 + col]);
+                    });
                 }
                 if (l == 1) MG_MARK();
                 exchange_sync(c, (uint32_t)c.G * 128u);             // x2
@@ -550,12 +545,10 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(MG_THREADS, 1) decod
                         tile_fma(c, tile, nbuf, 256, 0, acc[j]);
                         tile_release(c);
                     }
-                    const float v = tile_reduce<4>(c, acc);
-                    if (c.warp < 4 * c.G) {
-                        const int j = c.warp / c.G, g = c.warp % c.G;
+                    reduce_apply<4>(c, acc, [&](int j, int g, float v) {
                         bcast_store(c, MegaSmem::hbuf + (g * 1024 + c.h * 128 + j * 32 + c.lane) * 4,
                                     gelu_erf(v + P[P_B1 + j * 32 + c.lane]));
-                    }
+                    });
                 }
                 if (l == 1) MG_MARK();
                 exchange_sync(c, (uint32_t)c.G * 512u);             // FFN hidden complete
@@ -568,11 +561,10 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(MG_THREADS, 1) decod
                         tile_fma(c, tile, hbuf, 1024, 256 * j, acc[0]);
                         tile_release(c);
                     }
-                    const float v = tile_reduce<1>(c, acc);
-                    if (c.warp < c.G) {
+                    reduce_apply<1>(c, acc, [&](int, int g, float v) {
                         const int col = c.h * 32 + c.lane;
-                        bcast_store(c, MegaSmem::xbuf + (c.warp * 256 + col) * 4, (v + P[P_B2 + c.lane]) + xbuf[c.warp * 256 + col]);
-                    }
+                        bcast_store(c, MegaSmem::xbuf + (g * 256 + col) * 4, (v + P[P_B2 + c.lane]) + xbuf[g * 256 + col]);
+                    });
                 }
                 if (l == 1) MG_MARK();
                 exchange_sync(c, (uint32_t)c.G * 128u);             // x3 = layer output
@@ -586,9 +578,9 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(MG_THREADS, 1) decod
                 const float* tile = tile_acquire(c);
                 tile_fma(c, tile, nbuf, 256, 0, acc[0]);
                 tile_release(c);
-                const float v = tile_reduce<1>(c, acc);
-                if (c.warp < c.G)
-                    bcast_store(c, MegaSmem::lgbuf + (c.warp * 256 + c.h * 32 + c.lane) * 4, v + fp[512 + c.h * 32 + c.lane]);
+                reduce_apply<1>(c, acc, [&](int, int g, float v) {
+                    bcast_store(c, MegaSmem::lgbuf + (g * 256 + c.h * 32 + c.lane) * 4, v + fp[512 + c.h * 32 + c.lane]);
+                });
             }
             MG_MARK();
             exchange_sync(c, (uint32_t)c.G * 128u);

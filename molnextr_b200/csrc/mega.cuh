@@ -7,7 +7,7 @@ namespace mnx {
 #define MG_TILE_FLOATS_H (256 * 32)
 #define MG_TILES_PER_LAYER_H 14
 #define MG_PARAM_FLOATS_H 1920
-#define MG_GMAX_H 2
+#define MG_GMAX_H 4
 
 struct MegaArgs {
     const float* wpack;
