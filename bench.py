@@ -99,27 +99,62 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_sample(n_enc_images: int, n_dec_steps: int):
-    """Time the CPU oracle on a bounded sample of the workload; returns (images/s scaled to the
-    full batch, description).  Encoder cost is linear in images, decode cost in steps."""
+_CPU_STATE = {}
+
+
+def _cpu_setup():
+    """Checkpoint, inputs and the fastest torch thread counts for the two CPU phases (many-core hosts
+    run the decoder's tiny ops far slower with all threads than with a few: give the baseline its
+    best setting rather than a strawman)."""
+    if _CPU_STATE:
+        return _CPU_STATE
     from molnextr_b200 import synth
     from oracle import restate
-    torch.set_num_threads(os.cpu_count() or 1)
     ck = synth.synthetic_checkpoint(0, "fixed480")
     g = torch.Generator(device="cpu").manual_seed(0)
     x = torch.randn((BATCH, 3, H, W), generator=g)
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (4, 8, 16, 32, 64, ncpu) if c <= ncpu})
+    best_enc, best_dec = (1e30, ncpu), (1e30, ncpu)
     with torch.no_grad():
+        f1 = None
+        for c in cands:
+            torch.set_num_threads(c)
+            t0 = time.perf_counter()
+            f1 = restate.swin_b_features(ck["encoder"], x[:1])
+            best_enc = min(best_enc, (time.perf_counter() - t0, c))
+        feats = f1.repeat(BATCH, 1, 1).contiguous()
+        for c in cands:
+            torch.set_num_threads(c)
+            t0 = time.perf_counter()
+            restate.greedy_decode(ck["decoder"], feats, max_len=6)
+            best_dec = min(best_dec, (time.perf_counter() - t0, c))
+    _CPU_STATE.update(ck=ck, x=x, enc_threads=best_enc[1], dec_threads=best_dec[1], ncpu=ncpu)
+    return _CPU_STATE
+
+
+def cpu_reference_sample(n_enc_images: int, n_dec_steps: int):
+    """Time the CPU oracle on a bounded sample of the workload; returns (images/s scaled to the
+    full batch, description, seconds).  Encoder cost is linear in images, decode cost in steps
+    (an under-estimate for the reference: its per-step cost grows with the KV length)."""
+    from oracle import restate
+    st = _cpu_setup()
+    ck, x = st["ck"], st["x"]
+    with torch.no_grad():
+        torch.set_num_threads(st["enc_threads"])
         t0 = time.perf_counter()
         f_part = restate.swin_b_features(ck["encoder"], x[:n_enc_images])
         t_enc = time.perf_counter() - t0
         feats = f_part.repeat((BATCH + n_enc_images - 1) // n_enc_images, 1, 1)[:BATCH].contiguous()
+        torch.set_num_threads(st["dec_threads"])
         t0 = time.perf_counter()
         restate.greedy_decode(ck["decoder"], feats, max_len=n_dec_steps)
         t_dec = time.perf_counter() - t0
     full = t_enc * (BATCH / n_enc_images) + t_dec * (T_MAX / n_dec_steps)
-    desc = (f"Swin-B encoder on {n_enc_images} of {BATCH} images ({t_enc:.2f} s) + greedy decode of all {BATCH} rows for "
-            f"{n_dec_steps} of {T_MAX} steps ({t_dec:.2f} s), fp32 torch on {torch.get_num_threads()} threads; "
-            f"scaled linearly to the full batch ({full:.1f} s); bond head and tokenizer excluded")
+    desc = (f"Swin-B encoder on {n_enc_images} of {BATCH} images ({t_enc:.2f} s, {st['enc_threads']} threads) + greedy decode "
+            f"of all {BATCH} rows for {n_dec_steps} of {T_MAX} steps ({t_dec:.2f} s, {st['dec_threads']} threads), fp32 torch, "
+            f"thread counts picked as the fastest of a sweep up to {st['ncpu']} cores; scaled linearly to the full batch "
+            f"({full:.1f} s); bond head and tokenizer excluded")
     return BATCH / full, desc, t_enc + t_dec
 
 
@@ -140,7 +175,8 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "note": "reference arm = the CPU oracle port of the reference's PyTorch path "
                    "(no compiled reference exists); each step is a bounded sample scaled to the full batch"},
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": desc},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": max(_CPU_STATE.get("enc_threads", 0), _CPU_STATE.get("dec_threads", 0)),
+                         "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t_all,
     }
@@ -243,7 +279,8 @@ def run_ours(args):
         d2h = BATCH * (MAX_LEN * 4 + 4 + MAX_LEN * 4 + MAX_ATOMS * 4 + 4 + MAX_ATOMS * MAX_ATOMS)
         try:
             cpu_val, cpu_desc, _ = cpu_reference_sample(8, 48)
-            cpu = {"value": cpu_val, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": cpu_desc}
+            cpu = {"value": cpu_val, "unit": "images/s", "cores": max(_CPU_STATE["enc_threads"], _CPU_STATE["dec_threads"]),
+                   "kind": "port", "sample": cpu_desc}
         except Exception as ex:  # the baseline must never take the bench line down
             cpu = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
         line = {

@@ -1,0 +1,82 @@
+"""Host-side mirror of the reference's `Encoder` / `Decoder` modules for the accelerated path
+(MolNexTR/components.py:110-174, :403-492): same constructor shape, same call signatures, same
+return structures -- but every tensor operation happens inside libmolnextr_b200.so."""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from .engine import Engine, MAX_LEN
+from .tokenization import CharTokenizer
+
+FORMAT_INFO = {"chartok_coords": {"max_len": MAX_LEN}}   # MolNexTR/utils.py:12-26 (this format only)
+
+
+class Encoder:
+    """`features, hiddens = encoder(images)`.  `hiddens` (per-stage maps) is returned empty: the
+    reference collects them but no consumer on the inference path reads them."""
+
+    def __init__(self, engine: Engine):
+        self.engine = engine
+        self.n_features = engine.encoder_dim
+
+    def __call__(self, images: torch.Tensor, refs=None):
+        return self.forward(images, refs)
+
+    def forward(self, images: torch.Tensor, refs=None):
+        return self.engine.encode(images), []
+
+
+class Decoder:
+    """`predictions = decoder.decode(features, hiddens)` with the reference's output schema:
+    [{'chartok_coords': {'smiles','symbols','coords','indices'}, 'edges': [[int]]}, ...]
+    (+ 'atom_scores', 'edge_scores', 'overall_score' when compute_confidence is set,
+    components.py:456-469,485-491)."""
+
+    def __init__(self, engine: Engine, tokenizer: Optional[dict] = None, compute_confidence: bool = False):
+        self.engine = engine
+        self.tokenizer = tokenizer or {"chartok_coords": engine.tok}
+        self.formats = ["chartok_coords", "edges"]
+        self.compute_confidence = compute_confidence
+
+    def decode(self, encoder_out: torch.Tensor, hiddens=None, refs=None, beam_size: int = 1, n_best: int = 1) -> List[dict]:
+        if beam_size != 1:
+            raise NotImplementedError("beam search is not runnable in the reference either (SURVEY.md F4); "
+                                      "only greedy decoding is part of the accelerated path")
+        eng = self.engine
+        tok: CharTokenizer = self.tokenizer["chartok_coords"]
+        out = eng.decode_greedy(encoder_out)
+        atom_idx, n_atoms = eng.atom_indices(out["ids"], out["lens"])
+        if self.compute_confidence:
+            edges, escore = eng.edges(atom_idx, n_atoms, return_scores=True)
+            escore = escore.cpu().numpy()
+        else:
+            edges = eng.edges(atom_idx, n_atoms)
+        ids, lens, logp = out["ids"].cpu().numpy(), out["lens"].cpu().numpy(), out["logp"].cpu().numpy()
+        edges, n_atoms = edges.cpu().numpy(), n_atoms.cpu().numpy()
+        atom_idx = atom_idx.cpu().numpy()
+        predictions = []
+        for i in range(ids.shape[0]):
+            L = int(lens[i])
+            seq = ids[i, :L].tolist()
+            ct = tok.sequence_to_smiles(seq)
+            k = len(ct["indices"])
+            if k != int(n_atoms[i]) or ct["indices"] != atom_idx[i, :k].tolist():
+                raise RuntimeError("device atom scan disagrees with the tokenizer")   # never expected
+            pred = {"chartok_coords": ct, "edges": edges[i, :k, :k].astype(int).tolist()}
+            if self.compute_confidence:
+                token_scores = np.exp(logp[i, :L].astype(np.float64))
+                idx = np.array(ct["indices"]) - 3
+                atom_scores = []
+                for symbol, index in zip(ct["symbols"], idx):
+                    s = token_scores[index - len(symbol) + 1:index + 1]
+                    atom_scores.append(float(np.prod(s) ** (1 / len(symbol))))
+                ct["atom_scores"] = atom_scores
+                avg = float(np.exp(np.mean(logp[i, :L].astype(np.float64))))
+                es = escore[i, :k, :k].astype(np.float64)
+                pred["edge_scores"] = es.tolist()
+                pred["overall_score"] = avg * float(np.sqrt(np.prod(es)))
+            predictions.append(pred)
+        return predictions

@@ -1,0 +1,59 @@
+"""CPU: host-side logic that needs no GPU -- the C-ABI library exports, the class table fed to the
+device atom scan, preprocessing, and the loud failure when CUDA is absent."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from molnextr_b200 import _cabi
+from molnextr_b200.engine import token_class_table
+from molnextr_b200.tokenization import CharTokenizer
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "molnextr_b200.h")).read()
+    declared = set(re.findall(r"\b(mnx_[a-z0-9_]+)\s*\(", header))
+    declared.discard("mnx_engine")
+    assert declared == set(_cabi.EXPORTS), declared ^ set(_cabi.EXPORTS)
+    if not os.path.exists(_cabi.LIB_PATH):
+        from molnextr_b200 import build
+        build.build()
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_token_class_table_matches_tokenizer():
+    tok = CharTokenizer(64)
+    tab = token_class_table(tok)
+    assert tab.shape == (229,) and tab[101:].sum() == 0
+    for i in range(101):
+        assert bool(tab[i] & 1) == tok.is_symbol(i)
+        assert bool(tab[i] & 2) == tok.is_atom(i)
+    assert tab[tok.stoi["["]] & 4 and tab[tok.stoi["]"]] & 8
+    assert tab[tok.stoi["C"]] & 16 and tab[tok.stoi["l"]] & 32 and tab[tok.stoi["B"]] & 64 and tab[tok.stoi["r"]] & 128
+
+
+def test_preprocess_shapes_and_crop():
+    from molnextr_b200.preprocess import crop_white, transform
+    img = np.full((200, 300, 3), 255, np.uint8)
+    img[50:120, 80:200] = 0
+    c = crop_white(img)
+    assert c.shape == (70 + 100, 120 + 100, 3)
+    assert (crop_white(np.full((40, 40, 3), 255, np.uint8)).shape == (140, 140, 3))
+    t = transform(img)
+    assert t.shape == (3, 384, 384) and t.dtype == np.float32
+    assert np.allclose(t[0] * 0.229 + 0.485, t[1] * 0.224 + 0.456, atol=1e-5)   # three equal gray channels
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful without a GPU")
+def test_engine_refuses_to_run_without_cuda():
+    from molnextr_b200 import synth
+    from molnextr_b200.engine import Engine, EngineError
+    with pytest.raises(EngineError, match="no CPU fallback"):
+        Engine({"decoder": synth.decoder_state(0), "encoder": None})
