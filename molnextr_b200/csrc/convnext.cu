@@ -1,0 +1,367 @@
+// ConvNeXt-B encoder (dims 128/256/512/1024, depths 3/3/27/3) on sm_100a -- the encoder `north_star`
+// names.  The reference's branch for it (MolNexTR/components.py:121-126,163-166) is dead code
+// (SURVEY.md F2), so the semantics implemented are timm's ConvNeXt `forward_features`:
+//   stem conv4x4/4 + LayerNorm2d | per stage: [LayerNorm2d + conv2x2/2] then blocks of
+//   dwconv7x7 -> LayerNorm(C, eps 1e-6) -> Linear C->4C -> GELU -> Linear 4C->C -> *gamma -> +x.
+//
+// Kernels: dwconv_ln_kernel (7x7 depthwise conv fused with the channel LayerNorm, NHWC fp32 in,
+// bf16 GEMM operand out; input halo tiles arrive by 4-D TMA with out-of-bounds zero fill = the conv's
+// zero padding), downsample_ln_kernel (per-pixel LN + 2x2 patch gather -> bf16), and the shared
+// tcgen05 GEMM (gemm_tc.cu) for fc1 (+GELU), fc2 (+gamma, +residual, in place) and the 2x2 conv.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "encoder.cuh"
+#include "gemm_tc.cuh"
+
+namespace mnx {
+
+cudaError_t launch_patch_embed(const float* img, int B, int H, int W, const float* w, const float* bias,
+                               const float* ln_w, const float* ln_b, float eps, float* x, cudaStream_t s);
+
+static const int CN_DEPTH[4] = {3, 3, 27, 3};
+
+struct CnBlockW {
+    const float *dw_w, *dw_b;        // [49][C] tap-major, [C]
+    const float *ln_w, *ln_b;
+    const __nv_bfloat16 *fc1_w, *fc2_w;
+    const float *fc1_b, *fc2_b, *gamma;
+};
+struct CnDownW {
+    const float *ln_w, *ln_b;        // LayerNorm2d over C_in
+    const __nv_bfloat16* w;          // [C_out][4*C_in], k = (kh*2 + kw)*C_in + c
+    const float* b;
+};
+struct ConvNextState {
+    const float *stem_w, *stem_b, *stem_ln_w, *stem_ln_b;
+    std::vector<CnBlockW> blocks[4];
+    CnDownW down[4];
+    float *x0 = nullptr, *x1 = nullptr;
+    __nv_bfloat16 *abuf = nullptr, *hbuf = nullptr;
+    size_t max_tokens = 0;
+    int last_B = 0, last_H = 0, last_W = 0;
+};
+
+// ------------------------------------------------------------------------------------------
+// depthwise 7x7 (pad 3) + bias + LayerNorm over channels -> bf16
+// One CTA = TILE x TILE output pixels x ALL channels.  Channels are processed 32 at a time (lane =
+// channel): the (TILE+6)^2 x 32 input halo tile of chunk i+1 is fetched by TMA while chunk i is
+// convolved with a register sliding window (one shared-memory read per 4 FMAs); conv outputs stay
+// in shared memory until the whole channel vector of every pixel is known, then each warp
+// normalises its pixels and writes bf16 rows (the fc1 GEMM's A operand).
+// ------------------------------------------------------------------------------------------
+template <int TILE>
+__global__ void __launch_bounds__(TILE * 32) dwconv_ln_kernel(const __grid_constant__ CUtensorMap tmap_x, int H, int W,
+                                                              int C, const float* __restrict__ dw_w,
+                                                              const float* __restrict__ dw_b,
+                                                              const float* __restrict__ ln_w,
+                                                              const float* __restrict__ ln_b, float eps,
+                                                              __nv_bfloat16* __restrict__ out) {
+    constexpr int IN = TILE + 6;
+    constexpr int IN_FLOATS = IN * IN * 32;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    float* in_buf = reinterpret_cast<float*>(sm);                       // [2][IN][IN][32]
+    float* obuf = in_buf + 2 * IN_FLOATS;                               // [TILE*TILE][C]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(obuf + (size_t)TILE * TILE * C);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;        // warp = output row of the tile
+    const int tiles_x = (W + TILE - 1) / TILE;
+    const int b = blockIdx.y;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x % tiles_x;
+    const int y0 = ty * TILE, x0 = tx * TILE;
+    const int nchunks = C / 32;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_barrier_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_x)) : "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int chunk) {
+        uint64_t* bb = &bar[chunk & 1];
+        mbar_arrive_expect_tx(bb, IN_FLOATS * 4);
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+                smem_u32(in_buf + (chunk & 1) * IN_FLOATS)),
+            "l"(reinterpret_cast<uint64_t>(&tmap_x)), "r"(smem_u32(bb)), "r"(chunk * 32), "r"(x0 - 3), "r"(y0 - 3), "r"(b)
+            : "memory");
+    };
+    if (threadIdx.x == 0) issue(0);
+
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+        if (threadIdx.x == 0 && chunk + 1 < nchunks) issue(chunk + 1);
+        const int c = chunk * 32 + lane;
+        float wreg[49];
+#pragma unroll
+        for (int i = 0; i < 49; ++i) wreg[i] = dw_w[(size_t)i * C + c];
+        const float bias = dw_b[c];
+        mbar_wait(&bar[chunk & 1], (uint32_t)(chunk >> 1) & 1u);
+        const float* tin = in_buf + (chunk & 1) * IN_FLOATS;
+        float acc[TILE];
+#pragma unroll
+        for (int ox = 0; ox < TILE; ++ox) acc[ox] = bias;
+#pragma unroll
+        for (int ky = 0; ky < 7; ++ky) {
+            float row[IN];
+#pragma unroll
+            for (int ix = 0; ix < IN; ++ix) row[ix] = tin[((warp + ky) * IN + ix) * 32 + lane];
+#pragma unroll
+            for (int kx = 0; kx < 7; ++kx)
+#pragma unroll
+                for (int ox = 0; ox < TILE; ++ox) acc[ox] = fmaf(row[ox + kx], wreg[ky * 7 + kx], acc[ox]);
+        }
+#pragma unroll
+        for (int ox = 0; ox < TILE; ++ox) obuf[(size_t)(warp * TILE + ox) * C + c] = acc[ox];
+        __syncthreads();   // everyone is done with this input buffer before it is refilled (chunk + 2)
+    }
+    // LayerNorm over C for each pixel of the tile (warp = output row: TILE pixels per warp)
+    for (int ox = 0; ox < TILE; ++ox) {
+        const int y = y0 + warp, x = x0 + ox;
+        if (y >= H || x >= W) continue;
+        const float* v = obuf + (size_t)(warp * TILE + ox) * C;
+        float s = 0.f;
+        for (int i = lane; i < C; i += 32) s += v[i];
+        const float mean = warp_sum(s) / (float)C;
+        float sq = 0.f;
+        for (int i = lane; i < C; i += 32) { const float d = v[i] - mean; sq += d * d; }
+        const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)C + eps);
+        __nv_bfloat16* o = out + (((size_t)b * H + y) * W + x) * C;
+        for (int i = lane * 2; i < C; i += 64) {
+            const float a0 = (v[i] - mean) * rstd * ln_w[i] + ln_b[i];
+            const float a1 = (v[i + 1] - mean) * rstd * ln_w[i + 1] + ln_b[i + 1];
+            *reinterpret_cast<__nv_bfloat162*>(o + i) = __floats2bfloat162_rn(a0, a1);
+        }
+    }
+}
+
+// LayerNorm2d (per pixel over C_in) then 2x2 / stride-2 patch gather: out row (b, h2, w2) holds the four
+// normalised pixels in (kh, kw, c) order.  One warp per output row.
+__global__ void __launch_bounds__(256) downsample_ln_kernel(const float* __restrict__ x, int B, int H, int W, int C,
+                                                            const float* __restrict__ w, const float* __restrict__ bvec,
+                                                            float eps, __nv_bfloat16* __restrict__ out) {
+    const int H2 = H / 2, W2 = W / 2;
+    const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= (long long)B * H2 * W2) return;
+    const int lane = threadIdx.x & 31;
+    const int bb = (int)(r / ((long long)H2 * W2));
+    const int rem = (int)(r % ((long long)H2 * W2));
+    const int h2 = rem / W2, w2 = rem % W2;
+    const int n4 = C >> 2;
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    const float4* b4 = reinterpret_cast<const float4*>(bvec);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int hh = 2 * h2 + (p >> 1), ww = 2 * w2 + (p & 1);
+        const float4* src = reinterpret_cast<const float4*>(x + (((size_t)bb * H + hh) * W + ww) * C);
+        float s = 0.f;
+        for (int i = lane; i < n4; i += 32) { const float4 v = src[i]; s += (v.x + v.y) + (v.z + v.w); }
+        const float mean = warp_sum(s) / (float)C;
+        float sq = 0.f;
+        for (int i = lane; i < n4; i += 32) {
+            const float4 v = src[i];
+            const float a = v.x - mean, b2 = v.y - mean, c = v.z - mean, d = v.w - mean;
+            sq += (a * a + b2 * b2) + (c * c + d * d);
+        }
+        const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)C + eps);
+        uint2* o = reinterpret_cast<uint2*>(out + (size_t)r * 4 * C + (size_t)p * C);
+        for (int i = lane; i < n4; i += 32) {
+            const float4 v = src[i], g = w4[i], be = b4[i];
+            __nv_bfloat162 lo = __floats2bfloat162_rn((v.x - mean) * rstd * g.x + be.x, (v.y - mean) * rstd * g.y + be.y);
+            __nv_bfloat162 hi = __floats2bfloat162_rn((v.z - mean) * rstd * g.z + be.z, (v.w - mean) * rstd * g.w + be.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            o[i] = pk;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_cn_encode = nullptr;
+
+#define CN_CUDA(e, x)                                                                                     \
+    do {                                                                                                  \
+        cudaError_t _c = (x);                                                                             \
+        if (_c != cudaSuccess) {                                                                          \
+            std::string m = std::string(#x) + " failed: " + cudaGetErrorString(_c);                       \
+            mnx_set_error(e, m.c_str());                                                                  \
+            return MNX_ERR_CUDA;                                                                          \
+        }                                                                                                 \
+    } while (0)
+#define CN_TRY(x) do { int _r = (x); if (_r != MNX_OK) return _r; } while (0)
+
+static int cn_f32(mnx_engine* e, const std::string& key, std::initializer_list<int64_t> shape, const float** out) {
+    const std::vector<float>* v = mnx_need(e, key, shape);
+    if (!v) return MNX_ERR_WEIGHTS;
+    CN_CUDA(e, mnx_upload(e, *v, out));
+    return MNX_OK;
+}
+static int cn_bf16_vec(mnx_engine* e, const std::vector<float>& v, const __nv_bfloat16** out) {
+    std::vector<__nv_bfloat16> h(v.size());
+    for (size_t i = 0; i < v.size(); ++i) h[i] = __float2bfloat16_rn(v[i]);
+    void* d = nullptr;
+    CN_CUDA(e, mnx_upload_raw(e, h.data(), h.size() * sizeof(__nv_bfloat16), &d));
+    *out = reinterpret_cast<const __nv_bfloat16*>(d);
+    return MNX_OK;
+}
+static int cn_bf16(mnx_engine* e, const std::string& key, std::initializer_list<int64_t> shape, const __nv_bfloat16** out) {
+    const std::vector<float>* v = mnx_need(e, key, shape);
+    if (!v) return MNX_ERR_WEIGHTS;
+    return cn_bf16_vec(e, *v, out);
+}
+
+template <int TILE>
+static size_t dw_smem(int C) {
+    return (size_t)(2 * (TILE + 6) * (TILE + 6) * 32 + TILE * TILE * C) * 4 + 16 + 128;
+}
+
+int convnext_finalize(mnx_engine* e, ConvNextState** out, const mnx_config& cfg) {
+    CN_CUDA(e, gemm_tc_configure());
+    if (!g_cn_encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CN_CUDA(e, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !fn) { mnx_set_error(e, "cuTensorMapEncodeTiled unavailable"); return MNX_ERR_CUDA; }
+        g_cn_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    }
+    CN_CUDA(e, cudaFuncSetAttribute(dwconv_ln_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem<8>(512)));
+    CN_CUDA(e, cudaFuncSetAttribute(dwconv_ln_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem<4>(1024)));
+    if (cfg.max_height % 32 != 0 || cfg.max_width % 32 != 0) {
+        mnx_set_error(e, "ConvNeXt-B needs image bounds that are multiples of 32");
+        return MNX_ERR_INVALID;
+    }
+    ConvNextState* st = new ConvNextState();
+    *out = st;
+    const std::string P = "encoder.cnn.";
+    CN_TRY(cn_f32(e, P + "stem.0.weight", {128, 3, 4, 4}, &st->stem_w));
+    CN_TRY(cn_f32(e, P + "stem.0.bias", {128}, &st->stem_b));
+    CN_TRY(cn_f32(e, P + "stem.1.weight", {128}, &st->stem_ln_w));
+    CN_TRY(cn_f32(e, P + "stem.1.bias", {128}, &st->stem_ln_b));
+    for (int s = 0; s < 4; ++s) {
+        const int64_t C = 128 << s;
+        if (s > 0) {
+            const int64_t Ci = C / 2;
+            const std::string D = P + "stages." + std::to_string(s) + ".downsample.";
+            CN_TRY(cn_f32(e, D + "0.weight", {Ci}, &st->down[s].ln_w));
+            CN_TRY(cn_f32(e, D + "0.bias", {Ci}, &st->down[s].ln_b));
+            const std::vector<float>* w = mnx_need(e, D + "1.weight", {C, Ci, 2, 2});
+            if (!w) return MNX_ERR_WEIGHTS;
+            std::vector<float> r((size_t)C * 4 * Ci);
+            for (int64_t n = 0; n < C; ++n)
+                for (int64_t c = 0; c < Ci; ++c)
+                    for (int kh = 0; kh < 2; ++kh)
+                        for (int kw = 0; kw < 2; ++kw)
+                            r[(size_t)n * 4 * Ci + (size_t)(kh * 2 + kw) * Ci + c] = (*w)[(((size_t)n * Ci + c) * 2 + kh) * 2 + kw];
+            CN_TRY(cn_bf16_vec(e, r, &st->down[s].w));
+            CN_TRY(cn_f32(e, D + "1.bias", {C}, &st->down[s].b));
+        }
+        st->blocks[s].resize(CN_DEPTH[s]);
+        for (int j = 0; j < CN_DEPTH[s]; ++j) {
+            const std::string B = P + "stages." + std::to_string(s) + ".blocks." + std::to_string(j) + ".";
+            CnBlockW& w = st->blocks[s][j];
+            const std::vector<float>* dw = mnx_need(e, B + "conv_dw.weight", {C, 1, 7, 7});
+            if (!dw) return MNX_ERR_WEIGHTS;
+            std::vector<float> t((size_t)49 * C);
+            for (int64_t c = 0; c < C; ++c)
+                for (int i = 0; i < 49; ++i) t[(size_t)i * C + c] = (*dw)[(size_t)c * 49 + i];
+            CN_CUDA(e, mnx_upload(e, t, &w.dw_w));
+            CN_TRY(cn_f32(e, B + "conv_dw.bias", {C}, &w.dw_b));
+            CN_TRY(cn_f32(e, B + "norm.weight", {C}, &w.ln_w));
+            CN_TRY(cn_f32(e, B + "norm.bias", {C}, &w.ln_b));
+            CN_TRY(cn_bf16(e, B + "mlp.fc1.weight", {4 * C, C}, &w.fc1_w));
+            CN_TRY(cn_f32(e, B + "mlp.fc1.bias", {4 * C}, &w.fc1_b));
+            CN_TRY(cn_bf16(e, B + "mlp.fc2.weight", {C, 4 * C}, &w.fc2_w));
+            CN_TRY(cn_f32(e, B + "mlp.fc2.bias", {C}, &w.fc2_b));
+            CN_TRY(cn_f32(e, B + "gamma", {C}, &w.gamma));
+        }
+    }
+    const size_t tok = (size_t)cfg.max_batch * (cfg.max_height / 4) * (cfg.max_width / 4);
+    st->max_tokens = tok;
+    void* p = nullptr;
+    CN_CUDA(e, mnx_dev_alloc_bytes(e, &p, tok * 128 * sizeof(float))); st->x0 = (float*)p;
+    CN_CUDA(e, mnx_dev_alloc_bytes(e, &p, tok * 128 * sizeof(float) / 2 + 1024)); st->x1 = (float*)p;
+    CN_CUDA(e, mnx_dev_alloc_bytes(e, &p, tok * 128 * 2)); st->abuf = (__nv_bfloat16*)p;
+    CN_CUDA(e, mnx_dev_alloc_bytes(e, &p, tok * 512 * 2)); st->hbuf = (__nv_bfloat16*)p;
+    return MNX_OK;
+}
+
+void convnext_destroy(ConvNextState* st) { delete st; }
+
+static cudaError_t cn_gemm(const __nv_bfloat16* A, const __nv_bfloat16* W, long long M, int N, int K, int epi,
+                           const float* bias, const float* gamma, void* out, cudaStream_t s) {
+    GemmParams p{};
+    p.A = A; p.W = W; p.M = (int)M; p.N = N; p.K = K; p.epilogue = epi; p.bias = bias; p.gamma = gamma; p.out = out;
+    return gemm_tc_launch(p, s);
+}
+
+template <int TILE>
+static int launch_dwconv(mnx_engine* e, const float* x, int B, int H, int W, int C, const CnBlockW& w,
+                         __nv_bfloat16* out, cudaStream_t s) {
+    CUtensorMap map;
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    const cuuint32_t box[4] = {32, (cuuint32_t)(TILE + 6), (cuuint32_t)(TILE + 6), 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_cn_encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { mnx_set_error(e, "cuTensorMapEncodeTiled failed for the dwconv input"); return MNX_ERR_CUDA; }
+    const int tiles = ((H + TILE - 1) / TILE) * ((W + TILE - 1) / TILE);
+    dwconv_ln_kernel<TILE><<<dim3(tiles, B), TILE * 32, dw_smem<TILE>(C), s>>>(map, H, W, C, w.dw_w, w.dw_b, w.ln_w, w.ln_b,
+                                                                                1e-6f, out);
+    CN_CUDA(e, cudaGetLastError());
+    return MNX_OK;
+}
+
+int convnext_forward(mnx_engine* e, ConvNextState* st, const float* images, int B, int H, int W, float* features,
+                     cudaStream_t s, int* launches) {
+    if (H % 32 != 0 || W % 32 != 0) {
+        mnx_set_error(e, "ConvNeXt-B path needs H and W to be multiples of 32");
+        return MNX_ERR_INVALID;
+    }
+    int nl = 0;
+    int Hc = H / 4, Wc = W / 4;
+    if ((size_t)B * Hc * Wc > st->max_tokens) { mnx_set_error(e, "convnext workspace too small for this request"); return MNX_ERR_CAPACITY; }
+    CN_CUDA(e, launch_patch_embed(images, B, H, W, st->stem_w, st->stem_b, st->stem_ln_w, st->stem_ln_b, 1e-6f, st->x0, s));
+    ++nl;
+    float* x = st->x0;
+    float* x_other = st->x1;
+    for (int stage = 0; stage < 4; ++stage) {
+        const int C = 128 << stage;
+        if (stage > 0) {
+            const int Ci = C / 2, H2 = Hc / 2, W2 = Wc / 2;
+            const long long M2 = (long long)B * H2 * W2;
+            downsample_ln_kernel<<<(unsigned)((M2 + 7) / 8), 256, 0, s>>>(x, B, Hc, Wc, Ci, st->down[stage].ln_w,
+                                                                         st->down[stage].ln_b, 1e-6f, st->abuf);
+            CN_CUDA(e, cudaGetLastError()); ++nl;
+            float* dst = (stage == 3) ? features : x_other;     // the last stage lives in the caller's buffer
+            CN_CUDA(e, cn_gemm(st->abuf, st->down[stage].w, M2, C, 4 * Ci, GEMM_EPI_F32, st->down[stage].b, nullptr, dst, s)); ++nl;
+            if (stage == 3) { x = features; } else { float* t = x; x = x_other; x_other = t; }
+            Hc = H2; Wc = W2;
+        }
+        const long long M = (long long)B * Hc * Wc;
+        for (int j = 0; j < CN_DEPTH[stage]; ++j) {
+            const CnBlockW& w = st->blocks[stage][j];
+            if (C <= 512) CN_TRY(launch_dwconv<8>(e, x, B, Hc, Wc, C, w, st->abuf, s));
+            else CN_TRY(launch_dwconv<4>(e, x, B, Hc, Wc, C, w, st->abuf, s));
+            ++nl;
+            CN_CUDA(e, cn_gemm(st->abuf, w.fc1_w, M, 4 * C, C, GEMM_EPI_GELU_BF16, w.fc1_b, nullptr, st->hbuf, s)); ++nl;
+            CN_CUDA(e, cn_gemm(st->hbuf, w.fc2_w, M, C, 4 * C, GEMM_EPI_RESADD_F32, w.fc2_b, w.gamma, x, s)); ++nl;
+        }
+    }
+    st->last_B = B; st->last_H = H; st->last_W = W;
+    *launches += nl;
+    return MNX_OK;
+}
+
+}  // namespace mnx

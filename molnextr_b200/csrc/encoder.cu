@@ -8,6 +8,10 @@ int swin_forward(mnx_engine* e, SwinState* st, const float* images, int B, int H
                  cudaStream_t s, int* launches);
 int swin_time_kernel(mnx_engine* e, SwinState* st, int which, int iters, float* ms, cudaStream_t s);
 void swin_destroy(SwinState* st);
+int convnext_finalize(mnx_engine* e, ConvNextState** st, const mnx_config& cfg);
+int convnext_forward(mnx_engine* e, ConvNextState* st, const float* images, int B, int H, int W, float* features,
+                     cudaStream_t s, int* launches);
+void convnext_destroy(ConvNextState* st);
 
 int encoder_seq_len(int kind, int H, int W) {
     if (kind == MNX_ENCODER_SWIN_B) {
@@ -22,14 +26,16 @@ int encoder_seq_len(int kind, int H, int W) {
 int encoder_finalize(mnx_engine* e, EncoderState& st, const mnx_config& cfg) {
     st.kind = cfg.encoder_kind;
     if (st.kind == MNX_ENCODER_SWIN_B) return swin_finalize(e, &st.swin, cfg);
-    mnx_set_error(e, "encoder kind not built into this library yet");
+    if (st.kind == MNX_ENCODER_CONVNEXT_B) return convnext_finalize(e, &st.cnx, cfg);
+    mnx_set_error(e, "unknown encoder kind");
     return MNX_ERR_INVALID;
 }
 
 int encoder_forward(mnx_engine* e, EncoderState& st, const float* images, int B, int H, int W, float* features,
                     cudaStream_t s, int* launches) {
     if (st.kind == MNX_ENCODER_SWIN_B) return swin_forward(e, st.swin, images, B, H, W, features, s, launches);
-    mnx_set_error(e, "encoder kind not built into this library yet");
+    if (st.kind == MNX_ENCODER_CONVNEXT_B) return convnext_forward(e, st.cnx, images, B, H, W, features, s, launches);
+    mnx_set_error(e, "unknown encoder kind");
     return MNX_ERR_INVALID;
 }
 
@@ -41,7 +47,9 @@ int encoder_time_kernel(mnx_engine* e, EncoderState& st, int which, int iters, f
 
 void encoder_destroy(EncoderState& st) {
     if (st.swin) swin_destroy(st.swin);
+    if (st.cnx) convnext_destroy(st.cnx);
     st.swin = nullptr;
+    st.cnx = nullptr;
 }
 
 }  // namespace mnx

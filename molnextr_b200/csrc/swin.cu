@@ -112,6 +112,15 @@ __global__ void __launch_bounds__(128) patch_embed_kernel(const float* __restric
     }
 }
 
+// shared with convnext.cu (its stem is the same 4x4/4 patchify + channel LayerNorm, eps 1e-6)
+cudaError_t launch_patch_embed(const float* img, int B, int H, int W, const float* w, const float* bias,
+                               const float* ln_w, const float* ln_b, float eps, float* x, cudaStream_t s) {
+    const int Hc = (H + 3) / 4, Wc = (W + 3) / 4;
+    const long long ntok = (long long)B * Hc * Wc;
+    patch_embed_kernel<<<(unsigned)((ntok + 7) / 8), 128, 0, s>>>(img, B, H, W, Hc, Wc, w, bias, ln_w, ln_b, eps, x);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------
 // row map of one attention block: window-order row -> token row of x (or -1 for a padded position)
 // window order = (b, wh, ww, ph, pw) over the padded, cyclically shifted map (transformers.py:252-266)
