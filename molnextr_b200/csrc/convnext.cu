@@ -364,4 +364,28 @@ int convnext_forward(mnx_engine* e, ConvNextState* st, const float* images, int 
     return MNX_OK;
 }
 
+// isolated timing of the fused dwconv+LN kernel at the shapes of stage (which - 101) of the last call
+int convnext_time_kernel(mnx_engine* e, ConvNextState* st, int which, int iters, float* ms, cudaStream_t s) {
+    const int stage = which - 101;
+    if (stage < 0 || stage > 3 || st->last_B == 0) { mnx_set_error(e, "convnext timing: ids 101..104 after an encode"); return MNX_ERR_INVALID; }
+    const int C = 128 << stage, B = st->last_B;
+    const int Hc = st->last_H / (4 << stage), Wc = st->last_W / (4 << stage);
+    const CnBlockW& w = st->blocks[stage][0];
+    const float* x = (stage == 3) ? st->x0 : ((stage & 1) ? st->x1 : st->x0);   // any resident map of the right size
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int rc = MNX_OK;
+    for (int i = 0; i < 3 + iters && rc == MNX_OK; ++i) {
+        if (i == 3) cudaEventRecord(e0, s);
+        rc = (C <= 512) ? launch_dwconv<8>(e, x, B, Hc, Wc, C, w, st->abuf, s) : launch_dwconv<4>(e, x, B, Hc, Wc, C, w, st->abuf, s);
+    }
+    cudaEventRecord(e1, s);
+    cudaStreamSynchronize(s);
+    float t = 0.f;
+    cudaEventElapsedTime(&t, e0, e1);
+    *ms = t / iters;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return rc;
+}
+
 }  // namespace mnx

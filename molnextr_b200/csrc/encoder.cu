@@ -12,6 +12,7 @@ int convnext_finalize(mnx_engine* e, ConvNextState** st, const mnx_config& cfg);
 int convnext_forward(mnx_engine* e, ConvNextState* st, const float* images, int B, int H, int W, float* features,
                      cudaStream_t s, int* launches);
 void convnext_destroy(ConvNextState* st);
+int convnext_time_kernel(mnx_engine* e, ConvNextState* st, int which, int iters, float* ms, cudaStream_t s);
 
 int encoder_seq_len(int kind, int H, int W) {
     if (kind == MNX_ENCODER_SWIN_B) {
@@ -41,6 +42,7 @@ int encoder_forward(mnx_engine* e, EncoderState& st, const float* images, int B,
 
 int encoder_time_kernel(mnx_engine* e, EncoderState& st, int which, int iters, float* ms, cudaStream_t s) {
     if (st.kind == MNX_ENCODER_SWIN_B) return swin_time_kernel(e, st.swin, which, iters, ms, s);
+    if (st.kind == MNX_ENCODER_CONVNEXT_B) return convnext_time_kernel(e, st.cnx, which, iters, ms, s);
     mnx_set_error(e, "no encoder on this handle");
     return MNX_ERR_INVALID;
 }

@@ -645,10 +645,40 @@ extern "C" int mnx_time_kernel(mnx_engine* e, int32_t which, int32_t iters, floa
         *ms = 0.f;
         return MNX_OK;
     }
-    if (!e->finalized || e->last_B == 0) return fail(e, MNX_ERR_INVALID, "run a decode first: timing uses its shapes and caches");
+    if (!e->finalized) return fail(e, MNX_ERR_INVALID, "weights not finalized");
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
     cudaStream_t s = (cudaStream_t)cuda_stream;
     if (which >= 100) return encoder_time_kernel(e, e->enc, which, iters, ms, s);
+    if (e->last_B == 0) return fail(e, MNX_ERR_INVALID, "run a decode first: timing uses its shapes and caches");
+    if (which == 7) {   // the persistent cluster decode kernel alone, on the K/V of the last call
+        const int usable = e->max_clusters < 16 ? e->max_clusters : 16;
+        const int B = e->last_B, S = e->last_S, T = e->cfg.max_len;
+        if (usable <= 0 || B > usable * MG_GMAX_H) return fail(e, MNX_ERR_INVALID, "last decode did not use the cluster kernel");
+        const int G = (B + usable - 1) / usable, clusters = (B + G - 1) / G;
+        MegaArgs a{};
+        a.wpack = e->wpack; a.ppack = e->ppack; a.finalp = e->finalp; a.emb = e->dw.emb; a.pe = e->dw.pe;
+        a.selfK = e->selfK; a.selfV = e->selfV; a.crossK = e->crossK; a.crossV = e->crossV;
+        a.B = B; a.S = S; a.T = T; a.G = G;
+        a.ids = e->ids; a.logp = e->logp; a.hidden = e->hidden; a.lens = e->lens;
+        a.row_state = e->row_state; a.steps_run = e->steps_run_dev; a.g = e->g; a.prof = nullptr;
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        float total = 0.f;
+        for (int i = 0; i < iters; ++i) {
+            CUDA_TRY(e, cudaMemsetAsync(e->row_state, 0, sizeof(unsigned) * B, s));
+            CUDA_TRY(e, cudaMemsetAsync(e->steps_run_dev, 0, sizeof(int), s));
+            cudaEventRecord(e0, s);
+            CUDA_TRY(e, mega_launch(a, clusters, s));
+            cudaEventRecord(e1, s);
+            CUDA_TRY(e, cudaStreamSynchronize(s));
+            float t = 0.f;
+            cudaEventElapsedTime(&t, e0, e1);
+            total += t;
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        *ms = total / iters;
+        return MNX_OK;
+    }
     DecBuffers b = make_buffers(e, e->last_B, e->last_S);
     cudaError_t c = dec_time_kernel(which, iters, b, e->dw, e->g, e->cfg.max_len / 2, ms, s);
     if (c == cudaErrorInvalidValue) return fail(e, MNX_ERR_INVALID, "unknown kernel id %d", which);
