@@ -68,12 +68,13 @@ struct mnx_engine {
     int *ids = nullptr, *lens = nullptr;
     float *logp = nullptr, *hidden = nullptr;
     // persistent cluster decode kernel (mega.cu)
-    const float *wpack = nullptr, *ppack = nullptr, *finalp = nullptr;
+    const float *wpack = nullptr, *ppack = nullptr, *finalp = nullptr, *wpack16 = nullptr, *ppack16 = nullptr;
+    int max_clusters16 = 0;
     unsigned int* row_state = nullptr;
     int* steps_run_dev = nullptr;
     long long* prof_dev = nullptr;
     int max_clusters = 0;
-    int decode_path = 0;   // 0 auto, 1 force multi-kernel graph path, 2 force cluster kernel
+    int decode_path = 0;   // 0 auto, 1 force multi-kernel graph path, 2 force 8-CTA cluster kernel, 3 force 16-CTA cluster kernel
     // bond head
     float *hg = nullptr, *AB = nullptr, *prob = nullptr;
     // predict-path staging
@@ -88,7 +89,7 @@ struct mnx_engine {
     int* h_done = nullptr;   // pinned
     int64_t launches = 0;
     int last_steps = 0;
-    int last_B = 0, last_S = 0;
+    int last_B = 0, last_S = 0, last_path = 0;
     EncoderState enc{};
 };
 
@@ -181,9 +182,11 @@ extern "C" int mnx_create(const mnx_config* cfg, mnx_engine** out) {
     cudaError_t c = cudaSetDevice(cfg->device);
     if (c == cudaSuccess) c = dec_configure();
     if (c == cudaSuccess) c = mega_configure(&e->max_clusters);
+    if (c == cudaSuccess) c = mega16_configure(&e->max_clusters16);
     if (const char* env = getenv("MNX_DECODE_PATH")) {
         if (!strcmp(env, "graph")) e->decode_path = 1;
         else if (!strcmp(env, "cluster")) e->decode_path = 2;
+        else if (!strcmp(env, "cluster16")) e->decode_path = 3;
     }
     if (c == cudaSuccess) c = cudaMallocHost(&e->h_done, sizeof(int));
     if (c == cudaSuccess) c = cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking);
@@ -281,6 +284,14 @@ static int finalize_decoder(mnx_engine* e) {
         for (int k = 0; k < 256; ++k)
             for (int c = 0; c < 32; ++c) dst[k * 32 + c] = Wm[(size_t)(row0 + c) * in_dim + k0 + k];
     };
+    // 16-CTA-cluster variant: [16][L*14 + 1][256 k][16 cols] and [16][L][1728]
+    const size_t TILE16 = 256 * 16, PF16 = 1728;
+    std::vector<float> wpack16((size_t)16 * NTILE * TILE16, 0.f), ppack16((size_t)16 * MNX_DEC_L * PF16, 0.f);
+    auto put_tile16 = [&](int i, int l, int t, const std::vector<float>& Wm, int in_dim, int row0, int k0) {
+        float* dst = wpack16.data() + ((size_t)i * NTILE + (size_t)l * TPL + t) * TILE16;
+        for (int k = 0; k < 256; ++k)
+            for (int c = 0; c < 16; ++c) dst[k * 16 + c] = Wm[(size_t)(row0 + c) * in_dim + k0 + k];
+    };
     for (int l = 0; l < MNX_DEC_L; ++l) {
         const std::string L = P + "decoder.transformer_layers." + std::to_string(l) + ".";
         DecLayerW& w = e->dw.layer[l];
@@ -342,6 +353,26 @@ static int finalize_decoder(mnx_engine* e) {
             }
             for (int c = 0; c < 128; ++c) pp[1728 + c] = b1->f[h * 128 + c];
         }
+        for (int i = 0; i < 16; ++i) {
+            put_tile16(i, l, 0, sq->f, D, i * 16, 0);
+            put_tile16(i, l, 1, sk->f, D, i * 16, 0);
+            put_tile16(i, l, 2, sv->f, D, i * 16, 0);
+            put_tile16(i, l, 3, so->f, D, i * 16, 0);
+            put_tile16(i, l, 4, cq->f, D, i * 16, 0);
+            put_tile16(i, l, 5, co->f, D, i * 16, 0);
+            for (int j = 0; j < 4; ++j) put_tile16(i, l, 6 + j, w1->f, D, i * 64 + j * 16, 0);
+            for (int j = 0; j < 4; ++j) put_tile16(i, l, 10 + j, w2->f, MNX_DEC_FF, i * 16, 256 * j);
+            float* pp = ppack16.data() + ((size_t)i * MNX_DEC_L + l) * PF16;
+            std::copy(ln1w->f.begin(), ln1w->f.end(), pp + 0);    std::copy(ln1b->f.begin(), ln1b->f.end(), pp + 256);
+            std::copy(ln2w->f.begin(), ln2w->f.end(), pp + 512);  std::copy(ln2b->f.begin(), ln2b->f.end(), pp + 768);
+            std::copy(lnfw->f.begin(), lnfw->f.end(), pp + 1024); std::copy(lnfb->f.begin(), lnfb->f.end(), pp + 1280);
+            for (int c = 0; c < 16; ++c) {
+                pp[1536 + c] = sqb->f[i * 16 + c]; pp[1552 + c] = skb->f[i * 16 + c]; pp[1568 + c] = svb->f[i * 16 + c];
+                pp[1584 + c] = sob->f[i * 16 + c]; pp[1600 + c] = cqb->f[i * 16 + c]; pp[1616 + c] = cob->f[i * 16 + c];
+                pp[1632 + c] = b2->f[i * 16 + c];
+            }
+            for (int c = 0; c < 64; ++c) pp[1648 + c] = b1->f[i * 64 + c];
+        }
     }
     UP(e->dw.wkv_c_t, wkv); UP(e->dw.bkv_c, bkv);
     NEED(lnw, P + "decoder.layer_norm.weight", D); NEED(lnb, P + "decoder.layer_norm.bias", D);
@@ -361,7 +392,13 @@ static int finalize_decoder(mnx_engine* e) {
             for (int k = 0; k < 256; ++k)
                 for (int c = 0; c < 32; ++c) dst[k * 32 + c] = (h * 32 + c < V) ? ow->f[(size_t)(h * 32 + c) * D + k] : 0.f;
         }
+        for (int i = 0; i < 16; ++i) {
+            float* dst = wpack16.data() + ((size_t)i * NTILE + (size_t)MNX_DEC_L * TPL) * TILE16;
+            for (int k = 0; k < 256; ++k)
+                for (int c = 0; c < 16; ++c) dst[k * 16 + c] = (i * 16 + c < V) ? ow->f[(size_t)(i * 16 + c) * D + k] : 0.f;
+        }
         UP(e->wpack, wpack); UP(e->ppack, ppack); UP(e->finalp, fin);
+        UP(e->wpack16, wpack16); UP(e->ppack16, ppack16);
     }
     NEED(emb, P + "embeddings.make_embedding.emb_luts.0.weight", V, D);
     UP(e->dw.emb, emb->f);
@@ -493,25 +530,33 @@ static int decode_internal(mnx_engine* e, const float* features, int B, int S, c
     int nl = 0;
     CUDA_TRY(e, dec_precompute(b, e->dw, features, e->cfg.encoder_dim, s, &nl));
     e->launches += nl;
-    // persistent cluster kernel when every cluster (<= 4 rows each) can be co-resident
-    const int usable = e->max_clusters < 16 ? e->max_clusters : 16;
-    const bool fits = usable > 0 && B <= usable * MG_GMAX_H;
-    if (e->decode_path == 2 && !fits)
-        return fail(e, MNX_ERR_CAPACITY, "cluster decode path forced but %d rows need more than %d co-resident clusters", B, usable);
-    if (fits && e->decode_path != 1) {
+    // persistent cluster kernels when every cluster (<= 4 rows each) can be co-resident: prefer 16-CTA clusters
+    // (half the per-SM byte stream), then 8-CTA clusters, else the multi-kernel graph path
+    const int usable16 = e->max_clusters16 < 8 ? e->max_clusters16 : 8;
+    const int usable8 = e->max_clusters < 16 ? e->max_clusters : 16;
+    const bool fits16 = usable16 > 0 && B <= usable16 * MG_GMAX_H;
+    const bool fits8 = usable8 > 0 && B <= usable8 * MG_GMAX_H;
+    if (e->decode_path == 3 && !fits16) return fail(e, MNX_ERR_CAPACITY, "16-CTA cluster path forced but %d rows do not fit %d clusters", B, usable16);
+    if (e->decode_path == 2 && !fits8) return fail(e, MNX_ERR_CAPACITY, "8-CTA cluster path forced but %d rows do not fit %d clusters", B, usable8);
+    const bool use16 = (e->decode_path == 3) || (e->decode_path == 0 && fits16);
+    const bool use8 = !use16 && ((e->decode_path == 2) || (e->decode_path == 0 && fits8));
+    if (use16 || use8) {
+        const int usable = use16 ? usable16 : usable8;
         const int G = (B + usable - 1) / usable;
         const int clusters = (B + G - 1) / G;
         CUDA_TRY(e, cudaMemsetAsync(e->row_state, 0, sizeof(unsigned) * B, s));
         CUDA_TRY(e, cudaMemsetAsync(e->steps_run_dev, 0, sizeof(int), s));
         MegaArgs a{};
-        a.wpack = e->wpack; a.ppack = e->ppack; a.finalp = e->finalp; a.emb = e->dw.emb; a.pe = e->dw.pe;
+        a.wpack = e->wpack; a.ppack = e->ppack; a.wpack16 = e->wpack16; a.ppack16 = e->ppack16;
+        a.finalp = e->finalp; a.emb = e->dw.emb; a.pe = e->dw.pe;
         a.selfK = e->selfK; a.selfV = e->selfV; a.crossK = e->crossK; a.crossV = e->crossV;
         a.B = B; a.S = S; a.T = T; a.G = G;
         a.ids = e->ids; a.logp = e->logp; a.hidden = e->hidden; a.lens = e->lens;
         a.row_state = e->row_state; a.steps_run = e->steps_run_dev; a.g = e->g;
         a.prof = getenv("MNX_DECODE_PROFILE") ? e->prof_dev : nullptr;
-        CUDA_TRY(e, mega_launch(a, clusters, s));
+        CUDA_TRY(e, use16 ? mega16_launch(a, clusters, s) : mega_launch(a, clusters, s));
         e->launches += 1;
+        e->last_path = use16 ? 3 : 2;
         int steps = 0;
         CUDA_TRY(e, cudaMemcpyAsync(&steps, e->steps_run_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(e, cudaStreamSynchronize(s));
@@ -519,6 +564,7 @@ static int decode_internal(mnx_engine* e, const float* features, int B, int S, c
         e->last_B = B; e->last_S = S;
         return MNX_OK;
     }
+    e->last_path = 1;
     int rc = ensure_graph(e, b);
     if (rc != MNX_OK) return rc;
     for (int chunk = 0; chunk < T / STEPS_PER_GRAPH; ++chunk) {
@@ -637,6 +683,8 @@ extern "C" int32_t mnx_last_decode_steps(const mnx_engine* e) { return e ? e->la
 
 extern "C" int mnx_time_kernel(mnx_engine* e, int32_t which, int32_t iters, float* ms, void* cuda_stream) {
     if (!e || !ms || iters < 1) return fail(e, MNX_ERR_INVALID, "mnx_time_kernel: bad argument");
+    if (which == 1002) { *ms = (float)e->max_clusters16; return MNX_OK; }
+    if (which == 1003) { *ms = (float)e->last_path; return MNX_OK; }
     if (which == 1000) { *ms = (float)e->max_clusters; return MNX_OK; }   // introspection: co-resident 8-CTA clusters
     if (which == 1001) {   // dump the cycle stamps recorded by the last profiled cluster decode (MNX_DECODE_PROFILE=1)
         long long h[64];
@@ -651,12 +699,14 @@ extern "C" int mnx_time_kernel(mnx_engine* e, int32_t which, int32_t iters, floa
     if (which >= 100) return encoder_time_kernel(e, e->enc, which, iters, ms, s);
     if (e->last_B == 0) return fail(e, MNX_ERR_INVALID, "run a decode first: timing uses its shapes and caches");
     if (which == 7) {   // the persistent cluster decode kernel alone, on the K/V of the last call
-        const int usable = e->max_clusters < 16 ? e->max_clusters : 16;
+        if (e->last_path != 2 && e->last_path != 3) return fail(e, MNX_ERR_INVALID, "last decode did not use a cluster kernel");
+        const bool use16 = e->last_path == 3;
+        const int usable = use16 ? (e->max_clusters16 < 8 ? e->max_clusters16 : 8) : (e->max_clusters < 16 ? e->max_clusters : 16);
         const int B = e->last_B, S = e->last_S, T = e->cfg.max_len;
-        if (usable <= 0 || B > usable * MG_GMAX_H) return fail(e, MNX_ERR_INVALID, "last decode did not use the cluster kernel");
         const int G = (B + usable - 1) / usable, clusters = (B + G - 1) / G;
         MegaArgs a{};
-        a.wpack = e->wpack; a.ppack = e->ppack; a.finalp = e->finalp; a.emb = e->dw.emb; a.pe = e->dw.pe;
+        a.wpack = e->wpack; a.ppack = e->ppack; a.wpack16 = e->wpack16; a.ppack16 = e->ppack16;
+        a.finalp = e->finalp; a.emb = e->dw.emb; a.pe = e->dw.pe;
         a.selfK = e->selfK; a.selfV = e->selfV; a.crossK = e->crossK; a.crossV = e->crossV;
         a.B = B; a.S = S; a.T = T; a.G = G;
         a.ids = e->ids; a.logp = e->logp; a.hidden = e->hidden; a.lens = e->lens;
@@ -668,7 +718,7 @@ extern "C" int mnx_time_kernel(mnx_engine* e, int32_t which, int32_t iters, floa
             CUDA_TRY(e, cudaMemsetAsync(e->row_state, 0, sizeof(unsigned) * B, s));
             CUDA_TRY(e, cudaMemsetAsync(e->steps_run_dev, 0, sizeof(int), s));
             cudaEventRecord(e0, s);
-            CUDA_TRY(e, mega_launch(a, clusters, s));
+            CUDA_TRY(e, use16 ? mega16_launch(a, clusters, s) : mega_launch(a, clusters, s));
             cudaEventRecord(e1, s);
             CUDA_TRY(e, cudaStreamSynchronize(s));
             float t = 0.f;

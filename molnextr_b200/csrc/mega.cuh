@@ -12,6 +12,8 @@ namespace mnx {
 struct MegaArgs {
     const float* wpack;
     const float* ppack;
+    const float* wpack16;   // 16-CTA-cluster variant: [16][L*14 + 1][256*16]
+    const float* ppack16;   // [16][L][1728]
     const float* finalp;
     const float* emb;
     const float* pe;
@@ -32,5 +34,7 @@ struct MegaArgs {
 
 cudaError_t mega_configure(int* max_clusters);
 cudaError_t mega_launch(const MegaArgs& a, int clusters, cudaStream_t s);
+cudaError_t mega16_configure(int* max_clusters);
+cudaError_t mega16_launch(const MegaArgs& a, int clusters, cudaStream_t s);
 
 }  // namespace mnx

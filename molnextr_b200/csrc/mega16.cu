@@ -1,0 +1,659 @@
+// Persistent decode kernel, 16-CTA clusters (non-portable cluster size): the same algorithm as mega.cu
+// with every per-SM byte stream halved.
+//
+// What limits mega.cu is the ~40 B/clk a single SM can pull from L2: per decode step each CTA of an
+// 8-CTA cluster ingests 2.7 MB of fp32 weights plus the K/V rows of its (row, head) pairs.  Here a
+// cluster has 16 CTAs and owns G <= 4 rows: CTA i owns a 1/16 column slice of every Linear (16 KB tiles
+// [256 k][16 cols], 1.35 MB per step) and the attention of head i/2 for rows {i%2, i%2 + 2}.
+// All global -> shared traffic (weight tiles, parameter blocks, K/V tiles) is issued by ONE producer
+// thread in the order the math consumes it, so latency-critical K/V tiles never queue behind weight
+// tiles that are only needed later.  Exchanges between CTAs use st.async into distributed shared
+// memory with mbarrier complete_tx signalling; q/k/v slices go only to the CTA that owns the head.
+// Arithmetic is fp32 and follows the same reference lines as decoder.cu / mega.cu.
+#include "mega.cuh"
+
+namespace mnx {
+
+#define H_CS 16
+#define H_THREADS 288
+#define H_GMAX 4
+#define H_TILE_FLOATS (256 * 16)
+#define H_TILE_BYTES (H_TILE_FLOATS * 4)
+#define H_RING 6
+#define H_TILES_PER_LAYER 14
+#define H_PARAM_FLOATS 1728
+#define H_TK 144
+#define H_QSCALE 5.656854152679443f
+
+enum { HP_LN1W = 0, HP_LN1B = 256, HP_LN2W = 512, HP_LN2B = 768, HP_LNFW = 1024, HP_LNFB = 1280,
+       HP_BQ = 1536, HP_BK = 1552, HP_BV = 1568, HP_BO = 1584, HP_BQC = 1600, HP_BOC = 1616, HP_B2 = 1632, HP_B1 = 1648 };
+
+struct HSmem {
+    static constexpr int ring = 0;
+    static constexpr int kv = ring + H_RING * H_TILE_BYTES;                   // 98304; [2 groups][2 bufs][144][32]
+    static constexpr int params = kv + 4 * H_TK * 128;                         // +73728
+    static constexpr int finalp = params + 2 * H_PARAM_FLOATS * 4;
+    static constexpr int xbuf = finalp + 768 * 4;
+    static constexpr int nbuf = xbuf + H_GMAX * 256 * 4;
+    static constexpr int ctxbuf = nbuf + H_GMAX * 256 * 4;
+    static constexpr int lgbuf = ctxbuf + H_GMAX * 256 * 4;
+    static constexpr int hbuf = lgbuf + H_GMAX * 256 * 4;
+    static constexpr int qkvs = hbuf + H_GMAX * 1024 * 4;                      // [2 groups][3][32]
+    static constexpr int red = qkvs + 2 * 3 * 32 * 4;                          // [4 sets][8 warps][G][16]; scores alias
+    static constexpr int scores = red;                                         // [2 groups][1024]
+    static constexpr int ared = red + 2 * 1024 * 4;
+    static constexpr int misc = ared + 2 * 128 * 4;
+    static constexpr int total = misc + 512;
+};
+static_assert(4 * 8 * H_GMAX * 16 * 4 <= 2 * 1024 * 4, "reduction scratch must fit in the scores area");
+static_assert(HSmem::total <= 232448, "shared memory budget exceeded");
+
+__device__ __forceinline__ uint32_t h_mapa(uint32_t local_addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void h_wait_cluster(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP_H:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_H;\n"
+        "bra WAIT_LOOP_H;\n"
+        "DONE_H:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void h_cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ void h_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ unsigned h_ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void h_st_release(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+struct HCtx {
+    uint8_t* sm;
+    int rank, head, half;           // cluster rank i, head = i / 2, half = i % 2
+    int tid, lane, warp;
+    int G;
+    int grp, gtid, gwarp;           // attention group (0/1), 128 threads each
+    uint64_t *full, *empty, *kvfull, *kvempty, *pbar, *xbar, *stepbar;
+    uint32_t tile_seq, x_seq, kv_seq;
+    uint32_t xbar_base;             // shared::cta address of xbar[0] (same offset in every CTA)
+};
+
+__device__ __forceinline__ const float* h_tile_acquire(HCtx& c) {
+    const uint32_t slot = c.tile_seq % H_RING, ph = (c.tile_seq / H_RING) & 1u;
+    mbar_wait(&c.full[slot], ph);
+    return reinterpret_cast<const float*>(c.sm + HSmem::ring + slot * H_TILE_BYTES);
+}
+__device__ __forceinline__ void h_tile_release(HCtx& c) {
+    const uint32_t slot = c.tile_seq % H_RING;
+    __syncwarp();
+    if (c.lane == 0) mbar_arrive(&c.empty[slot]);
+    ++c.tile_seq;
+}
+// tile [256 k][16 cols]; warp w covers k in [32w, 32w+32); lane = col + 16 * parity, the two half-warps take
+// the even / odd k of the range (bank-conflict free: even rows hit banks 0-15, odd rows banks 16-31)
+__device__ __forceinline__ void h_tile_fma(const HCtx& c, const float* tile, const float* Xs, int ldx, int koff,
+                                           float (&acc)[H_GMAX]) {
+    const int col = c.lane & 15, par = c.lane >> 4;
+    const int kb = 32 * c.warp + par;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int k = kb + 2 * j;
+        const float w = tile[k * 16 + col];
+#pragma unroll
+        for (int g = 0; g < H_GMAX; ++g)
+            if (g < c.G) acc[g] = fmaf(Xs[g * ldx + koff + k], w, acc[g]);
+    }
+}
+// reduce the 2 k-parities (shuffle) and the 8 warps (shared memory) of NS accumulator sets, then call
+// f(set, row, col, value) once per output element.  Two h_syncs.
+template <int NS, class F>
+__device__ __forceinline__ void h_reduce_apply(const HCtx& c, float (&acc)[NS][H_GMAX], F f) {
+    float* red = reinterpret_cast<float*>(c.sm + HSmem::red);
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int g = 0; g < H_GMAX; ++g)
+            if (g < c.G) {
+                const float v = acc[s][g] + __shfl_xor_sync(0xffffffffu, acc[s][g], 16);
+                if (c.lane < 16) red[((s * 8 + c.warp) * H_GMAX + g) * 16 + c.lane] = v;
+            }
+    h_sync();
+    const int n_out = NS * c.G * 16;
+    for (int idx = c.tid; idx < n_out; idx += 256) {
+        const int col = idx & 15, sg = idx >> 4;
+        const int s = sg / c.G, g = sg - s * c.G;
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[((s * 8 + w) * H_GMAX + g) * 16 + col];
+        f(s, g, col, v);
+    }
+    h_sync();
+}
+// asynchronous remote store that signals the destination CTA's current exchange barrier with its bytes
+__device__ __forceinline__ void h_send(const HCtx& c, int byte_off, uint32_t dst_cta, float v) {
+    const uint32_t local = smem_u32(c.sm + byte_off);
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(h_mapa(local, dst_cta)),
+                 "r"(__float_as_uint(v)), "r"(h_mapa(c.xbar_base + 8u * (c.x_seq & 3u), dst_cta))
+                 : "memory");
+}
+__device__ __forceinline__ void h_bcast(const HCtx& c, int byte_off, float v) {
+#pragma unroll
+    for (uint32_t d = 0; d < H_CS; ++d) h_send(c, byte_off, d, v);
+}
+// finish an exchange in which this CTA receives `bytes_in` bytes in total.  Four barriers rotate: the
+// targeted q/k/v exchanges only synchronise a head's two CTAs, so a fast CTA can run up to two
+// exchanges ahead of a slow one -- its traffic must never land in a phase the slow CTA still waits on.
+__device__ __forceinline__ void h_exchange(HCtx& c, uint32_t bytes_in) {
+    uint64_t* bar = c.xbar + (c.x_seq & 3u);
+    if (c.tid == 0) mbar_arrive_expect_tx(bar, bytes_in);
+    h_wait_cluster(bar, (c.x_seq >> 2) & 1u);
+    ++c.x_seq;
+}
+__device__ __forceinline__ void h_layer_norm(const HCtx& c, const float* w, const float* b) {
+    if (c.warp < c.G) {
+        const float* x = reinterpret_cast<const float*>(c.sm + HSmem::xbuf) + c.warp * 256;
+        float* n = reinterpret_cast<float*>(c.sm + HSmem::nbuf) + c.warp * 256;
+        float4 v0 = reinterpret_cast<const float4*>(x)[c.lane];
+        float4 v1 = reinterpret_cast<const float4*>(x)[c.lane + 32];
+        const float sum = ((v0.x + v0.y) + (v0.z + v0.w)) + ((v1.x + v1.y) + (v1.z + v1.w));
+        const float mean = warp_sum(sum) * (1.0f / 256.0f);
+        v0.x -= mean; v0.y -= mean; v0.z -= mean; v0.w -= mean;
+        v1.x -= mean; v1.y -= mean; v1.z -= mean; v1.w -= mean;
+        const float sq = ((v0.x * v0.x + v0.y * v0.y) + (v0.z * v0.z + v0.w * v0.w)) +
+                         ((v1.x * v1.x + v1.y * v1.y) + (v1.z * v1.z + v1.w * v1.w));
+        const float rstd = 1.0f / sqrtf(warp_sum(sq) * (1.0f / 256.0f) + 1e-6f);
+        const float4 g0 = reinterpret_cast<const float4*>(w)[c.lane], g1 = reinterpret_cast<const float4*>(w)[c.lane + 32];
+        const float4 c0 = reinterpret_cast<const float4*>(b)[c.lane], c1 = reinterpret_cast<const float4*>(b)[c.lane + 32];
+        v0.x = v0.x * rstd * g0.x + c0.x; v0.y = v0.y * rstd * g0.y + c0.y;
+        v0.z = v0.z * rstd * g0.z + c0.z; v0.w = v0.w * rstd * g0.w + c0.w;
+        v1.x = v1.x * rstd * g1.x + c1.x; v1.y = v1.y * rstd * g1.y + c1.y;
+        v1.z = v1.z * rstd * g1.z + c1.z; v1.w = v1.w * rstd * g1.w + c1.w;
+        reinterpret_cast<float4*>(n)[c.lane] = v0;
+        reinterpret_cast<float4*>(n)[c.lane + 32] = v1;
+    }
+    h_sync();
+}
+__device__ __forceinline__ void h_group_sync(const HCtx& c) {
+    asm volatile("bar.sync %0, 128;" ::"r"(2 + c.grp) : "memory");
+}
+
+// single-query attention of this CTA's head for the row of thread group c.grp (cluster row `g`).
+// K/V tiles are delivered by the producer into kv[grp][seq & 1]; with `extra` the row's new key / value
+// (already in qkvs) is appended as key index nglobal.  The context slice goes to all 16 CTAs.
+__device__ void h_attend(HCtx& c, int g, int nglobal, bool extra) {
+    float* scores = reinterpret_cast<float*>(c.sm + HSmem::scores) + c.grp * 1024;
+    float* ared = reinterpret_cast<float*>(c.sm + HSmem::ared) + c.grp * 128;
+    const float* qs = reinterpret_cast<const float*>(c.sm + HSmem::qkvs) + (c.grp * 3 + 0) * 32;
+    const float* ks = reinterpret_cast<const float*>(c.sm + HSmem::qkvs) + (c.grp * 3 + 1) * 32;
+    const float* vs = reinterpret_cast<const float*>(c.sm + HSmem::qkvs) + (c.grp * 3 + 2) * 32;
+    const int nkeys = nglobal + (extra ? 1 : 0);
+    const int ntiles = (nkeys + H_TK - 1) / H_TK;
+    float acc = 0.f;
+    for (int i = 0; i < 2 * ntiles; ++i) {
+        const uint32_t seq = c.kv_seq + (uint32_t)i, slot = seq & 1u;
+        mbar_wait(&c.kvfull[c.grp * 2 + slot], (seq >> 1) & 1u);
+        float* tb = reinterpret_cast<float*>(c.sm + HSmem::kv + (c.grp * 2 + slot) * H_TK * 128);
+        const int tile = (i < ntiles) ? i : i - ntiles;
+        const int nk = min(H_TK, nkeys - tile * H_TK);
+        if (extra && tile == ntiles - 1) {
+            if (c.gtid < 32) tb[(nkeys - 1 - tile * H_TK) * 32 + c.gtid] = (i < ntiles) ? ks[c.gtid] : vs[c.gtid];
+            h_group_sync(c);
+        }
+        if (i < ntiles) {
+            for (int j = c.gtid; j < nk; j += 128) {
+                const float4* kr = reinterpret_cast<const float4*>(tb + j * 32);
+                float s = 0.f;
+#pragma unroll
+                for (int cc0 = 0; cc0 < 8; ++cc0) {
+                    const int cc = (cc0 + j) & 7;
+                    const float4 kv = kr[cc];
+                    const float4 qv = reinterpret_cast<const float4*>(qs)[cc];
+                    s = fmaf(qv.x, kv.x, s); s = fmaf(qv.y, kv.y, s);
+                    s = fmaf(qv.z, kv.z, s); s = fmaf(qv.w, kv.w, s);
+                }
+                scores[tile * H_TK + j] = s;
+            }
+        } else {
+            if (i == ntiles) {
+                h_group_sync(c);
+                if (c.gwarp == 0) {   // softmax by one warp, shuffles only
+                    float m = -INFINITY;
+                    for (int j = c.lane; j < nkeys; j += 32) m = fmaxf(m, scores[j]);
+                    m = warp_max(m);
+                    float sum = 0.f;
+                    for (int j = c.lane; j < nkeys; j += 32) {
+                        const float e = expf(scores[j] - m);
+                        scores[j] = e;
+                        sum += e;
+                    }
+                    sum = warp_sum(sum);
+                    for (int j = c.lane; j < nkeys; j += 32) scores[j] = scores[j] / sum;
+                }
+                h_group_sync(c);
+            }
+            const float* ps = scores + tile * H_TK;
+#pragma unroll 4
+            for (int j = c.gwarp; j < nk; j += 4) acc = fmaf(ps[j], tb[j * 32 + c.lane], acc);
+        }
+        h_group_sync(c);   // tile consumed
+        if (c.gtid == 0) mbar_arrive(&c.kvempty[c.grp * 2 + slot]);
+    }
+    c.kv_seq += (uint32_t)(2 * ntiles);
+    ared[c.gwarp * 32 + c.lane] = acc;
+    h_group_sync(c);
+    if (c.gwarp == 0)
+        h_bcast(c, HSmem::ctxbuf + (g * 256 + c.head * 32 + c.lane) * 4,
+                (ared[c.lane] + ared[32 + c.lane]) + (ared[64 + c.lane] + ared[96 + c.lane]));
+}
+
+__global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    HCtx c;
+    c.sm = sm;
+    c.tid = threadIdx.x; c.lane = c.tid & 31; c.warp = c.tid >> 5;
+    {
+        uint32_t r;
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+        c.rank = (int)r;
+    }
+    c.head = c.rank >> 1; c.half = c.rank & 1;
+    c.grp = (c.warp >> 2) & 1; c.gtid = c.tid & 127; c.gwarp = c.warp & 3;
+    const int cluster = blockIdx.x / H_CS;
+    const int row0 = cluster * a.G;
+    c.G = min(a.G, a.B - row0);
+    c.tile_seq = 0; c.x_seq = 0; c.kv_seq = 0;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + HSmem::misc);
+    c.full = bars; c.empty = bars + H_RING; c.kvfull = bars + 2 * H_RING; c.kvempty = c.kvfull + 4;
+    c.pbar = c.kvempty + 4; c.xbar = c.pbar + 2; c.stepbar = c.xbar + 4;
+    c.xbar_base = smem_u32(&c.xbar[0]);
+    int* s_tok = reinterpret_cast<int*>(c.stepbar + 1);
+    int* s_fin = s_tok + H_GMAX;
+    int* s_rank = s_fin + H_GMAX;
+    int* s_go = s_rank + H_GMAX;
+
+    if (c.tid == 0) {
+        for (int i = 0; i < H_RING; ++i) { mbar_init(&c.full[i], 1); mbar_init(&c.empty[i], 8); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&c.kvfull[i], 1); mbar_init(&c.kvempty[i], 1); }
+        mbar_init(&c.pbar[0], 1); mbar_init(&c.pbar[1], 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&c.xbar[i], 1);
+        mbar_init(c.stepbar, 1);
+        fence_barrier_init();
+        for (int g = 0; g < H_GMAX; ++g) { s_tok[g] = a.g.sos; s_fin[g] = (g < c.G) ? 0 : 1; s_rank[g] = 0; }
+        *s_go = 1;
+    }
+    for (int i = c.tid; i < 768; i += H_THREADS) reinterpret_cast<float*>(sm + HSmem::finalp)[i] = a.finalp[i];
+    h_cluster_sync_all();
+
+    const size_t kv_layer = (size_t)a.B * 8 * a.T * 32;
+    const float* wbase = a.wpack16 + (size_t)c.rank * (MNX_DEC_L * H_TILES_PER_LAYER + 1) * H_TILE_FLOATS;
+    const float* pbase = a.ppack16 + (size_t)c.rank * MNX_DEC_L * H_PARAM_FLOATS;
+
+    if (c.warp == 8) {
+        // ======================= producer: every global -> shared transfer, in consumption order =======================
+        if (c.lane == 0) {
+            const uint64_t keep = l2_policy_evict_last(), stream = l2_policy_evict_first();
+            uint32_t seq = 0, pseq = 0, step = 0, kvseq[2] = {0u, 0u};
+            auto weight_tile = [&](int index) {
+                const uint32_t slot = seq % H_RING, ph = (seq / H_RING) & 1u;
+                mbar_wait(&c.empty[slot], ph ^ 1u);
+                mbar_arrive_expect_tx(&c.full[slot], H_TILE_BYTES);
+                bulk_g2s_hint(sm + HSmem::ring + slot * H_TILE_BYTES, wbase + (size_t)index * H_TILE_FLOATS, H_TILE_BYTES,
+                              &c.full[slot], keep);
+                ++seq;
+            };
+            // K/V tile sequence K0..K(n-1), V0..V(n-1) of both live groups, interleaved
+            auto kv_tiles = [&](const float* const* Kb, const float* const* Vb, const bool* live, int nglobal,
+                                bool extra, uint64_t pol) {
+                const int nkeys = nglobal + (extra ? 1 : 0);
+                const int ntiles = (nkeys + H_TK - 1) / H_TK;
+                for (int i = 0; i < 2 * ntiles; ++i) {
+                    for (int p = 0; p < 2; ++p) {
+                        if (!live[p]) continue;
+                        const uint32_t s = kvseq[p] + (uint32_t)i, slot = s & 1u;
+                        mbar_wait(&c.kvempty[p * 2 + slot], ((s >> 1) & 1u) ^ 1u);
+                        const int tile = (i < ntiles) ? i : i - ntiles;
+                        const float* src = ((i < ntiles) ? Kb[p] : Vb[p]) + (size_t)tile * H_TK * 32;
+                        const int rows = min(H_TK, nglobal - tile * H_TK);
+                        uint64_t* bar = &c.kvfull[p * 2 + slot];
+                        if (rows > 0) {
+                            asm volatile("fence.proxy.async;" ::: "memory");
+                            mbar_arrive_expect_tx(bar, (uint32_t)rows * 128u);
+                            bulk_g2s_hint(sm + HSmem::kv + (p * 2 + slot) * H_TK * 128, src, (uint32_t)rows * 128u, bar, pol);
+                        } else {
+                            mbar_arrive(bar);
+                        }
+                    }
+                }
+                for (int p = 0; p < 2; ++p)
+                    if (live[p]) kvseq[p] += (uint32_t)(2 * ntiles);
+            };
+            for (;;) {
+                mbar_wait(c.stepbar, step & 1u);
+                if (*reinterpret_cast<volatile int*>(s_go) == 0) break;
+                const int t = (int)step;
+                bool live[2];
+                int grow[2];
+                for (int p = 0; p < 2; ++p) {
+                    grow[p] = c.half + 2 * p;
+                    live[p] = grow[p] < c.G && reinterpret_cast<volatile int*>(s_fin)[grow[p]] == 0;
+                }
+                for (int l = 0; l < MNX_DEC_L; ++l) {
+                    {
+                        const uint32_t pb = pseq & 1u;
+                        mbar_arrive_expect_tx(&c.pbar[pb], H_PARAM_FLOATS * 4);
+                        bulk_g2s_hint(sm + HSmem::params + pb * H_PARAM_FLOATS * 4, pbase + (size_t)l * H_PARAM_FLOATS,
+                                      H_PARAM_FLOATS * 4, &c.pbar[pb], keep);
+                        ++pseq;
+                    }
+                    const int base = l * H_TILES_PER_LAYER;
+                    weight_tile(base + 0); weight_tile(base + 1); weight_tile(base + 2);          // q, k, v
+                    {
+                        const float* Kb[2], *Vb[2];
+                        for (int p = 0; p < 2; ++p) {
+                            const size_t off = l * kv_layer + ((size_t)(row0 + grow[p]) * 8 + c.head) * a.T * 32;
+                            Kb[p] = a.selfK + off; Vb[p] = a.selfV + off;
+                        }
+                        kv_tiles(Kb, Vb, live, t, true, stream);
+                    }
+                    weight_tile(base + 3); weight_tile(base + 4);                                  // Wo, Wq_ctx
+                    {
+                        const float* Kb[2], *Vb[2];
+                        for (int p = 0; p < 2; ++p) {
+                            const size_t off = (((size_t)l * a.B + row0 + grow[p]) * 8 + c.head) * (size_t)a.S * 32;
+                            Kb[p] = a.crossK + off; Vb[p] = a.crossV + off;
+                        }
+                        kv_tiles(Kb, Vb, live, a.S, false, keep);
+                    }
+                    for (int i = 5; i < H_TILES_PER_LAYER; ++i) weight_tile(base + i);              // Wo_ctx, W1 x4, W2 x4
+                }
+                weight_tile(MNX_DEC_L * H_TILES_PER_LAYER);                                        // vocabulary slice
+                ++step;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ======================= 8 compute warps =======================
+        float* xbuf = reinterpret_cast<float*>(sm + HSmem::xbuf);
+        float* nbuf = reinterpret_cast<float*>(sm + HSmem::nbuf);
+        float* ctxbuf = reinterpret_cast<float*>(sm + HSmem::ctxbuf);
+        float* hbuf = reinterpret_cast<float*>(sm + HSmem::hbuf);
+        float* lgbuf = reinterpret_cast<float*>(sm + HSmem::lgbuf);
+        const float* fp = reinterpret_cast<const float*>(sm + HSmem::finalp);
+        uint32_t pseq = 0;
+        int pm = 0;
+#define H_MARK() do { if (a.prof && t == 100 && l == 1 && blockIdx.x == 0 && c.tid == 0 && pm < 64) a.prof[pm++] = clock64(); } while (0)
+        for (int t = 0;; ++t) {
+            int n_alive = 0;
+            for (int g = 0; g < c.G; ++g) n_alive += (s_fin[g] == 0) ? 1 : 0;
+            if (c.tid == 0) {
+                *reinterpret_cast<volatile int*>(s_go) = n_alive > 0 ? 1 : 0;
+                __threadfence_block();
+                mbar_arrive(c.stepbar);
+            }
+            if (n_alive == 0) break;
+            // rows of this CTA's two attention groups and how many q/k/v slices it will receive
+            const int my_g = c.half + 2 * c.grp;                       // cluster row handled by this thread's group
+            const bool my_row = my_g < c.G && s_fin[my_g] == 0;
+            int n_my = 0;
+            for (int p = 0; p < 2; ++p) n_my += (c.half + 2 * p < c.G && s_fin[c.half + 2 * p] == 0) ? 1 : 0;
+            // ---- rank of each alive row among all alive rows of the batch (row-rank PE rule) ----
+            if (c.warp == 0) {
+                int finished_before = 0;
+                for (int r = c.lane; r < row0; r += 32) {
+                    unsigned s;
+                    do { s = h_ld_acquire(a.row_state + r); } while ((s >> 1) < (unsigned)t && (s & 1u) == 0u);
+                    if ((s & 1u) && (s >> 1) <= (unsigned)t) ++finished_before;
+                }
+                finished_before = (int)warp_sum((float)finished_before);
+                if (c.lane == 0) {
+                    int alive_lower = row0 - finished_before;
+                    for (int g = 0; g < c.G; ++g) {
+                        s_rank[g] = alive_lower;
+                        if (s_fin[g] == 0) ++alive_lower;
+                    }
+                }
+            }
+            h_sync();
+            for (int i = c.tid; i < c.G * 256; i += 256) {
+                const int g = i >> 8, d = i & 255;
+                xbuf[i] = (s_fin[g] == 0) ? a.emb[s_tok[g] * 256 + d] * 16.0f + a.pe[(size_t)s_rank[g] * 256 + d] : 0.f;
+            }
+            h_sync();
+
+            for (int l = 0; l < MNX_DEC_L; ++l) {
+                mbar_wait(&c.pbar[pseq & 1u], (pseq >> 1) & 1u);
+                const float* P = reinterpret_cast<const float*>(sm + HSmem::params + (pseq & 1u) * H_PARAM_FLOATS * 4);
+                ++pseq;
+                float* Kc = a.selfK + l * kv_layer;
+                float* Vc = a.selfV + l * kv_layer;
+                H_MARK();   // 0: layer start (after param wait)
+                // ---------- self attention ----------
+                h_layer_norm(c, P + HP_LN1W, P + HP_LN1B);
+                H_MARK();   // 1: LN1
+                {
+                    float acc[3][H_GMAX] = {};
+#pragma unroll
+                    for (int which = 0; which < 3; ++which) {
+                        const float* tile = h_tile_acquire(c);
+                        h_tile_fma(c, tile, nbuf, 256, 0, acc[which]);
+                        h_tile_release(c);
+                    }
+                    h_reduce_apply<3>(c, acc, [&](int which, int g, int col, float v) {
+                        float o = v + P[HP_BQ + which * 16 + col];
+                        if (s_fin[g]) return;
+                        if (which == 0) o = o / H_QSCALE;
+                        else {
+                            float* dst = (which == 1) ? Kc : Vc;
+                            dst[(((size_t)(row0 + g) * 8 + c.head) * a.T + t) * 32 + c.half * 16 + col] = o;
+                        }
+                        // the slice goes to the CTA that runs this (row, head): cluster rank 2*head + (g & 1), group g >> 1
+                        h_send(c, HSmem::qkvs + (((g >> 1) * 3 + which) * 32 + c.half * 16 + col) * 4,
+                               (uint32_t)(2 * c.head + (g & 1)), o);
+                    });
+                }
+                H_MARK();   // 2: QKV gemm + sends
+                h_exchange(c, (uint32_t)n_my * 2u * 3u * 16u * 4u);       // q, k, v of my rows, from both halves of the head
+                H_MARK();   // 3: qkv exchange
+                if (my_row) h_attend(c, my_g, t, true);
+                H_MARK();   // 4: self attention
+                h_exchange(c, (uint32_t)n_alive * 1024u);                // ctx complete everywhere
+                H_MARK();   // 5: ctx exchange
+                {
+                    float acc[1][H_GMAX] = {};
+                    const float* tile = h_tile_acquire(c);
+                    h_tile_fma(c, tile, ctxbuf, 256, 0, acc[0]);
+                    h_tile_release(c);
+                    h_reduce_apply<1>(c, acc, [&](int, int g, int col, float v) {
+                        const int n = c.rank * 16 + col;
+                        h_bcast(c, HSmem::xbuf + (g * 256 + n) * 4, (v + P[HP_BO + col]) + xbuf[g * 256 + n]);
+                    });
+                }
+                H_MARK();   // 6: Wo gemm
+                h_exchange(c, (uint32_t)c.G * 1024u);                     // x1
+                H_MARK();   // 7: x1 exchange
+                // ---------- context attention ----------
+                h_layer_norm(c, P + HP_LN2W, P + HP_LN2B);
+                {
+                    float acc[1][H_GMAX] = {};
+                    const float* tile = h_tile_acquire(c);
+                    h_tile_fma(c, tile, nbuf, 256, 0, acc[0]);
+                    h_tile_release(c);
+                    h_reduce_apply<1>(c, acc, [&](int, int g, int col, float v) {
+                        if (s_fin[g]) return;
+                        h_send(c, HSmem::qkvs + (((g >> 1) * 3 + 0) * 32 + c.half * 16 + col) * 4,
+                               (uint32_t)(2 * c.head + (g & 1)), (v + P[HP_BQC + col]) / H_QSCALE);
+                    });
+                }
+                H_MARK();   // 8: LN2 + Wq gemm
+                h_exchange(c, (uint32_t)n_my * 2u * 16u * 4u);
+                H_MARK();   // 9: q exchange
+                if (my_row) h_attend(c, my_g, a.S, false);
+                H_MARK();   // 10: cross attention
+                h_exchange(c, (uint32_t)n_alive * 1024u);
+                H_MARK();   // 11: ctx exchange
+                {
+                    float acc[1][H_GMAX] = {};
+                    const float* tile = h_tile_acquire(c);
+                    h_tile_fma(c, tile, ctxbuf, 256, 0, acc[0]);
+                    h_tile_release(c);
+                    h_reduce_apply<1>(c, acc, [&](int, int g, int col, float v) {
+                        const int n = c.rank * 16 + col;
+                        h_bcast(c, HSmem::xbuf + (g * 256 + n) * 4, (v + P[HP_BOC + col]) + xbuf[g * 256 + n]);
+                    });
+                }
+                H_MARK();   // 12: Wo_c gemm
+                h_exchange(c, (uint32_t)c.G * 1024u);                     // x2
+                H_MARK();   // 13: x2 exchange
+                // ---------- feed forward ----------
+                h_layer_norm(c, P + HP_LNFW, P + HP_LNFB);
+                {
+                    float acc[4][H_GMAX] = {};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float* tile = h_tile_acquire(c);
+                        h_tile_fma(c, tile, nbuf, 256, 0, acc[j]);
+                        h_tile_release(c);
+                    }
+                    h_reduce_apply<4>(c, acc, [&](int j, int g, int col, float v) {
+                        h_bcast(c, HSmem::hbuf + (g * 1024 + c.rank * 64 + j * 16 + col) * 4, gelu_erf(v + P[HP_B1 + j * 16 + col]));
+                    });
+                }
+                H_MARK();   // 14: LN + W1
+                h_exchange(c, (uint32_t)c.G * 4096u);                     // FFN hidden
+                H_MARK();   // 15: h exchange
+                {
+                    float acc[1][H_GMAX] = {};
+#pragma unroll 1
+                    for (int j = 0; j < 4; ++j) {
+                        const float* tile = h_tile_acquire(c);
+                        h_tile_fma(c, tile, hbuf, 1024, 256 * j, acc[0]);
+                        h_tile_release(c);
+                    }
+                    h_reduce_apply<1>(c, acc, [&](int, int g, int col, float v) {
+                        const int n = c.rank * 16 + col;
+                        h_bcast(c, HSmem::xbuf + (g * 256 + n) * 4, (v + P[HP_B2 + col]) + xbuf[g * 256 + n]);
+                    });
+                }
+                H_MARK();   // 16: W2
+                h_exchange(c, (uint32_t)c.G * 1024u);                     // x3
+                H_MARK();   // 17: x3 exchange
+            }
+            // ---------- final LayerNorm, vocabulary slice, logits all-gather ----------
+            h_layer_norm(c, fp, fp + 256);
+            {
+                float acc[1][H_GMAX] = {};
+                const float* tile = h_tile_acquire(c);
+                h_tile_fma(c, tile, nbuf, 256, 0, acc[0]);
+                h_tile_release(c);
+                h_reduce_apply<1>(c, acc, [&](int, int g, int col, float v) {
+                    const int n = c.rank * 16 + col;
+                    h_bcast(c, HSmem::lgbuf + (g * 256 + n) * 4, v + fp[512 + n]);
+                });
+            }
+            h_exchange(c, (uint32_t)c.G * 1024u);
+            // ---------- log_softmax, grammar mask, argmax (identically in every CTA) ----------
+            if (c.warp < c.G && s_fin[c.warp] == 0) {
+                const int g = c.warp, row = row0 + g;
+                float lg[8];
+                float m = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int v = i * 32 + c.lane;
+                    lg[i] = (v < a.g.vocab) ? lgbuf[g * 256 + v] : -INFINITY;
+                    m = fmaxf(m, lg[i]);
+                }
+                m = warp_max(m);
+                float se = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) se += (i * 32 + c.lane < a.g.vocab) ? expf(lg[i] - m) : 0.f;
+                se = warp_sum(se);
+                const float lse = logf(se);
+                const int tok_in = s_tok[g];
+                const bool in_x = tok_in >= a.g.offset && tok_in < a.g.offset + a.g.maxx;
+                const bool in_y = tok_in >= a.g.offset + a.g.maxx;
+                float bv = -INFINITY;
+                int bi = 1 << 30;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int v = i * 32 + c.lane;
+                    float lp = (lg[i] - m) - lse;
+                    if (in_x && v < a.g.offset + a.g.maxx) lp = -10000.0f;
+                    if (in_y && v >= a.g.offset) lp = -10000.0f;
+                    if (t == 0 && v == a.g.eos) lp = -1e20f;
+                    if (v >= a.g.vocab) lp = -INFINITY;
+                    if (lp > bv) { bv = lp; bi = v; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                }
+                const int fin = (bi == a.g.eos) || (t == a.g.max_len - 1);
+                if (c.rank == 0) {
+                    float* hd = a.hidden + ((size_t)row * a.T + t) * 256;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) hd[i * 32 + c.lane] = nbuf[g * 256 + i * 32 + c.lane];
+                    if (c.lane == 0) {
+                        a.ids[(size_t)row * a.T + t] = bi;
+                        a.logp[(size_t)row * a.T + t] = bv;
+                        if (fin) { a.lens[row] = t + 1; atomicMax(a.steps_run, t + 1); }
+                        h_st_release(a.row_state + row, ((unsigned)(t + 1) << 1) | (fin ? 1u : 0u));
+                    }
+                }
+                __syncwarp();
+                if (c.lane == 0) { s_tok[g] = bi; s_fin[g] = fin; }
+            }
+            h_sync();
+        }
+    }
+    h_cluster_sync_all();
+}
+
+cudaError_t mega16_configure(int* max_clusters) {
+    cudaError_t e = cudaFuncSetAttribute(decode_mega16_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(decode_mega16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HSmem::total);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(H_CS * 8);
+    cfg.blockDim = dim3(H_THREADS);
+    cfg.dynamicSmemBytes = HSmem::total;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = H_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    e = cudaOccupancyMaxActiveClusters(&n, decode_mega16_kernel, &cfg);
+    if (e != cudaSuccess) { *max_clusters = 0; cudaGetLastError(); return cudaSuccess; }   // unsupported -> path disabled
+    *max_clusters = n;
+    return cudaSuccess;
+}
+
+cudaError_t mega16_launch(const MegaArgs& a, int clusters, cudaStream_t s) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(H_CS * clusters);
+    cfg.blockDim = dim3(H_THREADS);
+    cfg.dynamicSmemBytes = HSmem::total;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = H_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, decode_mega16_kernel, a);
+}
+
+}  // namespace mnx
