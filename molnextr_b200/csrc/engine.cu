@@ -534,7 +534,7 @@ static int decode_internal(mnx_engine* e, const float* features, int B, int S, c
     // (half the per-SM byte stream), then 8-CTA clusters, else the multi-kernel graph path
     const int usable16 = e->max_clusters16 < 8 ? e->max_clusters16 : 8;
     const int usable8 = e->max_clusters < 16 ? e->max_clusters : 16;
-    const bool fits16 = usable16 > 0 && B <= usable16 * MG_GMAX_H;
+    const bool fits16 = usable16 > 0 && B <= usable16 * MG16_GMAX_H;
     const bool fits8 = usable8 > 0 && B <= usable8 * MG_GMAX_H;
     if (e->decode_path == 3 && !fits16) return fail(e, MNX_ERR_CAPACITY, "16-CTA cluster path forced but %d rows do not fit %d clusters", B, usable16);
     if (e->decode_path == 2 && !fits8) return fail(e, MNX_ERR_CAPACITY, "8-CTA cluster path forced but %d rows do not fit %d clusters", B, usable8);

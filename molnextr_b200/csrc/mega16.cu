@@ -13,6 +13,7 @@
 #include "mega.cuh"
 
 namespace mnx {
+namespace {
 
 #define H_CS 16
 #define H_THREADS 288
@@ -622,6 +623,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a)
     }
     h_cluster_sync_all();
 }
+
+}  // anonymous namespace
 
 cudaError_t mega16_configure(int* max_clusters) {
     cudaError_t e = cudaFuncSetAttribute(decode_mega16_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
