@@ -48,93 +48,123 @@ struct ConvNextState {
 
 // ------------------------------------------------------------------------------------------
 // depthwise 7x7 (pad 3) + bias + LayerNorm over channels -> bf16
-// One CTA = TILE x TILE output pixels x ALL channels.  Channels are processed 32 at a time (lane =
-// channel): the (TILE+6)^2 x 32 input halo tile of chunk i+1 is fetched by TMA while chunk i is
-// convolved with a register sliding window (one shared-memory read per 4 FMAs); conv outputs stay
-// in shared memory until the whole channel vector of every pixel is known, then each warp
-// normalises its pixels and writes bf16 rows (the fc1 GEMM's A operand).
+// One CTA = TILE x TILE output pixels x ALL channels.  Channels are processed 64 at a time (lane = a
+// PAIR of channels, arithmetic on packed fp32x2 FFMA2): the (TILE+6)^2 x 64 input halo tile and the
+// 49 x 64 weight tile of chunk i+1 are fetched by TMA (4-D / 2-D tensor maps; out-of-bounds zero fill is
+// the conv's zero padding) while chunk i is convolved with a register sliding window along x (one
+// 8-byte shared-memory read per 7 FFMA2).  Conv outputs wait in shared memory as bf16 -- the GEMM
+// operand precision -- while their fp32 sum / sum of squares accumulate in registers; once every
+// channel of a pixel is known the warp that owns the pixel row normalises it and writes bf16 rows
+// (the fc1 GEMM's A operand).
 // ------------------------------------------------------------------------------------------
-template <int TILE>
-__global__ void __launch_bounds__(TILE * 32) dwconv_ln_kernel(const __grid_constant__ CUtensorMap tmap_x, int H, int W,
-                                                              int C, const float* __restrict__ dw_w,
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(r)
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+          "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&r);
+}
+
+template <int TILE, int C>
+__global__ void __launch_bounds__(TILE * 32) dwconv_ln_kernel(const __grid_constant__ CUtensorMap tmap_x,
+                                                              const __grid_constant__ CUtensorMap tmap_w, int H, int W,
                                                               const float* __restrict__ dw_b,
                                                               const float* __restrict__ ln_w,
                                                               const float* __restrict__ ln_b, float eps,
                                                               __nv_bfloat16* __restrict__ out) {
     constexpr int IN = TILE + 6;
-    constexpr int IN_FLOATS = IN * IN * 32;
+    constexpr int IN_FLOATS = IN * IN * 64;
+    constexpr int W_FLOATS = 49 * 64;
+    constexpr int NCHUNK = C / 64;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-    float* in_buf = reinterpret_cast<float*>(sm);                       // [2][IN][IN][32]
-    float* obuf = in_buf + 2 * IN_FLOATS;                               // [TILE*TILE][C]
+    float* in_buf = reinterpret_cast<float*>(sm);                                   // [2][IN][IN][64]
+    float* w_buf = in_buf + 2 * IN_FLOATS;                                          // [2][49][64]
+    __nv_bfloat16* obuf = reinterpret_cast<__nv_bfloat16*>(w_buf + 2 * W_FLOATS);   // [TILE*TILE][C]
     uint64_t* bar = reinterpret_cast<uint64_t*>(obuf + (size_t)TILE * TILE * C);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;        // warp = output row of the tile
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;                    // warp = output row of the tile
     const int tiles_x = (W + TILE - 1) / TILE;
     const int b = blockIdx.y;
     const int ty = blockIdx.x / tiles_x, tx = blockIdx.x % tiles_x;
     const int y0 = ty * TILE, x0 = tx * TILE;
-    const int nchunks = C / 32;
 
     if (threadIdx.x == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
         fence_barrier_init();
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_x)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w)) : "memory");
     }
     __syncthreads();
     auto issue = [&](int chunk) {
         uint64_t* bb = &bar[chunk & 1];
-        mbar_arrive_expect_tx(bb, IN_FLOATS * 4);
+        mbar_arrive_expect_tx(bb, (IN_FLOATS + W_FLOATS) * 4);
         asm volatile(
             "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
                 smem_u32(in_buf + (chunk & 1) * IN_FLOATS)),
-            "l"(reinterpret_cast<uint64_t>(&tmap_x)), "r"(smem_u32(bb)), "r"(chunk * 32), "r"(x0 - 3), "r"(y0 - 3), "r"(b)
+            "l"(reinterpret_cast<uint64_t>(&tmap_x)), "r"(smem_u32(bb)), "r"(chunk * 64), "r"(x0 - 3), "r"(y0 - 3), "r"(b)
+            : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                smem_u32(w_buf + (chunk & 1) * W_FLOATS)),
+            "l"(reinterpret_cast<uint64_t>(&tmap_w)), "r"(smem_u32(bb)), "r"(chunk * 64), "r"(0)
             : "memory");
     };
     if (threadIdx.x == 0) issue(0);
 
-    for (int chunk = 0; chunk < nchunks; ++chunk) {
-        if (threadIdx.x == 0 && chunk + 1 < nchunks) issue(chunk + 1);
-        const int c = chunk * 32 + lane;
-        float wreg[49];
+    float psum[TILE], psq[TILE];   // this lane's share of each pixel's channel sum / sum of squares
 #pragma unroll
-        for (int i = 0; i < 49; ++i) wreg[i] = dw_w[(size_t)i * C + c];
-        const float bias = dw_b[c];
+    for (int ox = 0; ox < TILE; ++ox) psum[ox] = psq[ox] = 0.f;
+
+#pragma unroll 1
+    for (int chunk = 0; chunk < NCHUNK; ++chunk) {
+        if (threadIdx.x == 0 && chunk + 1 < NCHUNK) issue(chunk + 1);
+        const int c = chunk * 64 + 2 * lane;
+        const float2 bias = *reinterpret_cast<const float2*>(dw_b + c);
         mbar_wait(&bar[chunk & 1], (uint32_t)(chunk >> 1) & 1u);
-        const float* tin = in_buf + (chunk & 1) * IN_FLOATS;
-        float acc[TILE];
+        const float2* tin = reinterpret_cast<const float2*>(in_buf + (chunk & 1) * IN_FLOATS);
+        const float2* tw = reinterpret_cast<const float2*>(w_buf + (chunk & 1) * W_FLOATS);
+        float2 acc[TILE];
 #pragma unroll
         for (int ox = 0; ox < TILE; ++ox) acc[ox] = bias;
 #pragma unroll
         for (int ky = 0; ky < 7; ++ky) {
-            float row[IN];
+            float2 row[IN];
 #pragma unroll
             for (int ix = 0; ix < IN; ++ix) row[ix] = tin[((warp + ky) * IN + ix) * 32 + lane];
 #pragma unroll
-            for (int kx = 0; kx < 7; ++kx)
+            for (int kx = 0; kx < 7; ++kx) {
+                const float2 wv = tw[(ky * 7 + kx) * 32 + lane];
 #pragma unroll
-                for (int ox = 0; ox < TILE; ++ox) acc[ox] = fmaf(row[ox + kx], wreg[ky * 7 + kx], acc[ox]);
+                for (int ox = 0; ox < TILE; ++ox) acc[ox] = ffma2(row[ox + kx], wv, acc[ox]);
+            }
         }
 #pragma unroll
-        for (int ox = 0; ox < TILE; ++ox) obuf[(size_t)(warp * TILE + ox) * C + c] = acc[ox];
-        __syncthreads();   // everyone is done with this input buffer before it is refilled (chunk + 2)
+        for (int ox = 0; ox < TILE; ++ox) {
+            psum[ox] += acc[ox].x + acc[ox].y;
+            psq[ox] = fmaf(acc[ox].x, acc[ox].x, fmaf(acc[ox].y, acc[ox].y, psq[ox]));
+            *reinterpret_cast<__nv_bfloat162*>(obuf + (size_t)(warp * TILE + ox) * C + c) = __floats2bfloat162_rn(acc[ox].x, acc[ox].y);
+        }
+        __syncthreads();   // everyone is done with this input / weight buffer before it is refilled (chunk + 2)
     }
-    // LayerNorm over C for each pixel of the tile (warp = output row: TILE pixels per warp)
+    // LayerNorm over C for each pixel of the warp's row (statistics from the unrounded fp32 conv outputs)
+#pragma unroll
     for (int ox = 0; ox < TILE; ++ox) {
+        const float mean = warp_sum(psum[ox]) * (1.0f / (float)C);
+        const float var = fmaxf(warp_sum(psq[ox]) * (1.0f / (float)C) - mean * mean, 0.f);
+        const float rstd = 1.0f / sqrtf(var + eps);
         const int y = y0 + warp, x = x0 + ox;
         if (y >= H || x >= W) continue;
-        const float* v = obuf + (size_t)(warp * TILE + ox) * C;
-        float s = 0.f;
-        for (int i = lane; i < C; i += 32) s += v[i];
-        const float mean = warp_sum(s) / (float)C;
-        float sq = 0.f;
-        for (int i = lane; i < C; i += 32) { const float d = v[i] - mean; sq += d * d; }
-        const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)C + eps);
+        const __nv_bfloat16* v = obuf + (size_t)(warp * TILE + ox) * C;
         __nv_bfloat16* o = out + (((size_t)b * H + y) * W + x) * C;
+#pragma unroll
         for (int i = lane * 2; i < C; i += 64) {
-            const float a0 = (v[i] - mean) * rstd * ln_w[i] + ln_b[i];
-            const float a1 = (v[i + 1] - mean) * rstd * ln_w[i + 1] + ln_b[i + 1];
-            *reinterpret_cast<__nv_bfloat162*>(o + i) = __floats2bfloat162_rn(a0, a1);
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(v + i));
+            const float2 g = *reinterpret_cast<const float2*>(ln_w + i);
+            const float2 be = *reinterpret_cast<const float2*>(ln_b + i);
+            *reinterpret_cast<__nv_bfloat162*>(o + i) =
+                __floats2bfloat162_rn((f.x - mean) * rstd * g.x + be.x, (f.y - mean) * rstd * g.y + be.y);
         }
     }
 }
@@ -222,7 +252,7 @@ static int cn_bf16(mnx_engine* e, const std::string& key, std::initializer_list<
 
 template <int TILE>
 static size_t dw_smem(int C) {
-    return (size_t)(2 * (TILE + 6) * (TILE + 6) * 32 + TILE * TILE * C) * 4 + 16 + 128;
+    return (size_t)(2 * (TILE + 6) * (TILE + 6) * 64 + 2 * 49 * 64) * 4 + (size_t)TILE * TILE * C * 2 + 16 + 128;
 }
 
 int convnext_finalize(mnx_engine* e, ConvNextState** out, const mnx_config& cfg) {
@@ -234,8 +264,10 @@ int convnext_finalize(mnx_engine* e, ConvNextState** out, const mnx_config& cfg)
         if (qres != cudaDriverEntryPointSuccess || !fn) { mnx_set_error(e, "cuTensorMapEncodeTiled unavailable"); return MNX_ERR_CUDA; }
         g_cn_encode = reinterpret_cast<PFN_encodeTiled>(fn);
     }
-    CN_CUDA(e, cudaFuncSetAttribute(dwconv_ln_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem<8>(512)));
-    CN_CUDA(e, cudaFuncSetAttribute(dwconv_ln_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem<4>(1024)));
+    CN_CUDA(e, cudaFuncSetAttribute(dwconv_ln_kernel<8, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem<8>(128)));
+    CN_CUDA(e, cudaFuncSetAttribute(dwconv_ln_kernel<8, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem<8>(256)));
+    CN_CUDA(e, cudaFuncSetAttribute(dwconv_ln_kernel<8, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem<8>(512)));
+    CN_CUDA(e, cudaFuncSetAttribute(dwconv_ln_kernel<4, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem<4>(1024)));
     if (cfg.max_height % 32 != 0 || cfg.max_width % 32 != 0) {
         mnx_set_error(e, "ConvNeXt-B needs image bounds that are multiples of 32");
         return MNX_ERR_INVALID;
@@ -304,23 +336,43 @@ static cudaError_t cn_gemm(const __nv_bfloat16* A, const __nv_bfloat16* W, long 
     return gemm_tc_launch(p, s);
 }
 
-template <int TILE>
-static int launch_dwconv(mnx_engine* e, const float* x, int B, int H, int W, int C, const CnBlockW& w,
-                         __nv_bfloat16* out, cudaStream_t s) {
-    CUtensorMap map;
-    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-    const cuuint32_t box[4] = {32, (cuuint32_t)(TILE + 6), (cuuint32_t)(TILE + 6), 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = g_cn_encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { mnx_set_error(e, "cuTensorMapEncodeTiled failed for the dwconv input"); return MNX_ERR_CUDA; }
+template <int TILE, int C>
+static int launch_dwconv_t(mnx_engine* e, const float* x, int B, int H, int W, const CnBlockW& w, __nv_bfloat16* out,
+                           cudaStream_t s) {
+    CUtensorMap map, wmap;
+    {
+        const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+        const cuuint32_t box[4] = {64, (cuuint32_t)(TILE + 6), (cuuint32_t)(TILE + 6), 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = g_cn_encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { mnx_set_error(e, "cuTensorMapEncodeTiled failed for the dwconv input"); return MNX_ERR_CUDA; }
+    }
+    {
+        const cuuint64_t dims[2] = {(cuuint64_t)C, 49};
+        const cuuint64_t strides[1] = {(cuuint64_t)C * 4};
+        const cuuint32_t box[2] = {64, 49};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult r = g_cn_encode(&wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w.dw_w), dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { mnx_set_error(e, "cuTensorMapEncodeTiled failed for the dwconv weights"); return MNX_ERR_CUDA; }
+    }
     const int tiles = ((H + TILE - 1) / TILE) * ((W + TILE - 1) / TILE);
-    dwconv_ln_kernel<TILE><<<dim3(tiles, B), TILE * 32, dw_smem<TILE>(C), s>>>(map, H, W, C, w.dw_w, w.dw_b, w.ln_w, w.ln_b,
-                                                                                1e-6f, out);
+    dwconv_ln_kernel<TILE, C><<<dim3(tiles, B), TILE * 32, dw_smem<TILE>(C), s>>>(map, wmap, H, W, w.dw_b, w.ln_w, w.ln_b, 1e-6f, out);
     CN_CUDA(e, cudaGetLastError());
     return MNX_OK;
+}
+static int launch_dwconv(mnx_engine* e, const float* x, int B, int H, int W, int C, const CnBlockW& w, __nv_bfloat16* out,
+                         cudaStream_t s) {
+    switch (C) {
+        case 128: return launch_dwconv_t<8, 128>(e, x, B, H, W, w, out, s);
+        case 256: return launch_dwconv_t<8, 256>(e, x, B, H, W, w, out, s);
+        case 512: return launch_dwconv_t<8, 512>(e, x, B, H, W, w, out, s);
+        default: return launch_dwconv_t<4, 1024>(e, x, B, H, W, w, out, s);
+    }
 }
 
 int convnext_forward(mnx_engine* e, ConvNextState* st, const float* images, int B, int H, int W, float* features,
@@ -352,8 +404,7 @@ int convnext_forward(mnx_engine* e, ConvNextState* st, const float* images, int 
         const long long M = (long long)B * Hc * Wc;
         for (int j = 0; j < CN_DEPTH[stage]; ++j) {
             const CnBlockW& w = st->blocks[stage][j];
-            if (C <= 512) CN_TRY(launch_dwconv<8>(e, x, B, Hc, Wc, C, w, st->abuf, s));
-            else CN_TRY(launch_dwconv<4>(e, x, B, Hc, Wc, C, w, st->abuf, s));
+            CN_TRY(launch_dwconv(e, x, B, Hc, Wc, C, w, st->abuf, s));
             ++nl;
             CN_CUDA(e, cn_gemm(st->abuf, w.fc1_w, M, 4 * C, C, GEMM_EPI_GELU_BF16, w.fc1_b, nullptr, st->hbuf, s)); ++nl;
             CN_CUDA(e, cn_gemm(st->hbuf, w.fc2_w, M, C, 4 * C, GEMM_EPI_RESADD_F32, w.fc2_b, w.gamma, x, s)); ++nl;
@@ -377,7 +428,7 @@ int convnext_time_kernel(mnx_engine* e, ConvNextState* st, int which, int iters,
     int rc = MNX_OK;
     for (int i = 0; i < 3 + iters && rc == MNX_OK; ++i) {
         if (i == 3) cudaEventRecord(e0, s);
-        rc = (C <= 512) ? launch_dwconv<8>(e, x, B, Hc, Wc, C, w, st->abuf, s) : launch_dwconv<4>(e, x, B, Hc, Wc, C, w, st->abuf, s);
+        rc = launch_dwconv(e, x, B, Hc, Wc, C, w, st->abuf, s);
     }
     cudaEventRecord(e1, s);
     cudaStreamSynchronize(s);
