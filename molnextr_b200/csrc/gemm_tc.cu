@@ -1,12 +1,13 @@
 // bf16 GEMM on the 5th-generation tensor cores of sm_100a, hand-written:
-//   * operands staged by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) into a 3-stage ring,
+//   * operands staged by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) into a 5-stage ring,
 //   * one elected thread issues tcgen05.mma (UMMA 128 x 128 x 16, kind::f16, bf16 in / fp32 out),
 //   * the accumulator lives in TMEM (128 lanes x 128 columns) and is read back with tcgen05.ld,
 //   * four epilogue warps apply bias / GELU / layer-scale / residual-add (optionally through a
 //     row map that undoes Swin's window partition + cyclic shift) and write straight to HBM.
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
-// One 128 x 128 output tile per CTA; two CTAs are co-resident per SM (96 KB of shared memory and
-// 128 TMEM columns each) so one CTA's epilogue overlaps the other's main loop.
+// Persistent: one CTA per SM walks over 128 x 128 output tiles (n fastest, so CTAs working at the same
+// time share A rows through L2); the accumulator is double-buffered in TMEM (2 x 128 columns) so the
+// epilogue of tile i overlaps the TMA / MMA main loop of tile i+1; a 5-stage operand ring (160 KB).
 #include "gemm_tc.cuh"
 
 #include <cuda.h>
@@ -15,12 +16,12 @@
 
 namespace mnx {
 
-static constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
+static constexpr int BM = 128, BN = 128, BK = 64, STAGES = 5;
 static constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 static constexpr int B_STAGE_BYTES = BN * BK * 2;   // 16 KB
 static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
 static constexpr int GEMM_THREADS = 192;
-static constexpr uint32_t TMEM_COLS = 128;
+static constexpr uint32_t TMEM_COLS = 256;   // two 128-column accumulators
 
 // ---- PTX wrappers --------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
@@ -101,7 +102,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 2)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, GemmKernelArgs g) {
     extern __shared__ uint8_t smem_raw[];
     // 128B-swizzled TMA / UMMA tiles need 1024-byte aligned bases
@@ -110,12 +111,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* acc_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+    uint64_t* acc_full = empty_bar + STAGES;     // [2] accumulator ready for the epilogue
+    uint64_t* acc_empty = acc_full + 2;          // [2] accumulator drained by the 4 epilogue warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tile = blockIdx.x, m_tile = blockIdx.y;
     const int num_kb = g.K / BK;
+    const int n_tiles = g.N / BN;
+    const int m_tiles = (g.M + BM - 1) / BM;
+    const int total_tiles = n_tiles * m_tiles;
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
@@ -124,7 +128,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(acc_bar, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 4);
+        }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -136,96 +143,113 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-                mbar_wait(&empty_bar[s], ph ^ 1u);     // slot free (first lap passes immediately)
-                mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + B_STAGE_BYTES);
-                tma_load_2d(smem_a + s * A_STAGE_BYTES, &tmap_a, &full_bar[s], kb * BK, m_tile * BM);
-                tma_load_2d(smem_b + s * B_STAGE_BYTES, &tmap_w, &full_bar[s], kb * BK, n_tile * BN);
+            uint32_t it = 0;   // running k-block counter over all tiles of this CTA
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n_tile = tile % n_tiles, m_tile = tile / n_tiles;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                    mbar_wait(&empty_bar[s], ph ^ 1u);     // slot free (first lap passes immediately)
+                    mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + B_STAGE_BYTES);
+                    tma_load_2d(smem_a + s * A_STAGE_BYTES, &tmap_a, &full_bar[s], kb * BK, m_tile * BM);
+                    tma_load_2d(smem_b + s * B_STAGE_BYTES, &tmap_w, &full_bar[s], kb * BK, n_tile * BN);
+                }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
             const uint32_t idesc = make_idesc(BM, BN);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-                mbar_wait(&full_bar[s], ph);
+            uint32_t it = 0, j = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+                const uint32_t acc = j & 1u;
+                mbar_wait(&acc_empty[acc], ((j >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + s * A_STAGE_BYTES));
-                const uint64_t b_desc = make_smem_desc(smem_u32(smem_b + s * B_STAGE_BYTES));
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint64_t a_desc = make_smem_desc(smem_u32(smem_a + s * A_STAGE_BYTES));
+                    const uint64_t b_desc = make_smem_desc(smem_u32(smem_b + s * B_STAGE_BYTES));
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    // advancing 16 bf16 (32 bytes) along K inside the swizzle atom = +2 in 16-byte units
-                    umma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                              (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // advancing 16 bf16 (32 bytes) along K inside the swizzle atom = +2 in 16-byte units
+                        umma_bf16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[s]);            // frees the smem slot when these MMAs retire
                 }
-                umma_commit(&empty_bar[s]);            // frees the smem slot when these MMAs retire
+                umma_commit(&acc_full[acc]);               // accumulator complete
             }
-            umma_commit(acc_bar);                      // accumulator complete
         }
     } else {
         // ===================== epilogue: TMEM -> registers -> HBM =====================
         const int q = warp & 3;                        // TMEM lane quarter this warp may access
-        const int row_in_tile = q * 32 + lane;
-        const int m = m_tile * BM + row_in_tile;
-        mbar_wait(acc_bar, 0);
-        tc_fence_after();
-        int dst_row = m;
-        if (g.row_map != nullptr && m < g.M) dst_row = g.row_map[m];
-        const bool live = (m < g.M) && (dst_row >= 0);
+        uint32_t j = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+            const int n_tile = tile % n_tiles, m_tile = tile / n_tiles;
+            const uint32_t acc = j & 1u;
+            const int row_in_tile = q * 32 + lane;
+            const int m = m_tile * BM + row_in_tile;
+            int dst_row = m;
+            if (g.row_map != nullptr && m < g.M) dst_row = g.row_map[m];
+            const bool live = (m < g.M) && (dst_row >= 0);
+            mbar_wait(&acc_full[acc], (j >> 1) & 1u);
+            tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-            if (!live) continue;
-            const int n0 = n_tile * BN + c * 32;
-            float v[32];
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(c * 32), r);
+                if (!live) continue;
+                const int n0 = n_tile * BN + c * 32;
+                float v[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-            if (g.bias != nullptr) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(g.bias + n0 + i);
-                    v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
-                }
-            }
-            if (g.epilogue == GEMM_EPI_BF16 || g.epilogue == GEMM_EPI_GELU_BF16) {
-                if (g.epilogue == GEMM_EPI_GELU_BF16) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-                }
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)dst_row * g.N + n0;
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    uint4 pk;
-                    pk.x = pack_bf16(v[i], v[i + 1]); pk.y = pack_bf16(v[i + 2], v[i + 3]);
-                    pk.z = pack_bf16(v[i + 4], v[i + 5]); pk.w = pack_bf16(v[i + 6], v[i + 7]);
-                    *reinterpret_cast<uint4*>(o + i) = pk;
-                }
-            } else if (g.epilogue == GEMM_EPI_RESADD_F32) {
-                float* o = reinterpret_cast<float*>(g.out) + (size_t)dst_row * g.N + n0;
-                if (g.gamma != nullptr) {
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                if (g.bias != nullptr) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
-                        const float4 g4 = *reinterpret_cast<const float4*>(g.gamma + n0 + i);
-                        v[i] *= g4.x; v[i + 1] *= g4.y; v[i + 2] *= g4.z; v[i + 3] *= g4.w;
+                        const float4 b4 = *reinterpret_cast<const float4*>(g.bias + n0 + i);
+                        v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
                     }
                 }
+                if (g.epilogue == GEMM_EPI_BF16 || g.epilogue == GEMM_EPI_GELU_BF16) {
+                    if (g.epilogue == GEMM_EPI_GELU_BF16) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    float4 x4 = *reinterpret_cast<float4*>(o + i);
-                    x4.x += v[i]; x4.y += v[i + 1]; x4.z += v[i + 2]; x4.w += v[i + 3];
-                    *reinterpret_cast<float4*>(o + i) = x4;
+                        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+                    }
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)dst_row * g.N + n0;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        uint4 pk;
+                        pk.x = pack_bf16(v[i], v[i + 1]); pk.y = pack_bf16(v[i + 2], v[i + 3]);
+                        pk.z = pack_bf16(v[i + 4], v[i + 5]); pk.w = pack_bf16(v[i + 6], v[i + 7]);
+                        *reinterpret_cast<uint4*>(o + i) = pk;
+                    }
+                } else if (g.epilogue == GEMM_EPI_RESADD_F32) {
+                    float* o = reinterpret_cast<float*>(g.out) + (size_t)dst_row * g.N + n0;
+                    if (g.gamma != nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 g4 = *reinterpret_cast<const float4*>(g.gamma + n0 + i);
+                            v[i] *= g4.x; v[i + 1] *= g4.y; v[i + 2] *= g4.z; v[i + 3] *= g4.w;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        float4 x4 = *reinterpret_cast<float4*>(o + i);
+                        x4.x += v[i]; x4.y += v[i + 1]; x4.z += v[i + 2]; x4.w += v[i + 3];
+                        *reinterpret_cast<float4*>(o + i) = x4;
+                    }
+                } else {
+                    float* o = reinterpret_cast<float*>(g.out) + (size_t)dst_row * g.N + n0;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                 }
-            } else {
-                float* o = reinterpret_cast<float*>(g.out) + (size_t)dst_row * g.N + n0;
-#pragma unroll
-                for (int i = 0; i < 32; i += 4)
-                    *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
             }
+            // all TMEM reads of this accumulator by this warp have completed (tcgen05.wait::ld inside tmem_ld32)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
         }
     }
     // ---- teardown: every role is done with TMEM before it is released ----
@@ -242,6 +266,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static PFN_encodeTiled g_encode = nullptr;
+static int g_num_sms = 148;
 
 cudaError_t gemm_tc_configure() {
     if (g_encode == nullptr) {
@@ -252,6 +277,9 @@ cudaError_t gemm_tc_configure() {
         if (qres != cudaDriverEntryPointSuccess || fn == nullptr) return cudaErrorNotSupported;
         g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
     }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     return cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
 }
 
@@ -275,7 +303,8 @@ cudaError_t gemm_tc_launch(const GemmParams& p, cudaStream_t s) {
     if (!make_map(&ma, p.A, (uint64_t)p.M, (uint64_t)p.K, BM)) return cudaErrorInvalidValue;
     if (!make_map(&mw, p.W, (uint64_t)p.N, (uint64_t)p.K, BN)) return cudaErrorInvalidValue;
     GemmKernelArgs g{p.M, p.N, p.K, p.epilogue, p.bias, p.gamma, p.row_map, p.out};
-    dim3 grid(p.N / BN, (p.M + BM - 1) / BM);
+    const int total_tiles = (p.N / BN) * ((p.M + BM - 1) / BM);
+    const int grid = total_tiles < g_num_sms ? total_tiles : g_num_sms;
     gemm_tc_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, s>>>(ma, mw, g);
     return cudaGetLastError();
 }

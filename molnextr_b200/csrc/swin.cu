@@ -50,6 +50,7 @@ struct SwinState {
 // ------------------------------------------------------------------------------------------
 // patch embed: conv 4x4 stride 4 (3 -> 128) + LayerNorm(128, eps 1e-5); 8 tokens per CTA
 // ------------------------------------------------------------------------------------------
+#define PE_TOK_PER_CTA 64
 __global__ void __launch_bounds__(128) patch_embed_kernel(const float* __restrict__ img, int B, int H, int W, int Hp,
                                                           int Wp, const float* __restrict__ w,
                                                           const float* __restrict__ bias, const float* __restrict__ ln_w,
@@ -58,57 +59,62 @@ __global__ void __launch_bounds__(128) patch_embed_kernel(const float* __restric
     __shared__ float patch[8][48];
     __shared__ float red[8][4][2];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const long long tok0 = (long long)blockIdx.x * 8;
     const long long ntok = (long long)B * Hp * Wp;
     float wr[48];
 #pragma unroll
     for (int k = 0; k < 48; ++k) wr[k] = w[tid * 48 + k];
-    for (int i = tid; i < 8 * 48; i += 128) {
-        const int t = i / 48, k = i % 48;
-        const long long tok = tok0 + t;
-        float v = 0.f;
-        if (tok < ntok) {
-            const int b = (int)(tok / ((long long)Hp * Wp));
-            const int r = (int)(tok % ((long long)Hp * Wp));
-            const int py = r / Wp, px = r % Wp;
-            const int c = k >> 4, dy = (k >> 2) & 3, dx = k & 3;
-            const int yy = py * 4 + dy, xx = px * 4 + dx;
-            if (yy < H && xx < W) v = img[(((size_t)b * 3 + c) * H + yy) * W + xx];
+    const float bi = bias[tid], g = ln_w[tid], be = ln_b[tid];
+    // the channel's 48 weights stay in registers while the CTA walks over 64 tokens, 8 at a time
+    for (int it = 0; it < PE_TOK_PER_CTA / 8; ++it) {
+        const long long tok0 = (long long)blockIdx.x * PE_TOK_PER_CTA + it * 8;
+        if (tok0 >= ntok) break;
+        for (int i = tid; i < 8 * 48; i += 128) {
+            const int t = i / 48, k = i % 48;
+            const long long tok = tok0 + t;
+            float v = 0.f;
+            if (tok < ntok) {
+                const int b = (int)(tok / ((long long)Hp * Wp));
+                const int r = (int)(tok % ((long long)Hp * Wp));
+                const int py = r / Wp, px = r % Wp;
+                const int c = k >> 4, dy = (k >> 2) & 3, dx = k & 3;
+                const int yy = py * 4 + dy, xx = px * 4 + dx;
+                if (yy < H && xx < W) v = img[(((size_t)b * 3 + c) * H + yy) * W + xx];
+            }
+            patch[t][k] = v;
         }
-        patch[t][k] = v;
-    }
-    __syncthreads();
-    float acc[8];
+        __syncthreads();
+        float acc[8];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        float a = bias[tid];
+        for (int t = 0; t < 8; ++t) {
+            float a = bi;
 #pragma unroll
-        for (int k = 0; k < 48; ++k) a = fmaf(patch[t][k], wr[k], a);
-        acc[t] = a;
-    }
-    // LayerNorm over the 128 channels of each token (two-pass)
+            for (int k = 0; k < 48; ++k) a = fmaf(patch[t][k], wr[k], a);
+            acc[t] = a;
+        }
+        // LayerNorm over the 128 channels of each token (two-pass)
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        const float s = warp_sum(acc[t]);
-        if (lane == 0) red[t][wid][0] = s;
-    }
-    __syncthreads();
-    float mean[8];
+        for (int t = 0; t < 8; ++t) {
+            const float s = warp_sum(acc[t]);
+            if (lane == 0) red[t][wid][0] = s;
+        }
+        __syncthreads();
+        float mean[8];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) mean[t] = ((red[t][0][0] + red[t][1][0]) + (red[t][2][0] + red[t][3][0])) * (1.0f / 128.0f);
+        for (int t = 0; t < 8; ++t) mean[t] = ((red[t][0][0] + red[t][1][0]) + (red[t][2][0] + red[t][3][0])) * (1.0f / 128.0f);
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        const float d = acc[t] - mean[t];
-        const float s = warp_sum(d * d);
-        if (lane == 0) red[t][wid][1] = s;
-    }
-    __syncthreads();
-    const float g = ln_w[tid], be = ln_b[tid];
+        for (int t = 0; t < 8; ++t) {
+            const float d = acc[t] - mean[t];
+            const float s = warp_sum(d * d);
+            if (lane == 0) red[t][wid][1] = s;
+        }
+        __syncthreads();
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        const float var = ((red[t][0][1] + red[t][1][1]) + (red[t][2][1] + red[t][3][1])) * (1.0f / 128.0f);
-        const float rstd = 1.0f / sqrtf(var + eps);
-        if (tok0 + t < ntok) x[(size_t)(tok0 + t) * 128 + tid] = (acc[t] - mean[t]) * rstd * g + be;
+        for (int t = 0; t < 8; ++t) {
+            const float var = ((red[t][0][1] + red[t][1][1]) + (red[t][2][1] + red[t][3][1])) * (1.0f / 128.0f);
+            const float rstd = 1.0f / sqrtf(var + eps);
+            if (tok0 + t < ntok) x[(size_t)(tok0 + t) * 128 + tid] = (acc[t] - mean[t]) * rstd * g + be;
+        }
+        __syncthreads();   // patch / red are rewritten by the next iteration
     }
 }
 
@@ -117,7 +123,7 @@ cudaError_t launch_patch_embed(const float* img, int B, int H, int W, const floa
                                const float* ln_w, const float* ln_b, float eps, float* x, cudaStream_t s) {
     const int Hc = (H + 3) / 4, Wc = (W + 3) / 4;
     const long long ntok = (long long)B * Hc * Wc;
-    patch_embed_kernel<<<(unsigned)((ntok + 7) / 8), 128, 0, s>>>(img, B, H, W, Hc, Wc, w, bias, ln_w, ln_b, eps, x);
+    patch_embed_kernel<<<(unsigned)((ntok + PE_TOK_PER_CTA - 1) / PE_TOK_PER_CTA), 128, 0, s>>>(img, B, H, W, Hc, Wc, w, bias, ln_w, ln_b, eps, x);
     return cudaGetLastError();
 }
 
@@ -513,8 +519,8 @@ int swin_forward(mnx_engine* e, SwinState* st, const float* images, int B, int H
     int Hc = (H + 3) / 4, Wc = (W + 3) / 4;
     {
         const long long ntok = (long long)B * Hc * Wc;
-        patch_embed_kernel<<<(unsigned)((ntok + 7) / 8), 128, 0, s>>>(images, B, H, W, Hc, Wc, st->pe_w, st->pe_b,
-                                                                      st->pe_ln_w, st->pe_ln_b, 1e-5f, st->x0);
+        patch_embed_kernel<<<(unsigned)((ntok + PE_TOK_PER_CTA - 1) / PE_TOK_PER_CTA), 128, 0, s>>>(
+            images, B, H, W, Hc, Wc, st->pe_w, st->pe_b, st->pe_ln_w, st->pe_ln_b, 1e-5f, st->x0);
         SW_CUDA(e, cudaGetLastError()); ++nl;
     }
     float* x = st->x0;
