@@ -279,14 +279,16 @@ def run_ours(args):
     extra = {}
     if rank == 0:
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        feats = eng.encode(x_dev)
         torch.cuda.synchronize()
         e0.record()
-        feats = eng.encode(x_dev)
+        for _ in range(5):
+            feats = eng.encode(x_dev)
         e1.record()
         eng.decode_greedy(feats)
         e2.record()
         torch.cuda.synchronize()
-        extra["encoder_ms"] = e0.elapsed_time(e1)
+        extra["encoder_ms"] = e0.elapsed_time(e1) / 5
         extra["decode_ms"] = e1.elapsed_time(e2)
         extra["decode_us_per_step"] = 1000.0 * extra["decode_ms"] / max(1, eng.last_decode_steps())
         names = {1: "cross_attn", 2: "self_attn_t240", 3: "ln1_qkv", 4: "sum_ln_w1_gelu", 5: "w2_partials", 6: "pick"}

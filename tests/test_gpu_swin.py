@@ -52,7 +52,6 @@ def test_swin_features_match_reference_fixture(engine_cache, name, hw):
     x = seeded_images(cfg["img_seed"], cfg["b"], cfg["h"], cfg["w"]).cuda()
     feats = eng.encode(x)
     torch.cuda.synchronize()
-    assert feats.shape[1] == g["feat_sub"].shape[1] * 4 or feats.shape[1] == (g["feat_sub"].shape[1] - 1) * 4 + 1 or True
     _feature_check(feats, g["feat_sub"], g["feat_abs"])
 
 
