@@ -19,6 +19,8 @@
  *                             ConvNeXt-B: timm forward_features, components.py:121-126)
  *   mnx_decode_greedy     <- TransformerDecoderAR.decode + GreedySearch
  *                            MolNexTR/components.py:253-334, MolNexTR/decoding/greedy_search.py:33-128
+ *   mnx_decode_beam       <- TransformerDecoderAR.decode + BeamSearch (repaired; see below)
+ *                            MolNexTR/components.py:253-334, MolNexTR/decoding/beam_search.py:84-190
  *   mnx_atom_indices      <- CharTokenizer.sequence_to_smiles (the `indices` output only)
  *                            MolNexTR/tokenization.py:464-515
  *   mnx_edges             <- GraphPredictor.forward + get_edge_prediction
@@ -66,6 +68,8 @@ typedef struct mnx_config {
     int32_t max_y;         /* number of y bins (64)                                        */
     int32_t max_atoms;     /* bond-head capacity per image (<= max_len/3 = 160)            */
     int32_t encoder_dim;   /* 1024                                                         */
+    int32_t max_beam;      /* largest beam width mnx_decode_beam may be called with (0 or 1:
+                            * greedy only); decoder rows per call = max_batch * max_beam <= 5000 */
     /* per-id class bits for the device-side atom scan (bit0 symbol, bit1 atom, bit2 '[',
      * bit3 ']', bit4 'C', bit5 'l', bit6 'B', bit7 'r'); `vocab` entries, host pointer.   */
     const uint8_t* token_class;
@@ -102,8 +106,28 @@ int mnx_decode_greedy(mnx_engine* e, const float* features, int32_t B, int32_t S
                       int32_t* ids, int32_t* lens, float* token_logp, float* hidden,
                       void* cuda_stream);
 
+/* Beam-search decode of B images with `beam` hypotheses each (n_best <= beam returned, best first).
+ * Replaces TransformerDecoderAR.decode with BeamSearch (MolNexTR/components.py:253-334,
+ * MolNexTR/decoding/beam_search.py:84-190).  That branch cannot execute in the reference
+ * (SURVEY.md F4); the semantics implemented are the repaired ones spelled out in
+ * oracle/restate.py beam_decode ("parity unpinned": checked against that oracle only).
+ * ids        int32 (B, n_best, max_len)  ids without <sos>, including <eos>, 0-padded
+ * lens       int32 (B, n_best)
+ * scores     fp32  (B, n_best)           length-normalised log score BeamSearch files a hypothesis under
+ * token_logp fp32  (B, n_best, max_len)  masked log-prob of each chosen id
+ * hidden     fp32  (B, max_len, 256)     final-LayerNorm outputs of each image's BEST hypothesis
+ *                                        (may be NULL: kept internally for mnx_edges)
+ * Any output pointer may be NULL.  Afterwards mnx_atom_indices(ids = lens = NULL) and
+ * mnx_edges(hidden = NULL) operate on each image's best hypothesis (what Decoder.decode uses,
+ * MolNexTR/components.py:455,477).
+ * Rows are image-major, beam-minor; row r of the alive batch receives pe[r]. */
+int mnx_decode_beam(mnx_engine* e, const float* features, int32_t B, int32_t S, int32_t beam, int32_t n_best,
+                    int32_t* ids, int32_t* lens, float* scores, float* token_logp, float* hidden,
+                    void* cuda_stream);
+
 /* atom_idx int32 (B, max_atoms) positions (into ids) right after each atom's Y token,
- * n_atoms int32 (B).  Atoms beyond max_atoms raise MNX_ERR_CAPACITY at mnx_edges. */
+ * n_atoms int32 (B).  ids and lens may both be NULL: the ids / lengths of the last decode on
+ * this handle (greedy result, or best beam hypothesis) are scanned. */
 int mnx_atom_indices(mnx_engine* e, const int32_t* ids, const int32_t* lens, int32_t B,
                      int32_t* atom_idx, int32_t* n_atoms, void* cuda_stream);
 
@@ -127,6 +151,11 @@ int mnx_predict_host(mnx_engine* e, const float* images_host, int32_t B, int32_t
 /* number of kernel launches issued by this handle since creation (graph nodes counted
  * per replay); used by bench.py for `gpu_launches`. */
 int64_t mnx_launch_count(const mnx_engine* e);
+/* selections of the last mnx_decode_beam, for parity tests: trace_host int32 (max_len, B, 8),
+ * entry [t][b][j] = flat index (parent beam * vocab + token) chosen as new beam j of image b at
+ * step t, -1 where image b was no longer decoded.  Synchronises the device. */
+#define MNX_MAX_BEAM 8
+int mnx_beam_trace(mnx_engine* e, int32_t* trace_host, int32_t B);
 /* steps executed by the last decode (<= max_len) */
 int32_t mnx_last_decode_steps(const mnx_engine* e);
 /* time one internal phase in isolation for the roofline report: fills ms with the mean

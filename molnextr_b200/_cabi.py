@@ -13,8 +13,8 @@ ENCODER_NONE, ENCODER_SWIN_B, ENCODER_CONVNEXT_B = 0, 1, 2
 
 EXPORTS = [
     "mnx_create", "mnx_destroy", "mnx_last_error", "mnx_load_tensor", "mnx_finalize_weights",
-    "mnx_encode", "mnx_decode_greedy", "mnx_atom_indices", "mnx_edges", "mnx_predict",
-    "mnx_predict_host", "mnx_launch_count", "mnx_last_decode_steps", "mnx_time_kernel",
+    "mnx_encode", "mnx_decode_greedy", "mnx_decode_beam", "mnx_atom_indices", "mnx_edges", "mnx_predict",
+    "mnx_predict_host", "mnx_beam_trace", "mnx_launch_count", "mnx_last_decode_steps", "mnx_time_kernel",
     "mnx_test_gemm_bf16",
 ]
 
@@ -24,7 +24,8 @@ class MnxConfig(C.Structure):
         ("device", C.c_int32), ("encoder_kind", C.c_int32), ("max_batch", C.c_int32),
         ("max_height", C.c_int32), ("max_width", C.c_int32), ("max_len", C.c_int32),
         ("vocab", C.c_int32), ("tok_offset", C.c_int32), ("max_x", C.c_int32), ("max_y", C.c_int32),
-        ("max_atoms", C.c_int32), ("encoder_dim", C.c_int32), ("token_class", C.POINTER(C.c_uint8)),
+        ("max_atoms", C.c_int32), ("encoder_dim", C.c_int32), ("max_beam", C.c_int32),
+        ("token_class", C.POINTER(C.c_uint8)),
     ]
 
 
@@ -49,10 +50,12 @@ def load() -> C.CDLL:
     lib.mnx_finalize_weights.argtypes = [vp]
     lib.mnx_encode.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     lib.mnx_decode_greedy.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp]
+    lib.mnx_decode_beam.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.mnx_atom_indices.argtypes = [vp, vp, vp, i32, vp, vp, vp]
     lib.mnx_edges.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp]
     lib.mnx_predict.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.mnx_predict_host.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    lib.mnx_beam_trace.argtypes = [vp, vp, i32]
     lib.mnx_launch_count.argtypes = [vp]
     lib.mnx_launch_count.restype = i64
     lib.mnx_last_decode_steps.argtypes = [vp]

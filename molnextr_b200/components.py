@@ -42,12 +42,17 @@ class Decoder:
         self.compute_confidence = compute_confidence
 
     def decode(self, encoder_out: torch.Tensor, hiddens=None, refs=None, beam_size: int = 1, n_best: int = 1) -> List[dict]:
-        if beam_size != 1:
-            raise NotImplementedError("beam search is not runnable in the reference either (SURVEY.md F4); "
-                                      "only greedy decoding is part of the accelerated path")
         eng = self.engine
         tok: CharTokenizer = self.tokenizer["chartok_coords"]
-        out = eng.decode_greedy(encoder_out)
+        if beam_size != 1:
+            # the reference's beam branch cannot run; this is the repaired algorithm
+            # of oracle/restate.py beam_decode.  As in Decoder.decode (components.py:455,477) only the
+            # best hypothesis of each image goes on to the atom scan and the bond head.
+            bo = eng.decode_beam(encoder_out, beam_size, n_best)
+            out = {"ids": bo["ids"][:, 0].contiguous(), "lens": bo["lens"][:, 0].contiguous(),
+                   "logp": bo["logp"][:, 0].contiguous()}
+        else:
+            out = eng.decode_greedy(encoder_out)
         atom_idx, n_atoms = eng.atom_indices(out["ids"], out["lens"])
         if self.compute_confidence:
             edges, escore = eng.edges(atom_idx, n_atoms, return_scores=True)

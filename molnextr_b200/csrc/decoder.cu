@@ -80,6 +80,68 @@ __global__ void __launch_bounds__(1024) embed_compact_kernel(DecBuffers b, DecWe
     }
 }
 
+// Beam search: the same compaction over IMAGES (BeamSearch.update_finished removes an image
+// when its top beam has finished and it holds n_best hypotheses, beam_search.py:156-190); the
+// row list handed to the layer kernels is image-major, beam-minor, and row rank r gets pe[r].
+__global__ void __launch_bounds__(1024) embed_compact_beam_kernel(DecBuffers b, DecWeights w, Grammar g, BeamBuffers bm) {
+    __shared__ int warp_cnt[32];
+    __shared__ int warp_excl[32];
+    __shared__ int chunk_total;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    DecState* st = b.st;
+    const int t = st->next_step;
+    const int K = bm.beam;
+    const int n_prev = (t == 0) ? bm.n_img0 : st->n_img;
+    const int* prev = bm.alive_img + ((t + 1) & 1) * bm.n_img0;
+    int* cur = bm.alive_img + (t & 1) * bm.n_img0;
+    int n = 0;
+    if (t < g.max_len) {
+        for (int base = 0; base < n_prev; base += 1024) {
+            const int i = base + tid;
+            int img = -1, keep = 0;
+            if (i < n_prev) {
+                img = (t == 0) ? i : prev[i];
+                keep = (t == 0) ? 1 : (bm.img_done[img] == 0);
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            const int pre = __popc(bal & ((1u << lane) - 1u));
+            if (lane == 0) warp_cnt[wid] = __popc(bal);
+            __syncthreads();
+            if (wid == 0) {
+                const int v = warp_cnt[lane];
+                int incl = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += up;
+                }
+                warp_excl[lane] = incl - v;
+                if (lane == 31) chunk_total = incl;
+            }
+            __syncthreads();
+            if (keep) cur[n + warp_excl[wid] + pre] = img;
+            n += chunk_total;
+            __syncthreads();
+        }
+    }
+    if (tid == 0) {
+        st->n_img = n;
+        st->n_alive = n * K;
+        st->step = t;
+        st->next_step = t + 1;
+        if (n == 0) st->done = 1; else st->steps_run = t + 1;
+    }
+    __syncthreads();
+    int* rows = b.alive + (t & 1) * b.B;
+    for (int r = tid; r < n * K; r += 1024) rows[r] = cur[r / K] * K + (r % K);
+    for (int idx = tid; idx < n * K * MNX_DEC_D; idx += 1024) {
+        const int rank = idx >> 8, d = idx & 255;
+        const int slot = cur[rank / K] * K + (rank % K);
+        const int tok = (t == 0) ? g.sos : b.cur_tok[slot];
+        b.xa[idx] = w.emb[tok * MNX_DEC_D + d] * 16.0f + w.pe[rank * MNX_DEC_D + d];
+    }
+}
+
 // =====================================================================================
 // skinny GEMM: out[rows<=32][N] = f(LN(x))[rows][K] * Wt[K][N]  (+ fused prologue / epilogue)
 // lane = output column, 8 warps split K, cross-warp reduction in shared memory.
@@ -276,6 +338,8 @@ struct AttnArgs {
     int nkeys_cross;      // S for cross attention; self uses step+1
     const float* wo_t;    // [256][256] final_linear, K-major
     float* part;          // [B][8][256]
+    int kv_div;           // cross attention under beam search: K/V row = row / kv_div (beams share their image's memory)
+    const int* anc;       // beam self-attention: [B][cap] ancestry rows of this step (nullptr otherwise)
 };
 
 #define ATTN_TK 160       // keys per staged tile (20 KB)
@@ -297,8 +361,9 @@ __global__ void __launch_bounds__(128) attn_kernel(AttnArgs a) {
     const int row = a.alive[(t & 1) * a.B + rank];
     const int nkeys = SELF ? (t + 1) : a.nkeys_cross;
     const int ntiles = (nkeys + ATTN_TK - 1) / ATTN_TK;
-    const float* Kb = a.Kc + ((size_t)row * 8 + h) * a.cap * 32;
-    const float* Vb = a.Vc + ((size_t)row * 8 + h) * a.cap * 32;
+    const int kvrow = SELF ? row : row / a.kv_div;
+    const float* Kb = a.Kc + ((size_t)kvrow * 8 + h) * a.cap * 32;
+    const float* Vb = a.Vc + ((size_t)kvrow * 8 + h) * a.cap * 32;
 
     // this head's final_linear slice, two output columns per thread: issue early
     float w0[32], w1[32];
@@ -397,14 +462,101 @@ __global__ void __launch_bounds__(128) attn_kernel(AttnArgs a) {
 }
 
 // =====================================================================================
+// beam-search self-attention: the keys of a hypothesis live in the slots of its ancestors
+// (BeamBuffers::anc), so K/V rows are gathered instead of bulk-copied.  8 lanes x float4 cover
+// one 128-byte key row, i.e. each warp-wide load instruction fetches four whole rows; beams of
+// one image share most of their ancestry, so the gathered rows hit in L1/L2.
+// =====================================================================================
+#define ATTN_MAXSELF 512   // >= max_len
+__global__ void __launch_bounds__(128) attn_self_beam_kernel(AttnArgs a) {
+    __shared__ int slots[ATTN_MAXSELF];
+    __shared__ float scores[ATTN_MAXSELF];
+    __shared__ float ctx_red[4][32];
+    __shared__ float ctx[32];
+    __shared__ float red_s[4];
+    const int rank = blockIdx.x, h = blockIdx.y;
+    if (rank >= a.st->n_alive) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int t = a.st->step;
+    const int row = a.alive[(t & 1) * a.B + rank];
+    const int nkeys = t + 1;
+
+    float w0[32], w1[32];
+#pragma unroll
+    for (int d = 0; d < 32; ++d) {
+        w0[d] = a.wo_t[(size_t)(h * 32 + d) * MNX_DEC_D + tid];
+        w1[d] = a.wo_t[(size_t)(h * 32 + d) * MNX_DEC_D + tid + 128];
+    }
+    const int* anc_row = a.anc + ((size_t)(t & 1) * a.B + row) * a.cap;   // anc[t & 1][row][:]
+    for (int j = tid; j < nkeys; j += 128) slots[j] = anc_row[j];
+    const int sub = lane & 7, grp = lane >> 3;
+    const float4 qv = reinterpret_cast<const float4*>(a.q + (size_t)rank * MNX_DEC_D + h * 32)[sub];
+    __syncthreads();
+    // scores
+    for (int j0 = wid * 4; j0 < nkeys; j0 += 16) {
+        const int j = j0 + grp;
+        float sdot = 0.f;
+        if (j < nkeys) {
+            const float4 kv = reinterpret_cast<const float4*>(a.Kc + (((size_t)slots[j] * 8 + h) * a.cap + j) * 32)[sub];
+            sdot = fmaf(qv.x, kv.x, sdot); sdot = fmaf(qv.y, kv.y, sdot);
+            sdot = fmaf(qv.z, kv.z, sdot); sdot = fmaf(qv.w, kv.w, sdot);
+        }
+        sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+        sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+        sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
+        if (sub == 0 && j < nkeys) scores[j] = sdot;
+    }
+    __syncthreads();
+    float m = -INFINITY;
+    for (int j = tid; j < nkeys; j += 128) m = fmaxf(m, scores[j]);
+    m = warp_max(m);
+    if (lane == 0) red_s[wid] = m;
+    __syncthreads();
+    m = fmaxf(fmaxf(red_s[0], red_s[1]), fmaxf(red_s[2], red_s[3]));
+    __syncthreads();
+    float sum = 0.f;
+    for (int j = tid; j < nkeys; j += 128) {
+        const float e = expf(scores[j] - m);
+        scores[j] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red_s[wid] = sum;
+    __syncthreads();
+    sum = (red_s[0] + red_s[1]) + (red_s[2] + red_s[3]);
+    for (int j = tid; j < nkeys; j += 128) scores[j] = scores[j] / sum;
+    __syncthreads();
+    // P.V : lane = feature, the 4 warps split the keys
+    float acc = 0.f;
+    for (int j = wid; j < nkeys; j += 4)
+        acc = fmaf(scores[j], a.Vc[(((size_t)slots[j] * 8 + h) * a.cap + j) * 32 + lane], acc);
+    ctx_red[wid][lane] = acc;
+    __syncthreads();
+    if (tid < 32) ctx[tid] = (ctx_red[0][tid] + ctx_red[1][tid]) + (ctx_red[2][tid] + ctx_red[3][tid]);
+    __syncthreads();
+    float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) {
+        const float c = ctx[d];
+        o0 = fmaf(c, w0[d], o0);
+        o1 = fmaf(c, w1[d], o1);
+    }
+    float* pr = a.part + ((size_t)rank * 8 + h) * MNX_DEC_D;
+    pr[tid] = o0;
+    pr[tid + 128] = o1;
+}
+
+// =====================================================================================
 // final LayerNorm -> vocab projection -> log_softmax -> grammar mask -> argmax -> bookkeeping
 // (components.py:293-306, greedy_search.py:76-98, decode_strategy.py:51-57)
 // =====================================================================================
 #define VPAD 256
 
 // x_in = x2 of the last layer; the W2 product arrives as 8 k-slice partials (+ bias b2)
+// BEAM: stop after the masked log-probs and hand them (by rank) to beam_topk_kernel
+template <bool BEAM>
 __global__ void __launch_bounds__(1024) pick_kernel(DecBuffers b, DecWeights w, Grammar g, const float* x_in,
-                                                    const float* part, const float* b2) {
+                                                    const float* part, const float* b2, float* lp_out) {
     __shared__ float hs[MNX_DEC_D];
     __shared__ float redf[8];
     __shared__ int redi[8];
@@ -492,6 +644,10 @@ __global__ void __launch_bounds__(1024) pick_kernel(DecBuffers b, DecWeights w, 
     if (in_y && tid >= g.offset) lp = -10000.0f;
     if (t == 0 && tid == g.eos) lp = -1e20f;          // ensure_min_length (min_length = 1)
     if (tid >= g.vocab) lp = -INFINITY;
+    if (BEAM) {
+        lp_out[(size_t)rank * VPAD + tid] = lp;
+        return;
+    }
     // argmax, lowest index wins ties (torch.topk(1))
     float bv = lp;
     int bi = tid;
@@ -517,6 +673,183 @@ __global__ void __launch_bounds__(1024) pick_kernel(DecBuffers b, DecWeights w, 
         const int fin = (ix == g.eos) || (t == g.max_len - 1);
         b.finished[row] = fin;
         if (fin) b.lens[row] = t + 1;
+    }
+}
+
+// =====================================================================================
+// BeamSearch.advance + update_finished for one alive image per CTA (beam_search.py:84-190 as
+// repaired in oracle/restate.py beam_decode): cumulative + token log-prob, length-normalised
+// score, top-`beam` over beam*V with ties to the lowest flat index, back-pointers applied to
+// the ancestry / id / log-prob histories, finished hypotheses filed, end condition.
+// =====================================================================================
+__global__ void __launch_bounds__(256) beam_topk_kernel(DecBuffers b, Grammar g, BeamBuffers bm) {
+    __shared__ float s_val[8];
+    __shared__ int s_idx[8];
+    __shared__ int sel_flat[MNX_MAX_BEAM];
+    __shared__ float sel_score[MNX_MAX_BEAM];
+    __shared__ int sel_store[MNX_MAX_BEAM];
+    const int r = blockIdx.x;
+    if (r >= b.st->n_img) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int t = b.st->step, K = bm.beam, V = g.vocab, T = b.T, R = b.B;
+    const int cur = t & 1, nxt = cur ^ 1;
+    const int img = bm.alive_img[cur * bm.n_img0 + r];
+    const float len = (float)(t + 2);             // curr_length = len(self) + 1, beam_search.py:99
+    const int BIG = 0x7fffffff;
+
+    float sc[MNX_MAX_BEAM];
+#pragma unroll
+    for (int k = 0; k < MNX_MAX_BEAM; ++k) {
+        sc[k] = -INFINITY;
+        if (k < K && tid < V) {
+            const float total = __fadd_rn(bm.lp[(size_t)(r * K + k) * VPAD + tid], bm.cum[cur * R + img * K + k]);
+            sc[k] = __fdiv_rn(total, len);
+        }
+    }
+    unsigned taken = 0;
+    for (int j = 0; j < K; ++j) {
+        float bv = -INFINITY;
+        int bi = BIG;
+        if (tid < V) {
+#pragma unroll
+            for (int k = 0; k < MNX_MAX_BEAM; ++k) {
+                if (k < K && !((taken >> k) & 1u)) {
+                    const int fi = k * V + tid;
+                    if (sc[k] > bv || (sc[k] == bv && fi < bi)) { bv = sc[k]; bi = fi; }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { s_val[wid] = bv; s_idx[wid] = bi; }
+        __syncthreads();
+        bv = s_val[0]; bi = s_idx[0];
+#pragma unroll
+        for (int i = 1; i < 8; ++i)
+            if (s_val[i] > bv || (s_val[i] == bv && s_idx[i] < bi)) { bv = s_val[i]; bi = s_idx[i]; }
+        if (tid == 0) {
+            sel_flat[j] = bi; sel_score[j] = bv;
+            bm.trace[((size_t)t * bm.n_img0 + img) * MNX_MAX_BEAM + j] = bi;
+        }
+        if (bi % V == tid) taken |= 1u << (bi / V);
+        __syncthreads();
+    }
+
+    if (tid == 0) {
+        int count = bm.hyp_count[img];
+        int topf = bm.top_fin[img];
+        const int NB = bm.n_best;
+        int* order = bm.hyp_order + img * MNX_MAX_BEAM;
+        float* hscore = bm.hyp_score + img * MNX_MAX_BEAM;
+        for (int j = 0; j < K; ++j) {
+            const int wtok = sel_flat[j] % V;
+            const float score = sel_score[j];
+            const int fin = (wtok == g.eos) || (t == g.max_len - 1);
+            int store = -1;
+            if (fin) {
+                const int kept = count < NB ? count : NB;
+                int pos = 0;
+                while (pos < kept && hscore[order[pos]] >= score) ++pos;   // stable: first stored wins ties
+                if (pos < NB) {
+                    store = (kept < NB) ? kept : order[NB - 1];
+                    for (int q = (kept < NB ? kept : NB - 1); q > pos; --q) order[q] = order[q - 1];
+                    order[pos] = store;
+                    hscore[store] = score;
+                    bm.hyp_len[img * MNX_MAX_BEAM + store] = t + 1;
+                }
+                ++count;
+                if (j == 0) topf = 1;
+            }
+            sel_store[j] = store;
+            const int slot = img * K + j;
+            bm.cum[nxt * R + slot] = fin ? -1e10f : __fmul_rn(score, len);   // beam_search.py:105,136
+            b.cur_tok[slot] = wtok;
+        }
+        bm.hyp_count[img] = count;
+        bm.top_fin[img] = topf;
+        if (topf && count >= NB) bm.img_done[img] = 1;
+    }
+    __syncthreads();
+
+    // histories follow their back-pointers (alive_seq.index_select(0, select_indices), :117-119)
+    for (int j = 0; j < K; ++j) {
+        const int pk = sel_flat[j] / V, wtok = sel_flat[j] % V;
+        const size_t src = ((size_t)cur * R + img * K + pk) * T;
+        const size_t dst = ((size_t)nxt * R + img * K + j) * T;
+        const int store = sel_store[j];
+        const size_t hdst = ((size_t)img * MNX_MAX_BEAM + (store < 0 ? 0 : store)) * T;
+        const float tok_lp = bm.lp[(size_t)(r * K + pk) * VPAD + wtok];
+        for (int i = tid; i <= t; i += 256) {
+            const int id = (i < t) ? bm.hist_ids[src + i] : wtok;
+            const float l = (i < t) ? bm.hist_logp[src + i] : tok_lp;
+            const int an = bm.anc[src + i];
+            bm.hist_ids[dst + i] = id;
+            bm.hist_logp[dst + i] = l;
+            bm.anc[dst + i] = an;
+            if (store >= 0) {
+                bm.hyp_ids[hdst + i] = id;
+                bm.hyp_logp[hdst + i] = l;
+                bm.hyp_anc[hdst + i] = an;
+            }
+        }
+        if (tid == 0 && t + 1 < T) bm.anc[dst + t + 1] = img * K + j;   // next step's own K/V position
+    }
+}
+
+// cum = [0, -inf, ...] per image (beam_search.py:45-47); every slot is its own ancestor at position 0
+__global__ void beam_init_kernel(DecBuffers b, BeamBuffers bm) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= b.B) return;
+    bm.cum[slot] = (slot % bm.beam == 0) ? 0.f : -INFINITY;
+    bm.anc[(size_t)slot * b.T] = slot;
+    if (slot < bm.n_img0) {
+        bm.img_done[slot] = 0; bm.top_fin[slot] = 0; bm.hyp_count[slot] = 0;
+    }
+}
+
+// results: n_best hypotheses per image, best first; the best one is also laid out like a greedy
+// result (ids/lens/logp per image + its hidden states gathered along the ancestry) so that the
+// atom scan and the bond head run on it unchanged (Decoder.decode uses pred[0], components.py:455).
+struct BeamOut {
+    int* ids;        // [n_img][n_best][T]
+    int* lens;       // [n_img][n_best]
+    float* scores;   // [n_img][n_best]
+    float* logp;     // [n_img][n_best][T]
+    int* best_ids;   // [n_img][T]
+    int* best_lens;  // [n_img]
+    float* best_logp;    // [n_img][T]
+    float* best_hidden;  // [n_img][T][256]
+};
+__global__ void __launch_bounds__(256) beam_finalize_kernel(DecBuffers b, BeamBuffers bm, BeamOut o) {
+    const int img = blockIdx.x, tid = threadIdx.x, T = b.T, NB = bm.n_best;
+    const int have = min(bm.hyp_count[img], NB);
+    for (int n = 0; n < NB; ++n) {
+        const int store = (n < have) ? bm.hyp_order[img * MNX_MAX_BEAM + n] : -1;
+        const int L = (store >= 0) ? bm.hyp_len[img * MNX_MAX_BEAM + store] : 0;
+        const size_t src = ((size_t)img * MNX_MAX_BEAM + (store < 0 ? 0 : store)) * T;
+        const size_t dst = ((size_t)img * NB + n) * T;
+        for (int i = tid; i < T; i += 256) {
+            const int id = (i < L) ? bm.hyp_ids[src + i] : 0;
+            const float l = (i < L) ? bm.hyp_logp[src + i] : 0.f;
+            if (o.ids) o.ids[dst + i] = id;
+            if (o.logp) o.logp[dst + i] = l;
+            if (n == 0) { o.best_ids[(size_t)img * T + i] = id; o.best_logp[(size_t)img * T + i] = l; }
+        }
+        if (tid == 0) {
+            if (o.lens) o.lens[img * NB + n] = L;
+            if (o.scores) o.scores[img * NB + n] = (store >= 0) ? bm.hyp_score[img * MNX_MAX_BEAM + store] : -INFINITY;
+            if (n == 0) o.best_lens[img] = L;
+        }
+        if (n == 0) {
+            for (int i = 0; i < L; ++i) {
+                const int slot = bm.hyp_anc[src + i];
+                o.best_hidden[((size_t)img * T + i) * MNX_DEC_D + tid] = b.hidden[((size_t)slot * T + i) * MNX_DEC_D + tid];
+            }
+        }
     }
 }
 
@@ -755,14 +1088,17 @@ cudaError_t dec_configure() {
 }
 
 // one decode step = 38 launches; returns the number of launches issued
-int dec_launch_step(const DecBuffers& b, const DecWeights& w, const Grammar& g, cudaStream_t s, cudaError_t* err) {
+// bm != nullptr: beam search (rows = image-major slots; 39 launches)
+int dec_launch_step(const DecBuffers& b, const DecWeights& w, const Grammar& g, const BeamBuffers* bm, cudaStream_t s,
+                    cudaError_t* err) {
     int n = 0;
     cudaError_t e = cudaSuccess;
 #define CK(x) do { e = (x); if (e != cudaSuccess) { *err = e; return n; } } while (0)
-    embed_compact_kernel<<<1, 1024, 0, s>>>(b, w, g);
+    if (bm) embed_compact_beam_kernel<<<1, 1024, 0, s>>>(b, w, g, *bm);
+    else embed_compact_kernel<<<1, 1024, 0, s>>>(b, w, g);
     CK(cudaGetLastError()); ++n;
     const size_t kv_layer = (size_t)b.B * 8 * b.T * 32;
-    const size_t ckv_layer = (size_t)b.B * 8 * b.S * 32;
+    const size_t ckv_layer = (size_t)(bm ? bm->n_img0 : b.B) * 8 * b.S * 32;
     // Residual-stream bookkeeping: every linear layer that ends a sub-block (final_linear of both
     // attentions, W2 of the FFN) leaves 8 partial sums in b.part; the NEXT kernel's prologue adds
     // them, the bias and the residual, and column-block 0 of that kernel stores the new stream.
@@ -786,8 +1122,14 @@ int dec_launch_step(const DecBuffers& b, const DecWeights& w, const Grammar& g, 
         AttnArgs at{};
         at.st = b.st; at.alive = b.alive; at.B = b.B; at.q = b.q;
         at.Kc = b.selfK + l * kv_layer; at.Vc = b.selfV + l * kv_layer; at.cap = b.T; at.nkeys_cross = 0;
-        at.wo_t = L.wo_s_t; at.part = b.part2;
-        attn_kernel<true><<<dim3(b.B, 8), 128, 0, s>>>(at);
+        at.wo_t = L.wo_s_t; at.part = b.part2; at.kv_div = 1;
+        if (bm) {
+            // ancestry rows of step t live in anc[t & 1]; both parities are passed and the kernel picks
+            at.anc = bm->anc;
+            attn_self_beam_kernel<<<dim3(b.B, 8), 128, 0, s>>>(at);
+        } else {
+            attn_kernel<true><<<dim3(b.B, 8), 128, 0, s>>>(at);
+        }
         CK(cudaGetLastError()); ++n;
         // (D) x1 = x + bo + sum(part); LN2 -> context query
         a = SkinnyArgs{};
@@ -797,7 +1139,7 @@ int dec_launch_step(const DecBuffers& b, const DecWeights& w, const Grammar& g, 
         CK((launch_skinny<256, PRO_SUM_LN, EPI_Q>(a, b.B, s))); ++n;
         // (E) cross attention over the S memory positions + partials
         at.Kc = b.crossK + l * ckv_layer; at.Vc = b.crossV + l * ckv_layer; at.cap = b.S; at.nkeys_cross = b.S;
-        at.wo_t = L.wo_c_t; at.part = b.part;
+        at.wo_t = L.wo_c_t; at.part = b.part; at.kv_div = bm ? bm->beam : 1; at.anc = nullptr;
         attn_kernel<false><<<dim3(b.B, 8), 128, 0, s>>>(at);
         CK(cudaGetLastError()); ++n;
         // (G) x2 = x1 + bo + sum(part); LN_ff -> W1 -> GELU
@@ -813,8 +1155,15 @@ int dec_launch_step(const DecBuffers& b, const DecWeights& w, const Grammar& g, 
         CK((launch_skinny<128, PRO_PLAIN, EPI_PART>(a, b.B, s))); ++n;
         // x_cur holds x2; the W2 partials are in b.part
     }
-    pick_kernel<<<b.B, 1024, 0, s>>>(b, w, g, x_cur, b.part, w.layer[MNX_DEC_L - 1].b2);
-    CK(cudaGetLastError()); ++n;
+    if (bm) {
+        pick_kernel<true><<<b.B, 1024, 0, s>>>(b, w, g, x_cur, b.part, w.layer[MNX_DEC_L - 1].b2, bm->lp);
+        CK(cudaGetLastError()); ++n;
+        beam_topk_kernel<<<bm->n_img0, 256, 0, s>>>(b, g, *bm);
+        CK(cudaGetLastError()); ++n;
+    } else {
+        pick_kernel<false><<<b.B, 1024, 0, s>>>(b, w, g, x_cur, b.part, w.layer[MNX_DEC_L - 1].b2, nullptr);
+        CK(cudaGetLastError()); ++n;
+    }
 #undef CK
     *err = cudaSuccess;
     return n;
@@ -866,6 +1215,18 @@ cudaError_t dec_edges(const float* hidden, const int* atom_idx, const int* n_ato
     return cudaGetLastError();
 }
 
+cudaError_t dec_beam_init(const DecBuffers& b, const BeamBuffers& bm, cudaStream_t s) {
+    beam_init_kernel<<<(b.B + 255) / 256, 256, 0, s>>>(b, bm);
+    return cudaGetLastError();
+}
+
+cudaError_t dec_beam_finalize(const DecBuffers& b, const BeamBuffers& bm, int* ids, int* lens, float* scores, float* logp,
+                              int* best_ids, int* best_lens, float* best_logp, float* best_hidden, cudaStream_t s) {
+    BeamOut o{ids, lens, scores, logp, best_ids, best_lens, best_logp, best_hidden};
+    beam_finalize_kernel<<<bm.n_img0, 256, 0, s>>>(b, bm, o);
+    return cudaGetLastError();
+}
+
 // -------------------------------------------------------------------------------------
 // isolated timing of one decode kernel on the shapes of the last call (roofline evidence):
 // which = 1 cross-attention, 2 self-attention at t=step, 3 ln1+qkv, 4 sum+lnff+W1, 5 W2+res, 6 pick
@@ -894,7 +1255,7 @@ cudaError_t dec_time_kernel(int which, int iters, const DecBuffers& b, const Dec
         SkinnyArgs a{};
         a.st = b.st; a.alive = b.alive; a.B = b.B;
         AttnArgs at{};
-        at.st = b.st; at.alive = b.alive; at.B = b.B; at.q = b.q; at.part = b.part;
+        at.st = b.st; at.alive = b.alive; at.B = b.B; at.q = b.q; at.part = b.part; at.kv_div = 1;
         switch (which) {
             case 1:
                 at.Kc = b.crossK; at.Vc = b.crossV; at.cap = b.S; at.nkeys_cross = b.S; at.wo_t = L.wo_c_t;
@@ -916,7 +1277,7 @@ cudaError_t dec_time_kernel(int which, int iters, const DecBuffers& b, const Dec
                 a.x_in = b.hbuf; a.x_stride = MNX_DEC_FF; a.wt = L.w2_t; a.N = 256; a.out = b.part;
                 return launch_skinny<128, PRO_PLAIN, EPI_PART>(a, b.B, s);
             default:
-                pick_kernel<<<b.B, 1024, 0, s>>>(b, w, g, b.xa, b.part, L.b2);
+                pick_kernel<false><<<b.B, 1024, 0, s>>>(b, w, g, b.xa, b.part, L.b2, nullptr);
                 return cudaGetLastError();
         }
     };

@@ -35,6 +35,7 @@ struct DecState {
     int next_step;   // t of the next step (advanced by the embed kernel)
     int done;        // 1 once every row has finished
     int steps_run;   // number of steps that had at least one alive row
+    int n_img;       // beam search: images alive in the step being executed (n_alive = n_img * beam)
 };
 
 struct DecBuffers {
@@ -59,6 +60,33 @@ struct DecBuffers {
     int* lens;         // [B]
     float* logp;       // [B][T]
     float* hidden;     // [B][T][256]
+};
+
+// Beam-search state (decoding/beam_search.py, repaired as described in oracle/restate.py
+// beam_decode).  A *slot* is a physical decoder row: slot = image * beam + k.  Hypotheses move
+// between slots every step; instead of permuting the self-attention K/V cache (what
+// `map_state(index_select)` does in OpenNMT) every slot keeps an ancestry row anc[slot][t'] =
+// the slot whose K/V (and hidden state) at position t' belongs to this hypothesis.
+#define MNX_MAX_BEAM 8
+struct BeamBuffers {
+    int beam, n_best, n_img0;   // beam width, hypotheses returned per image, images of this call
+    int* alive_img;     // [2][n_img0]  ordered list of alive images, ping-pong on step parity
+    int* img_done;      // [n_img0]
+    int* top_fin;       // [n_img0]     top_beam_finished
+    float* lp;          // [R][256]     masked log-probs of the current step, by rank
+    float* cum;         // [2][R]       topk_log_probs, by slot, ping-pong
+    int* anc;           // [2][R][T]    ancestry rows, ping-pong
+    int* hist_ids;      // [2][R][T]    alive_seq without <sos>, ping-pong
+    float* hist_logp;   // [2][R][T]    masked log-prob of each chosen token, ping-pong
+    // finished hypotheses kept per image: the best n_best so far, stable in insertion order
+    int* hyp_count;     // [n_img0]     hypotheses stored so far (all of them, not only the kept ones)
+    int* hyp_order;     // [n_img0][MNX_MAX_BEAM]  rank -> storage index
+    float* hyp_score;   // [n_img0][MNX_MAX_BEAM]  by storage index
+    int* hyp_len;       // [n_img0][MNX_MAX_BEAM]
+    int* hyp_ids;       // [n_img0][MNX_MAX_BEAM][T]
+    float* hyp_logp;    // [n_img0][MNX_MAX_BEAM][T]
+    int* hyp_anc;       // [n_img0][MNX_MAX_BEAM][T]
+    int* trace;         // [T][n_img0][MNX_MAX_BEAM] flat index (beam * V + token) selected per step, -1 = not run
 };
 
 struct Grammar {

@@ -21,7 +21,11 @@
 namespace mnx {
 // decoder.cu
 cudaError_t dec_configure();
-int dec_launch_step(const DecBuffers& b, const DecWeights& w, const Grammar& g, cudaStream_t s, cudaError_t* err);
+int dec_launch_step(const DecBuffers& b, const DecWeights& w, const Grammar& g, const BeamBuffers* bm, cudaStream_t s,
+                    cudaError_t* err);
+cudaError_t dec_beam_init(const DecBuffers& b, const BeamBuffers& bm, cudaStream_t s);
+cudaError_t dec_beam_finalize(const DecBuffers& b, const BeamBuffers& bm, int* ids, int* lens, float* scores, float* logp,
+                              int* best_ids, int* best_lens, float* best_logp, float* best_hidden, cudaStream_t s);
 cudaError_t dec_precompute(const DecBuffers& b, const DecWeights& w, const float* features, int enc_dim,
                            cudaStream_t s, int* launches);
 cudaError_t dec_atom_scan(const int* ids, const int* lens, int B, int T, const uint8_t* cls, const Grammar& g,
@@ -85,6 +89,13 @@ struct mnx_engine {
     // graph of STEPS_PER_GRAPH decode steps for one (B, S)
     cudaGraphExec_t graph = nullptr;
     int graph_B = -1, graph_S = -1, graph_nodes = 0;
+    // beam search (graph path only): second graph keyed on (images, S, beam)
+    BeamBuffers bm{};
+    float* hid_best = nullptr;           // [max_batch][T][256] hidden states of each image's best hypothesis
+    const float* edge_hidden = nullptr;  // what mnx_edges reads when the caller passes hidden == NULL
+    cudaGraphExec_t graph_beam = nullptr;
+    int gb_B = -1, gb_S = -1, gb_K = -1, gb_NB = -1, gb_nodes = 0;
+    int last_beam_B = 0;
     cudaStream_t cap_stream = nullptr;   // capture-only stream (the legacy default stream cannot be captured)
     int* h_done = nullptr;   // pinned
     int64_t launches = 0;
@@ -159,6 +170,11 @@ extern "C" int mnx_create(const mnx_config* cfg, mnx_engine** out) {
     if (cfg->max_atoms < 1 || cfg->max_atoms * 3 > cfg->max_len)
         return fail(nullptr, MNX_ERR_INVALID, "max_atoms must be in [1, max_len/3]");
     if (cfg->encoder_dim % 16 != 0) return fail(nullptr, MNX_ERR_INVALID, "encoder_dim must be a multiple of 16");
+    if (cfg->max_beam < 0 || cfg->max_beam > MNX_MAX_BEAM)
+        return fail(nullptr, MNX_ERR_INVALID, "max_beam must be in [0,%d]", MNX_MAX_BEAM);
+    if ((int64_t)cfg->max_batch * (cfg->max_beam > 1 ? cfg->max_beam : 1) > 5000)
+        return fail(nullptr, MNX_ERR_INVALID, "max_batch * max_beam must be <= 5000 (positional-encoding table has 5000 rows)");
+    if (cfg->max_beam > 1 && cfg->max_len > 512) return fail(nullptr, MNX_ERR_INVALID, "beam search supports max_len <= 512");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(nullptr, MNX_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
@@ -204,6 +220,7 @@ extern "C" int mnx_destroy(mnx_engine* e) {
     cudaSetDevice(e->cfg.device);
     cudaDeviceSynchronize();
     if (e->graph) cudaGraphExecDestroy(e->graph);
+    if (e->graph_beam) cudaGraphExecDestroy(e->graph_beam);
     encoder_destroy(e->enc);
     for (void* p : e->allocs) cudaFree(p);
     if (e->h_done) cudaFreeHost(e->h_done);
@@ -424,26 +441,49 @@ static int finalize_decoder(mnx_engine* e) {
 }
 
 static int alloc_workspaces(mnx_engine* e) {
+    // B = images per call; R = decoder rows per call (images x beams under beam search)
     const size_t B = e->cfg.max_batch, T = e->cfg.max_len, S = e->S_max, KA = e->cfg.max_atoms;
+    const size_t R = B * (e->cfg.max_beam > 1 ? e->cfg.max_beam : 1);
     CUDA_TRY(e, dev_alloc(e, &e->st, 1));
-    CUDA_TRY(e, dev_alloc(e, &e->alive, 2 * B));
-    CUDA_TRY(e, dev_alloc(e, &e->cur_tok, B));
-    CUDA_TRY(e, dev_alloc(e, &e->finished, B));
-    CUDA_TRY(e, dev_alloc(e, &e->xa, B * 256));
-    CUDA_TRY(e, dev_alloc(e, &e->xb, B * 256));
-    CUDA_TRY(e, dev_alloc(e, &e->q, B * 256));
-    CUDA_TRY(e, dev_alloc(e, &e->part, B * 8 * 256));
-    CUDA_TRY(e, dev_alloc(e, &e->part2, B * 8 * 256));
-    CUDA_TRY(e, dev_alloc(e, &e->hbuf, B * 1024));
-    CUDA_TRY(e, dev_alloc(e, &e->selfK, MNX_DEC_L * B * T * 256));
-    CUDA_TRY(e, dev_alloc(e, &e->selfV, MNX_DEC_L * B * T * 256));
+    CUDA_TRY(e, dev_alloc(e, &e->alive, 2 * R));
+    CUDA_TRY(e, dev_alloc(e, &e->cur_tok, R));
+    CUDA_TRY(e, dev_alloc(e, &e->finished, R));
+    CUDA_TRY(e, dev_alloc(e, &e->xa, R * 256));
+    CUDA_TRY(e, dev_alloc(e, &e->xb, R * 256));
+    CUDA_TRY(e, dev_alloc(e, &e->q, R * 256));
+    CUDA_TRY(e, dev_alloc(e, &e->part, R * 8 * 256));
+    CUDA_TRY(e, dev_alloc(e, &e->part2, R * 8 * 256));
+    CUDA_TRY(e, dev_alloc(e, &e->hbuf, R * 1024));
+    CUDA_TRY(e, dev_alloc(e, &e->selfK, MNX_DEC_L * R * T * 256));
+    CUDA_TRY(e, dev_alloc(e, &e->selfV, MNX_DEC_L * R * T * 256));
     CUDA_TRY(e, dev_alloc(e, &e->crossK, MNX_DEC_L * B * S * 256));
     CUDA_TRY(e, dev_alloc(e, &e->crossV, MNX_DEC_L * B * S * 256));
     CUDA_TRY(e, dev_alloc(e, &e->membank, B * S * 256));
     CUDA_TRY(e, dev_alloc(e, &e->ids, B * T));
     CUDA_TRY(e, dev_alloc(e, &e->lens, B));
     CUDA_TRY(e, dev_alloc(e, &e->logp, B * T));
-    CUDA_TRY(e, dev_alloc(e, &e->hidden, B * T * 256));
+    CUDA_TRY(e, dev_alloc(e, &e->hidden, R * T * 256));
+    e->edge_hidden = e->hidden;
+    if (e->cfg.max_beam > 1) {
+        BeamBuffers& m = e->bm;
+        CUDA_TRY(e, dev_alloc(e, &m.alive_img, 2 * B));
+        CUDA_TRY(e, dev_alloc(e, &m.img_done, B));
+        CUDA_TRY(e, dev_alloc(e, &m.top_fin, B));
+        CUDA_TRY(e, dev_alloc(e, &m.lp, R * 256));
+        CUDA_TRY(e, dev_alloc(e, &m.cum, 2 * R));
+        CUDA_TRY(e, dev_alloc(e, &m.anc, 2 * R * T));
+        CUDA_TRY(e, dev_alloc(e, &m.hist_ids, 2 * R * T));
+        CUDA_TRY(e, dev_alloc(e, &m.hist_logp, 2 * R * T));
+        CUDA_TRY(e, dev_alloc(e, &m.hyp_count, B));
+        CUDA_TRY(e, dev_alloc(e, &m.hyp_order, B * MNX_MAX_BEAM));
+        CUDA_TRY(e, dev_alloc(e, &m.hyp_score, B * MNX_MAX_BEAM));
+        CUDA_TRY(e, dev_alloc(e, &m.hyp_len, B * MNX_MAX_BEAM));
+        CUDA_TRY(e, dev_alloc(e, &m.hyp_ids, B * MNX_MAX_BEAM * T));
+        CUDA_TRY(e, dev_alloc(e, &m.hyp_logp, B * MNX_MAX_BEAM * T));
+        CUDA_TRY(e, dev_alloc(e, &m.hyp_anc, B * MNX_MAX_BEAM * T));
+        CUDA_TRY(e, dev_alloc(e, &m.trace, T * B * MNX_MAX_BEAM));
+        CUDA_TRY(e, dev_alloc(e, &e->hid_best, B * T * 256));
+    }
     CUDA_TRY(e, dev_alloc(e, &e->row_state, B));
     CUDA_TRY(e, dev_alloc(e, &e->steps_run_dev, 1));
     CUDA_TRY(e, dev_alloc(e, &e->prof_dev, 64));
@@ -501,7 +541,7 @@ static int ensure_graph(mnx_engine* e, const DecBuffers& b) {
     CUDA_TRY(e, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
     int nodes = 0;
     cudaError_t kerr = cudaSuccess;
-    for (int i = 0; i < STEPS_PER_GRAPH && kerr == cudaSuccess; ++i) nodes += dec_launch_step(b, e->dw, e->g, s, &kerr);
+    for (int i = 0; i < STEPS_PER_GRAPH && kerr == cudaSuccess; ++i) nodes += dec_launch_step(b, e->dw, e->g, nullptr, s, &kerr);
     cudaError_t cerr = cudaStreamEndCapture(s, &graph);
     if (kerr != cudaSuccess) {
         if (graph) cudaGraphDestroy(graph);
@@ -522,6 +562,7 @@ static int decode_internal(mnx_engine* e, const float* features, int B, int S, c
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
     DecBuffers b = make_buffers(e, B, S);
     const int T = e->cfg.max_len;
+    e->edge_hidden = e->hidden;
     CUDA_TRY(e, cudaMemsetAsync(e->st, 0, sizeof(DecState), s));
     CUDA_TRY(e, cudaMemsetAsync(e->finished, 0, sizeof(int) * B, s));
     CUDA_TRY(e, cudaMemsetAsync(e->lens, 0, sizeof(int) * B, s));
@@ -596,9 +637,81 @@ extern "C" int mnx_decode_greedy(mnx_engine* e, const float* features, int32_t B
     return MNX_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// beam search: multi-kernel graph path with rows = images x beams
+// ---------------------------------------------------------------------------------------
+static int ensure_graph_beam(mnx_engine* e, const DecBuffers& b, const BeamBuffers& bm) {
+    if (e->graph_beam && e->gb_B == bm.n_img0 && e->gb_S == b.S && e->gb_K == bm.beam && e->gb_NB == bm.n_best) return MNX_OK;
+    cudaStream_t s = e->cap_stream;
+    if (e->graph_beam) { cudaGraphExecDestroy(e->graph_beam); e->graph_beam = nullptr; }
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(e, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    int nodes = 0;
+    cudaError_t kerr = cudaSuccess;
+    for (int i = 0; i < STEPS_PER_GRAPH && kerr == cudaSuccess; ++i) nodes += dec_launch_step(b, e->dw, e->g, &bm, s, &kerr);
+    cudaError_t cerr = cudaStreamEndCapture(s, &graph);
+    if (kerr != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        return fail(e, MNX_ERR_CUDA, "beam decode-step launch failed during capture: %s", cudaGetErrorString(kerr));
+    }
+    CUDA_TRY(e, cerr);
+    cudaError_t ierr = cudaGraphInstantiate(&e->graph_beam, graph, 0);
+    cudaGraphDestroy(graph);
+    CUDA_TRY(e, ierr);
+    e->gb_B = bm.n_img0; e->gb_S = b.S; e->gb_K = bm.beam; e->gb_NB = bm.n_best; e->gb_nodes = nodes;
+    return MNX_OK;
+}
+
+extern "C" int mnx_decode_beam(mnx_engine* e, const float* features, int32_t B, int32_t S, int32_t beam, int32_t n_best,
+                               int32_t* ids, int32_t* lens, float* scores, float* token_logp, float* hidden,
+                               void* cuda_stream) {
+    if (!e || !features) return fail(e, MNX_ERR_INVALID, "mnx_decode_beam: null argument");
+    if (!e->finalized) return fail(e, MNX_ERR_INVALID, "weights not finalized");
+    if (beam < 1 || beam > e->cfg.max_beam || e->cfg.max_beam < 2)
+        return fail(e, MNX_ERR_CAPACITY, "beam %d outside [1, max_beam=%d] (create the handle with max_beam >= 2)", beam, e->cfg.max_beam);
+    if (n_best < 1 || n_best > beam) return fail(e, MNX_ERR_INVALID, "n_best must be in [1, beam]");
+    if (B < 1 || B > e->cfg.max_batch) return fail(e, MNX_ERR_CAPACITY, "batch %d exceeds max_batch %d", B, e->cfg.max_batch);
+    if (S < 1 || S > e->S_max) return fail(e, MNX_ERR_CAPACITY, "memory length %d exceeds capacity %d", S, e->S_max);
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    const int T = e->cfg.max_len, R = B * beam;
+    DecBuffers bi = make_buffers(e, B, S);     // image-shaped view for the once-per-call projections
+    DecBuffers b = make_buffers(e, R, S);      // row-shaped view for the step kernels
+    BeamBuffers bm = e->bm;
+    bm.beam = beam; bm.n_best = n_best; bm.n_img0 = B;
+    CUDA_TRY(e, cudaMemsetAsync(e->st, 0, sizeof(DecState), s));
+    CUDA_TRY(e, dec_beam_init(b, bm, s));
+    CUDA_TRY(e, cudaMemsetAsync(bm.trace, 0xff, sizeof(int) * (size_t)T * B * MNX_MAX_BEAM, s));
+    e->last_beam_B = B;
+    int nl = 1;
+    CUDA_TRY(e, dec_precompute(bi, e->dw, features, e->cfg.encoder_dim, s, &nl));
+    e->launches += nl;
+    e->last_path = 4;
+    int rc = ensure_graph_beam(e, b, bm);
+    if (rc != MNX_OK) return rc;
+    for (int chunk = 0; chunk < T / STEPS_PER_GRAPH; ++chunk) {
+        CUDA_TRY(e, cudaGraphLaunch(e->graph_beam, s));
+        e->launches += e->gb_nodes;
+        CUDA_TRY(e, cudaMemcpyAsync(e->h_done, &e->st->done, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(e, cudaStreamSynchronize(s));
+        if (*e->h_done) break;
+    }
+    CUDA_TRY(e, dec_beam_finalize(b, bm, ids, lens, scores, token_logp, e->ids, e->lens, e->logp, e->hid_best, s));
+    e->launches += 1;
+    e->edge_hidden = e->hid_best;
+    if (hidden) CUDA_TRY(e, cudaMemcpyAsync(hidden, e->hid_best, sizeof(float) * (size_t)B * T * 256, cudaMemcpyDeviceToDevice, s));
+    DecState hs{};
+    CUDA_TRY(e, cudaMemcpyAsync(&hs, e->st, sizeof(DecState), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(e, cudaStreamSynchronize(s));
+    e->last_steps = hs.steps_run;
+    e->last_B = 0; e->last_S = S;   // isolated kernel timing (mnx_time_kernel) is defined on greedy shapes only
+    return MNX_OK;
+}
+
 extern "C" int mnx_atom_indices(mnx_engine* e, const int32_t* ids, const int32_t* lens, int32_t B, int32_t* atom_idx,
                                 int32_t* n_atoms, void* cuda_stream) {
-    if (!e || !ids || !lens || !atom_idx || !n_atoms) return fail(e, MNX_ERR_INVALID, "mnx_atom_indices: null argument");
+    if (!e || !atom_idx || !n_atoms || (!ids != !lens)) return fail(e, MNX_ERR_INVALID, "mnx_atom_indices: null argument");
+    if (!ids) { ids = e->ids; lens = e->lens; }
     if (!e->finalized) return fail(e, MNX_ERR_INVALID, "weights not finalized");
     if (B < 1 || B > e->cfg.max_batch) return fail(e, MNX_ERR_CAPACITY, "batch %d exceeds max_batch %d", B, e->cfg.max_batch);
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
@@ -615,7 +728,7 @@ extern "C" int mnx_edges(mnx_engine* e, const float* hidden, const int32_t* atom
     if (B < 1 || B > e->cfg.max_batch) return fail(e, MNX_ERR_CAPACITY, "batch %d exceeds max_batch %d", B, e->cfg.max_batch);
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
     int nl = 0;
-    CUDA_TRY(e, dec_edges(hidden ? hidden : e->hidden, atom_idx, n_atoms, B, e->cfg.max_len, e->cfg.max_atoms, e->dw,
+    CUDA_TRY(e, dec_edges(hidden ? hidden : e->edge_hidden, atom_idx, n_atoms, B, e->cfg.max_len, e->cfg.max_atoms, e->dw,
                           e->hg, e->AB, e->prob, edges, edge_score, (cudaStream_t)cuda_stream, &nl));
     e->launches += nl;
     return MNX_OK;
@@ -675,6 +788,15 @@ extern "C" int mnx_predict_host(mnx_engine* e, const float* images_host, int32_t
                          edges_host, s);
     if (rc != MNX_OK) return rc;
     CUDA_TRY(e, cudaStreamSynchronize(s));
+    return MNX_OK;
+}
+
+extern "C" int mnx_beam_trace(mnx_engine* e, int32_t* trace_host, int32_t B) {
+    if (!e || !trace_host) return fail(e, MNX_ERR_INVALID, "mnx_beam_trace: null argument");
+    if (e->cfg.max_beam < 2 || e->last_beam_B == 0 || B != e->last_beam_B)
+        return fail(e, MNX_ERR_INVALID, "mnx_beam_trace: B must equal the batch of the last mnx_decode_beam (%d)", e->last_beam_B);
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    CUDA_TRY(e, cudaMemcpy(trace_host, e->bm.trace, sizeof(int) * (size_t)e->cfg.max_len * B * MNX_MAX_BEAM, cudaMemcpyDeviceToHost));
     return MNX_OK;
 }
 

@@ -53,7 +53,8 @@ class Engine:
     decoder-only handle."""
 
     def __init__(self, checkpoint: dict, tokenizer: Optional[CharTokenizer] = None, device: int = 0,
-                 max_batch: int = 32, max_height: int = 384, max_width: int = 384, encoder_dim: int = 1024):
+                 max_batch: int = 32, max_height: int = 384, max_width: int = 384, encoder_dim: int = 1024,
+                 max_beam: int = 1):
         if not torch.cuda.is_available():
             raise EngineError("no CUDA device: molnextr_b200 has no CPU fallback")
         self.lib = _cabi.load()
@@ -61,6 +62,7 @@ class Engine:
         self.device = torch.device("cuda", device)
         self.max_batch, self.max_height, self.max_width = max_batch, max_height, max_width
         self.encoder_dim = encoder_dim
+        self.max_beam = max_beam
         enc_sd = checkpoint.get("encoder")
         self.encoder_kind = encoder_kind_of(enc_sd)
         offset, maxx, maxy = self.tok.grammar_rule()
@@ -69,7 +71,7 @@ class Engine:
         cfg = _cabi.MnxConfig(device=device, encoder_kind=self.encoder_kind, max_batch=max_batch,
                               max_height=max_height, max_width=max_width, max_len=MAX_LEN, vocab=len(self.tok),
                               tok_offset=offset, max_x=maxx, max_y=maxy, max_atoms=MAX_ATOMS,
-                              encoder_dim=encoder_dim,
+                              encoder_dim=encoder_dim, max_beam=max_beam,
                               token_class=cls.ctypes.data_as(C.POINTER(C.c_uint8)))
         h = C.c_void_p()
         rc = self.lib.mnx_create(C.byref(cfg), C.byref(h))
@@ -153,10 +155,39 @@ class Engine:
             out["hidden"] = hidden
         return out
 
-    def atom_indices(self, ids: torch.Tensor, lens: torch.Tensor):
-        B = ids.size(0)
-        atom_idx = torch.full((B, MAX_ATOMS), -1, device=ids.device, dtype=torch.int32)
-        n_atoms = torch.empty((B,), device=ids.device, dtype=torch.int32)
+    def decode_beam(self, features: torch.Tensor, beam_size: int, n_best: int = 1, return_hidden: bool = False):
+        """TransformerDecoderAR.decode with BeamSearch (components.py:253-334, decoding/beam_search.py),
+        with the repairs listed in oracle/restate.py beam_decode -- the reference branch itself
+        cannot run.  ids/logp are (B, n_best, 480), lens/scores (B, n_best), best
+        hypothesis first; `hidden` (B, 480, 256) belongs to the best hypothesis."""
+        assert features.is_cuda and features.dtype == torch.float32
+        features = features.contiguous().view(features.size(0), -1, features.size(-1))
+        B, S, _ = features.shape
+        dev = features.device
+        ids = torch.empty((B, n_best, MAX_LEN), device=dev, dtype=torch.int32)
+        lens = torch.empty((B, n_best), device=dev, dtype=torch.int32)
+        scores = torch.empty((B, n_best), device=dev, dtype=torch.float32)
+        logp = torch.empty((B, n_best, MAX_LEN), device=dev, dtype=torch.float32)
+        hidden = torch.empty((B, MAX_LEN, 256), device=dev, dtype=torch.float32) if return_hidden else None
+        self._check(self.lib.mnx_decode_beam(self.h, self._p(features), B, S, beam_size, n_best, self._p(ids),
+                                             self._p(lens), self._p(scores), self._p(logp), self._p(hidden),
+                                             self._stream()), "mnx_decode_beam")
+        out = {"ids": ids, "lens": lens, "scores": scores, "logp": logp}
+        if return_hidden:
+            out["hidden"] = hidden
+        return out
+
+    def beam_trace(self, batch: int) -> np.ndarray:
+        """(480, batch, 8) int32 selections of the last decode_beam (parity tests; see the header)."""
+        tr = np.empty((MAX_LEN, batch, 8), np.int32)
+        self._check(self.lib.mnx_beam_trace(self.h, C.c_void_p(tr.ctypes.data), batch), "mnx_beam_trace")
+        return tr
+
+    def atom_indices(self, ids: Optional[torch.Tensor] = None, lens: Optional[torch.Tensor] = None, batch: int = 0):
+        """ids/lens None: scan the engine-internal result of the last decode (`batch` rows)."""
+        B = ids.size(0) if ids is not None else batch
+        atom_idx = torch.full((B, MAX_ATOMS), -1, device=self.device, dtype=torch.int32)
+        n_atoms = torch.empty((B,), device=self.device, dtype=torch.int32)
         self._check(self.lib.mnx_atom_indices(self.h, self._p(ids), self._p(lens), B, self._p(atom_idx),
                                               self._p(n_atoms), self._stream()), "mnx_atom_indices")
         return atom_idx, n_atoms

@@ -377,6 +377,152 @@ def greedy_decode(dec_sd: SD, features: torch.Tensor, max_len: int = 480,
     return results
 
 
+def beam_decode(dec_sd: SD, features: torch.Tensor, beam_size: int, n_best: int = 1, max_len: int = 480,
+                grammar=(101, 64, 64), min_length: int = 1, min_gap: Optional[list] = None,
+                follow: Optional[np.ndarray] = None, follow_stats: Optional[dict] = None,
+                record: Optional[np.ndarray] = None):
+    """TransformerDecoderAR.decode with BeamSearch -- PARITY UNPINNED.
+
+    The reference's beam branch cannot run (constructor arguments are passed in
+    the wrong order so max_length becomes False, `advance` is called with four arguments but
+    takes two, caches are only reordered when a hypothesis finished, hidden states are not
+    tracked).  This function is the *intended* algorithm of decoding/beam_search.py:84-190 with
+    exactly those four defects repaired, following the OpenNMT-py translator the file was
+    adapted from:
+      * length-normalised score `(cum + log_prob) / (len(self) + 1)` (beam_search.py:96-101),
+        cumulative log-prob recovered as `score * curr_length` (:105);
+      * top-`beam` over the flattened (beam * V) scores (:80-82); ties are broken by the LOWEST
+        flat index (torch.topk leaves tie order unspecified; this restatement pins it with a
+        stable sort so the CUDA path has something definite to match);
+      * caches, memory bank, per-hypothesis hidden states and token log-probs are reordered by
+        `select_indices` EVERY step (the OpenNMT behaviour; the reference does it only
+        `if any_finished`, components.py:314-319, which would corrupt the KV cache);
+      * finished hypotheses get cumulative log-prob -1e10 (:136), are stored with their
+        length-normalised score (:149-153); an image ends when its top beam has finished and
+        it holds >= n_best hypotheses (:156-167), the best n_best by score (stable, first
+        stored wins ties) are returned;
+      * grammar mask keyed on each row's input token and `ensure_min_length` as in greedy
+        (components.py:298-301, decode_strategy.py:51-53);
+      * row r of the alive (image-major, beam-minor) batch receives pe[r].
+
+    Returns a list (one per image) of lists (n_best) of dicts: ids (L,) int64 incl. <eos>,
+    logp (L,) masked log-prob of each chosen token, hidden (L,256), score (float, the
+    length-normalised log score BeamSearch stores -- not exponentiated).
+    `min_gap` (a list, one float per image, filled in place) receives the smallest difference, in
+    cumulative-log-prob units, between adjacent entries of the top beam+1 candidates over all
+    steps: how close this image came to a different selection (near-tie diagnosis in tests).
+    `follow` (T, B, >=beam) int: flat indices (beam * V + token) another implementation selected
+    at each step for each ORIGINAL image.  The oracle then adopts those selections instead of its
+    own after measuring how far they are from a valid descending top-`beam` of ITS scores
+    (`follow_stats['max_violation']`, in cumulative-log-prob units; 0 when they are exactly a valid
+    top-k) and counting the steps where they differ from its own choice
+    (`follow_stats['deviations']`).  With near-ties as frequent as they are under beam search
+    (candidates a few 1e-5 apart, fp32 summation order decides) this is the sound way to check a
+    second implementation end to end: every selection must be optimal within tolerance on the
+    oracle's own arithmetic, and everything derived from the selections must then match.
+    `record` (T, B, beam) int array: receives the selections actually applied, same layout."""
+    sd = _strip(dec_sd)
+    B, K = features.size(0), beam_size
+    V = sum(grammar)
+    mem = torch.repeat_interleave(memory_bank(sd, features), K, dim=0)       # beam_search.py:35
+    state = DecoderState()
+    w_out, b_out = sd[_P + "output_layer.weight"], sd[_P + "output_layer.bias"]
+    alive_seq = torch.full((B * K, 1), SOS_ID, dtype=torch.long)
+    alive_logp = torch.zeros((B * K, 0))
+    alive_hidden = torch.zeros((B * K, 0, DEC_DIM))
+    topk_log_probs = torch.tensor([0.0] + [float("-inf")] * (K - 1)).repeat(B)   # beam_search.py:45-47
+    batch_offset = torch.arange(B)
+    top_beam_finished = torch.zeros(B, dtype=torch.bool)
+    hypotheses: List[list] = [[] for _ in range(B)]
+    results: List[list] = [[] for _ in range(B)]
+    with torch.no_grad():
+        for step in range(max_len):
+            _B = alive_seq.size(0) // K
+            tgt = alive_seq[:, -1]
+            dec_out = decoder_step(sd, tgt, mem, state)
+            log_probs = F.log_softmax(F.linear(dec_out, w_out, b_out), dim=-1)
+            log_probs.masked_fill_(grammar_mask(tgt, *grammar), -10000)
+            cur_len = alive_seq.shape[1]                       # len(self)
+            if cur_len <= min_length:
+                log_probs[:, EOS_ID] = -1e20
+            token_lp = log_probs.clone()
+            log_probs = log_probs + topk_log_probs.view(_B * K, 1)
+            curr_length = cur_len + 1
+            curr_scores = (log_probs / curr_length).reshape(_B, K * V)
+            order = torch.sort(curr_scores, dim=-1, descending=True, stable=True)
+            topk_scores, topk_flat = order.values[:, :K], order.indices[:, :K]
+            if min_gap is not None:
+                top = order.values[:, :K + 1]
+                gaps = (top[:, :-1] - top[:, 1:]) * curr_length
+                gaps = torch.where(torch.isfinite(gaps), gaps, torch.full_like(gaps, float("inf"))).min(dim=1).values
+                for i in range(_B):
+                    b = int(batch_offset[i])
+                    min_gap[b] = min(min_gap[b], float(gaps[i]))
+            if follow is not None:
+                theirs = torch.as_tensor(np.asarray(follow[step])[batch_offset.numpy(), :K].astype(np.int64))
+                their_scores = curr_scores.gather(1, theirs)
+                if not torch.equal(theirs, topk_flat):
+                    follow_stats["deviations"] = follow_stats.get("deviations", 0) + 1
+                    fin = torch.isfinite(their_scores)
+                    # (a) listed in descending order, (b) nothing left out beats the last one listed
+                    desc = torch.where(fin[:, :-1] & fin[:, 1:], their_scores[:, 1:] - their_scores[:, :-1],
+                                       torch.zeros_like(their_scores[:, 1:])).clamp(min=0).max() if K > 1 else torch.tensor(0.0)
+                    rest = curr_scores.clone()
+                    rest.scatter_(1, theirs, float("-inf"))
+                    left = torch.where(fin[:, -1], rest.max(dim=1).values - their_scores[:, -1],
+                                       torch.zeros_like(their_scores[:, -1])).clamp(min=0).max()
+                    viol = float(max(desc, left)) * curr_length
+                    if len(set(theirs.view(-1).tolist())) and any(len(set(r)) < K for r in theirs.tolist()):
+                        viol = float("inf")            # a candidate selected twice
+                    follow_stats["max_violation"] = max(follow_stats.get("max_violation", 0.0), viol)
+                topk_flat, topk_scores = theirs, their_scores
+            if record is not None:
+                record[step, batch_offset.numpy(), :K] = topk_flat.numpy()
+            topk_log_probs = (topk_scores * curr_length).reshape(-1)
+            parent = topk_flat // V + (torch.arange(_B) * K).unsqueeze(1)
+            select = parent.view(-1)
+            topk_ids = topk_flat % V
+            new_tok = topk_ids.view(-1, 1)
+            alive_logp = torch.cat([alive_logp.index_select(0, select), token_lp[select].gather(1, new_tok)], -1)
+            alive_hidden = torch.cat([alive_hidden.index_select(0, select), dec_out[select].unsqueeze(1)], 1)
+            alive_seq = torch.cat([alive_seq.index_select(0, select), new_tok], -1)
+            is_finished = topk_ids.eq(EOS_ID)
+            if alive_seq.shape[1] == max_len + 1:
+                is_finished = torch.ones_like(is_finished)
+            # reorder decoder state every step (OpenNMT translator; see docstring)
+            mem = mem.index_select(0, select)
+            state.index_select(select)
+            if not bool(is_finished.any()):
+                continue
+            # update_finished, beam_search.py:133-190
+            topk_log_probs = topk_log_probs.view(_B, K).masked_fill(is_finished, -1e10).view(-1)
+            top_beam_finished |= is_finished[:, 0]
+            keep = []
+            for i in range(_B):
+                b = int(batch_offset[i])
+                for j in is_finished[i].nonzero().view(-1).tolist():
+                    r = i * K + j
+                    hypotheses[b].append(dict(score=float(topk_scores[i, j]), ids=alive_seq[r, 1:].clone(),
+                                              logp=alive_logp[r].clone(), hidden=alive_hidden[r].clone()))
+                if bool(top_beam_finished[i]) and len(hypotheses[b]) >= n_best:
+                    best = sorted(hypotheses[b], key=lambda h: h["score"], reverse=True)
+                    results[b] = best[:n_best]
+                else:
+                    keep.append(i)
+            if not keep:
+                break
+            if len(keep) < _B:
+                kept = torch.tensor(keep)
+                rows = (kept.unsqueeze(1) * K + torch.arange(K)).view(-1)
+                top_beam_finished = top_beam_finished.index_select(0, kept)
+                batch_offset = batch_offset.index_select(0, kept)
+                topk_log_probs = topk_log_probs.index_select(0, rows)
+                alive_seq, alive_logp, alive_hidden = alive_seq[rows], alive_logp[rows], alive_hidden[rows]
+                mem = mem.index_select(0, rows)
+                state.index_select(rows)
+    return results
+
+
 # --------------------------------------------------------------------------------------
 # Bond head  (components.py:350-400, driver :470-491)
 # --------------------------------------------------------------------------------------
