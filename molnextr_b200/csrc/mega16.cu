@@ -103,34 +103,69 @@ __device__ __forceinline__ void h_tile_release(HCtx& c) {
     if (c.lane == 0) mbar_arrive(&c.empty[slot]);
     ++c.tile_seq;
 }
-// tile [256 k][16 cols]; warp w covers k in [32w, 32w+32); lane = col + 16 * parity, the two half-warps take
-// the even / odd k of the range (bank-conflict free: even rows hit banks 0-15, odd rows banks 16-31)
-__device__ __forceinline__ void h_tile_fma(const HCtx& c, const float* tile, const float* Xs, int ldx, int koff,
-                                           float (&acc)[H_GMAX]) {
-    const int col = c.lane & 15, par = c.lane >> 4;
-    const int kb = 32 * c.warp + par;
+// ---- sliced GEMM: out[g][col] = sum_k X[g][k] * tile[k][col], tile = [256 k][16 cols] fp32 ---------------
+// The shared-memory pipe (not the FMA pipe) bounds these products, so the mapping minimises shared-memory
+// wavefronts: warp w owns k in [32w, 32w+32); lane = j*8 + r*4 + cg owns the four columns 4cg..4cg+3 and
+// the four rows k_i = 32w + 8j + 2i + r (i = 0..3).  Per tile a lane issues four 16-byte weight loads --
+// each quarter-warp reads two adjacent rows = 128 contiguous bytes, conflict free, i.e. exactly the tile's
+// bytes once -- and takes its 4 x G activations from registers, loaded once per phase and reused by every
+// tile that shares them (q|k|v, the four W1 tiles).  The eight lanes that share cg then combine their
+// partial sums with a halving butterfly (4G shuffles) that leaves lane (j1, j0, r, cg) holding the warp
+// total of column 4cg + 2r + j0 for every row g; the eight warps are combined through shared memory.
+__device__ __forceinline__ void h_load_x(const HCtx& c, const float* Xs, int ldx, int koff, float (&xr)[4][H_GMAX]) {
+    const int kb = koff + 32 * c.warp + 8 * (c.lane >> 3) + ((c.lane >> 2) & 1);
+    // rows g >= G are computed too (their buffers exist and hold finite values; nobody reads the results):
+    // keeping the loops free of G-dependent branches keeps the shuffles below convergent
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const int k = kb + 2 * j;
-        const float w = tile[k * 16 + col];
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int g = 0; g < H_GMAX; ++g)
-            if (g < c.G) acc[g] = fmaf(Xs[g * ldx + koff + k], w, acc[g]);
+        for (int g = 0; g < H_GMAX; ++g) xr[i][g] = Xs[g * ldx + kb + 2 * i];
+}
+__device__ __forceinline__ void h_tile_fma(const HCtx& c, const float* tile, const float (&xr)[4][H_GMAX],
+                                           float (&acc)[H_GMAX][4]) {
+    const float* tw = tile + (32 * c.warp + 8 * (c.lane >> 3) + ((c.lane >> 2) & 1)) * 16 + 4 * (c.lane & 3);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 w = *reinterpret_cast<const float4*>(tw + 32 * i);
+#pragma unroll
+        for (int g = 0; g < H_GMAX; ++g) {
+            acc[g][0] = fmaf(xr[i][g], w.x, acc[g][0]);
+            acc[g][1] = fmaf(xr[i][g], w.y, acc[g][1]);
+            acc[g][2] = fmaf(xr[i][g], w.z, acc[g][2]);
+            acc[g][3] = fmaf(xr[i][g], w.w, acc[g][3]);
+        }
     }
 }
-// reduce the 2 k-parities (shuffle) and the 8 warps (shared memory) of NS accumulator sets, then call
-// f(set, row, col, value) once per output element.  Two h_syncs.
+// halving butterfly over the 8 lanes that share cg: tot[g] = warp total of column 4cg + 2r + j0
+__device__ __forceinline__ void h_warp_reduce(const HCtx& c, const float (&acc)[H_GMAX][4], float (&tot)[H_GMAX]) {
+    const bool r = (c.lane >> 2) & 1, j0 = (c.lane >> 3) & 1;
+#pragma unroll
+    for (int g = 0; g < H_GMAX; ++g) {
+            // bit r: lanes with r = 0 keep columns {0,1}, lanes with r = 1 keep {2,3}
+            const float s0 = __shfl_xor_sync(0xffffffffu, r ? acc[g][0] : acc[g][2], 4);
+            const float s1 = __shfl_xor_sync(0xffffffffu, r ? acc[g][1] : acc[g][3], 4);
+            const float u0 = (r ? acc[g][2] : acc[g][0]) + s0;
+            const float u1 = (r ? acc[g][3] : acc[g][1]) + s1;
+            // bit j0: keep column 2r + j0
+            const float s2 = __shfl_xor_sync(0xffffffffu, j0 ? u0 : u1, 8);
+            float v = (j0 ? u1 : u0) + s2;
+            // bit j1: plain sum (both lanes end up with the total)
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            tot[g] = v;
+        }
+}
+// combine the 8 warps of NS output sets, then call f(set, row, col, value) once per output element.
+// Two h_syncs.
 template <int NS, class F>
-__device__ __forceinline__ void h_reduce_apply(const HCtx& c, float (&acc)[NS][H_GMAX], F f) {
+__device__ __forceinline__ void h_reduce_apply(const HCtx& c, float (&tot)[NS][H_GMAX], F f) {
     float* red = reinterpret_cast<float*>(c.sm + HSmem::red);
+    if (c.lane < 16) {
+        const int col = 4 * (c.lane & 3) + 2 * ((c.lane >> 2) & 1) + ((c.lane >> 3) & 1);
 #pragma unroll
-    for (int s = 0; s < NS; ++s)
+        for (int s = 0; s < NS; ++s)
 #pragma unroll
-        for (int g = 0; g < H_GMAX; ++g)
-            if (g < c.G) {
-                const float v = acc[s][g] + __shfl_xor_sync(0xffffffffu, acc[s][g], 16);
-                if (c.lane < 16) red[((s * 8 + c.warp) * H_GMAX + g) * 16 + c.lane] = v;
-            }
+            for (int g = 0; g < H_GMAX; ++g) red[((s * 8 + c.warp) * H_GMAX + g) * 16 + col] = tot[s][g];
+    }
     h_sync();
     const int n_out = NS * c.G * 16;
     for (int idx = c.tid; idx < n_out; idx += 256) {
@@ -142,6 +177,20 @@ __device__ __forceinline__ void h_reduce_apply(const HCtx& c, float (&acc)[NS][H
         f(s, g, col, v);
     }
     h_sync();
+}
+// NS tiles that share the activations Xs[g][0..255] (ldx floats apart): tot[s][g] per lane
+template <int NS>
+__device__ __forceinline__ void h_gemm_shared_x(HCtx& c, const float* Xs, int ldx, float (&tot)[NS][H_GMAX]) {
+    float xr[4][H_GMAX];
+    h_load_x(c, Xs, ldx, 0, xr);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        float acc[H_GMAX][4] = {};
+        const float* tile = h_tile_acquire(c);
+        h_tile_fma(c, tile, xr, acc);
+        h_tile_release(c);
+        h_warp_reduce(c, acc, tot[s]);
+    }
 }
 // asynchronous remote store that signals the destination CTA's current exchange barrier with its bytes
 __device__ __forceinline__ void h_send(const HCtx& c, int byte_off, uint32_t dst_cta, float v) {
@@ -229,20 +278,25 @@ __device__ void h_attend(HCtx& c, int g, int nglobal, bool extra) {
             }
         } else {
             if (i == ntiles) {
+                // softmax over all keys by the whole group: p = exp(s - max) / sum (fp32, as onmt MultiHeadedAttention)
                 h_group_sync(c);
-                if (c.gwarp == 0) {   // softmax by one warp, shuffles only
-                    float m = -INFINITY;
-                    for (int j = c.lane; j < nkeys; j += 32) m = fmaxf(m, scores[j]);
-                    m = warp_max(m);
-                    float sum = 0.f;
-                    for (int j = c.lane; j < nkeys; j += 32) {
-                        const float e = expf(scores[j] - m);
-                        scores[j] = e;
-                        sum += e;
-                    }
-                    sum = warp_sum(sum);
-                    for (int j = c.lane; j < nkeys; j += 32) scores[j] = scores[j] / sum;
+                float m = -INFINITY;
+                for (int j = c.gtid; j < nkeys; j += 128) m = fmaxf(m, scores[j]);
+                m = warp_max(m);
+                if (c.lane == 0) ared[c.gwarp] = m;
+                h_group_sync(c);
+                m = fmaxf(fmaxf(ared[0], ared[1]), fmaxf(ared[2], ared[3]));
+                float sum = 0.f;
+                for (int j = c.gtid; j < nkeys; j += 128) {
+                    const float e = expf(scores[j] - m);
+                    scores[j] = e;
+                    sum += e;
                 }
+                sum = warp_sum(sum);
+                if (c.lane == 0) ared[4 + c.gwarp] = sum;
+                h_group_sync(c);
+                sum = (ared[4] + ared[5]) + (ared[6] + ared[7]);
+                for (int j = c.gtid; j < nkeys; j += 128) scores[j] = scores[j] / sum;
                 h_group_sync(c);
             }
             const float* ps = scores + tile * H_TK;
@@ -445,13 +499,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a)
                 h_layer_norm(c, P + HP_LN1W, P + HP_LN1B);
                 H_MARK();   // 1: LN1
                 {
-                    float acc[3][H_GMAX] = {};
-#pragma unroll
-                    for (int which = 0; which < 3; ++which) {
-                        const float* tile = h_tile_acquire(c);
-                        h_tile_fma(c, tile, nbuf, 256, 0, acc[which]);
-                        h_tile_release(c);
-                    }
+                    float acc[3][H_GMAX];
+                    h_gemm_shared_x<3>(c, nbuf, 256, acc);
                     h_reduce_apply<3>(c, acc, [&](int which, int g, int col, float v) {
                         float o = v + P[HP_BQ + which * 16 + col];
                         if (s_fin[g]) return;
@@ -473,10 +522,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a)
                 h_exchange(c, (uint32_t)n_alive * 1024u);                // ctx complete everywhere
                 H_MARK();   // 5: ctx exchange
                 {
-                    float acc[1][H_GMAX] = {};
-                    const float* tile = h_tile_acquire(c);
-                    h_tile_fma(c, tile, ctxbuf, 256, 0, acc[0]);
-                    h_tile_release(c);
+                    float acc[1][H_GMAX];
+                    h_gemm_shared_x<1>(c, ctxbuf, 256, acc);
                     h_reduce_apply<1>(c, acc, [&](int, int g, int col, float v) {
                         const int n = c.rank * 16 + col;
                         h_bcast(c, HSmem::xbuf + (g * 256 + n) * 4, (v + P[HP_BO + col]) + xbuf[g * 256 + n]);
@@ -488,10 +535,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a)
                 // ---------- context attention ----------
                 h_layer_norm(c, P + HP_LN2W, P + HP_LN2B);
                 {
-                    float acc[1][H_GMAX] = {};
-                    const float* tile = h_tile_acquire(c);
-                    h_tile_fma(c, tile, nbuf, 256, 0, acc[0]);
-                    h_tile_release(c);
+                    float acc[1][H_GMAX];
+                    h_gemm_shared_x<1>(c, nbuf, 256, acc);
                     h_reduce_apply<1>(c, acc, [&](int, int g, int col, float v) {
                         if (s_fin[g]) return;
                         h_send(c, HSmem::qkvs + (((g >> 1) * 3 + 0) * 32 + c.half * 16 + col) * 4,
@@ -506,10 +551,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a)
                 h_exchange(c, (uint32_t)n_alive * 1024u);
                 H_MARK();   // 11: ctx exchange
                 {
-                    float acc[1][H_GMAX] = {};
-                    const float* tile = h_tile_acquire(c);
-                    h_tile_fma(c, tile, ctxbuf, 256, 0, acc[0]);
-                    h_tile_release(c);
+                    float acc[1][H_GMAX];
+                    h_gemm_shared_x<1>(c, ctxbuf, 256, acc);
                     h_reduce_apply<1>(c, acc, [&](int, int g, int col, float v) {
                         const int n = c.rank * 16 + col;
                         h_bcast(c, HSmem::xbuf + (g * 256 + n) * 4, (v + P[HP_BOC + col]) + xbuf[g * 256 + n]);
@@ -521,13 +564,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a)
                 // ---------- feed forward ----------
                 h_layer_norm(c, P + HP_LNFW, P + HP_LNFB);
                 {
-                    float acc[4][H_GMAX] = {};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float* tile = h_tile_acquire(c);
-                        h_tile_fma(c, tile, nbuf, 256, 0, acc[j]);
-                        h_tile_release(c);
-                    }
+                    float acc[4][H_GMAX];
+                    h_gemm_shared_x<4>(c, nbuf, 256, acc);
                     h_reduce_apply<4>(c, acc, [&](int j, int g, int col, float v) {
                         h_bcast(c, HSmem::hbuf + (g * 1024 + c.rank * 64 + j * 16 + col) * 4, gelu_erf(v + P[HP_B1 + j * 16 + col]));
                     });
@@ -536,12 +574,18 @@ __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a)
                 h_exchange(c, (uint32_t)c.G * 4096u);                     // FFN hidden
                 H_MARK();   // 15: h exchange
                 {
-                    float acc[1][H_GMAX] = {};
+                    float acc[1][H_GMAX];
+                    {
+                        float a4[H_GMAX][4] = {};
 #pragma unroll 1
-                    for (int j = 0; j < 4; ++j) {
-                        const float* tile = h_tile_acquire(c);
-                        h_tile_fma(c, tile, hbuf, 1024, 256 * j, acc[0]);
-                        h_tile_release(c);
+                        for (int j = 0; j < 4; ++j) {
+                            float xr[4][H_GMAX];
+                            h_load_x(c, hbuf, 1024, 256 * j, xr);
+                            const float* tile = h_tile_acquire(c);
+                            h_tile_fma(c, tile, xr, a4);
+                            h_tile_release(c);
+                        }
+                        h_warp_reduce(c, a4, acc[0]);
                     }
                     h_reduce_apply<1>(c, acc, [&](int, int g, int col, float v) {
                         const int n = c.rank * 16 + col;
@@ -555,10 +599,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a)
             // ---------- final LayerNorm, vocabulary slice, logits all-gather ----------
             h_layer_norm(c, fp, fp + 256);
             {
-                float acc[1][H_GMAX] = {};
-                const float* tile = h_tile_acquire(c);
-                h_tile_fma(c, tile, nbuf, 256, 0, acc[0]);
-                h_tile_release(c);
+                float acc[1][H_GMAX];
+                h_gemm_shared_x<1>(c, nbuf, 256, acc);
                 h_reduce_apply<1>(c, acc, [&](int, int g, int col, float v) {
                     const int n = c.rank * 16 + col;
                     h_bcast(c, HSmem::lgbuf + (g * 256 + n) * 4, v + fp[512 + n]);
