@@ -8,7 +8,7 @@ namespace mnx {
 #define MG_TILES_PER_LAYER_H 14
 #define MG_PARAM_FLOATS_H 1920
 #define MG_GMAX_H 4      // rows per 8-CTA cluster (mega.cu)
-#define MG16_GMAX_H 4    // rows per 16-CTA cluster (mega16.cu)
+#define MG16_GMAX_H 5    // rows per 16-CTA cluster (mega16.cu)
 
 struct MegaArgs {
     const float* wpack;

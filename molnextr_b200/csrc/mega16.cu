@@ -3,11 +3,13 @@
 //
 // What limits mega.cu is the ~40 B/clk a single SM can pull from L2: per decode step each CTA of an
 // 8-CTA cluster ingests 2.7 MB of fp32 weights plus the K/V rows of its (row, head) pairs.  Here a
-// cluster has 16 CTAs and owns G <= 4 rows: CTA i owns a 1/16 column slice of every Linear (16 KB tiles
-// [256 k][16 cols], 1.35 MB per step) and the attention of head i/2 for rows {i%2, i%2 + 2}.
+// cluster has 16 CTAs and owns G <= 5 rows: CTA i owns a 1/16 column slice of every Linear (16 KB tiles
+// [256 k][16 cols], 1.35 MB per step) and the attention of head i/2 for rows {i%2, i%2 + 2, i%2 + 4}.
 // All global -> shared traffic (weight tiles, parameter blocks, K/V tiles) is issued by ONE producer
 // thread in the order the math consumes it, so latency-critical K/V tiles never queue behind weight
-// tiles that are only needed later.  Exchanges between CTAs use st.async into distributed shared
+// tiles that are only needed later.  Each CTA runs up to three attention groups of three warps (rows
+// half, half + 2, half + 4 of the cluster), so a cluster serves G <= 5 rows and seven co-resident clusters
+// cover a batch of 32.  Exchanges between CTAs use st.async into distributed shared
 // memory with mbarrier complete_tx signalling; q/k/v slices go only to the CTA that owns the head.
 // Arithmetic is fp32 and follows the same reference lines as decoder.cu / mega.cu.
 #include "mega.cuh"
@@ -16,11 +18,14 @@ namespace mnx {
 namespace {
 
 #define H_CS 16
-#define H_THREADS 288
-#define H_GMAX 4
+#define H_CT 288                  // compute threads: 9 warps (8 split K in the GEMMs; 3 attention groups x 3 warps)
+#define H_THREADS 320             // + 1 producer warp
+#define H_GMAX 5
+#define H_NG 3                    // attention groups per CTA
+#define H_GT 96                   // threads per attention group
 #define H_TILE_FLOATS (256 * 16)
 #define H_TILE_BYTES (H_TILE_FLOATS * 4)
-#define H_RING 6
+#define H_RING 3
 #define H_TILES_PER_LAYER 14
 #define H_PARAM_FLOATS 1728
 #define H_TK 144
@@ -31,22 +36,25 @@ enum { HP_LN1W = 0, HP_LN1B = 256, HP_LN2W = 512, HP_LN2B = 768, HP_LNFW = 1024,
 
 struct HSmem {
     static constexpr int ring = 0;
-    static constexpr int kv = ring + H_RING * H_TILE_BYTES;                   // 98304; [2 groups][2 bufs][144][32]
-    static constexpr int params = kv + 4 * H_TK * 128;                         // +73728
+    static constexpr int kv = ring + H_RING * H_TILE_BYTES;                   // [3 groups][2 bufs][144][32]
+    static constexpr int params = kv + H_NG * 2 * H_TK * 128;
     static constexpr int finalp = params + 2 * H_PARAM_FLOATS * 4;
     static constexpr int xbuf = finalp + 768 * 4;
     static constexpr int nbuf = xbuf + H_GMAX * 256 * 4;
     static constexpr int ctxbuf = nbuf + H_GMAX * 256 * 4;
-    static constexpr int lgbuf = ctxbuf + H_GMAX * 256 * 4;
-    static constexpr int hbuf = lgbuf + H_GMAX * 256 * 4;
-    static constexpr int qkvs = hbuf + H_GMAX * 1024 * 4;                      // [2 groups][3][32]
-    static constexpr int red = qkvs + 2 * 3 * 32 * 4;                          // [4 sets][8 warps][G][16]; scores alias
-    static constexpr int scores = red;                                         // [2 groups][1024]
-    static constexpr int ared = red + 2 * 1024 * 4;
-    static constexpr int misc = ared + 2 * 128 * 4;
+    static constexpr int hbuf = ctxbuf + H_GMAX * 256 * 4;
+    // the logits alias the FFN hidden buffer: they are sent after the x3 exchange of the last layer (every
+    // CTA has finished reading hbuf) and hbuf is next written after the x1 exchange of the following step
+    // (every CTA has finished its argmax)
+    static constexpr int lgbuf = hbuf;
+    static constexpr int qkvs = hbuf + H_GMAX * 1024 * 4;                      // [3 groups][3][32]
+    static constexpr int red = qkvs + H_NG * 3 * 32 * 4;                       // [4 sets][8 warps][G][16]; scores alias
+    static constexpr int scores = red;                                         // [3 groups][1024]
+    static constexpr int ared = red + H_NG * 1024 * 4;
+    static constexpr int misc = ared + H_NG * 128 * 4;
     static constexpr int total = misc + 512;
 };
-static_assert(4 * 8 * H_GMAX * 16 * 4 <= 2 * 1024 * 4, "reduction scratch must fit in the scores area");
+static_assert(4 * 8 * H_GMAX * 16 * 4 <= H_NG * 1024 * 4, "reduction scratch must fit in the scores area");
 static_assert(HSmem::total <= 232448, "shared memory budget exceeded");
 
 __device__ __forceinline__ uint32_t h_mapa(uint32_t local_addr, uint32_t cta) {
@@ -71,7 +79,7 @@ __device__ __forceinline__ void h_cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
 }
-__device__ __forceinline__ void h_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void h_sync() { asm volatile("bar.sync 1, 288;" ::: "memory"); }
 __device__ __forceinline__ unsigned h_ld_acquire(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -86,7 +94,8 @@ struct HCtx {
     int rank, head, half;           // cluster rank i, head = i / 2, half = i % 2
     int tid, lane, warp;
     int G;
-    int grp, gtid, gwarp;           // attention group (0/1), 128 threads each
+    int grp, gtid, gwarp;           // attention group (0..2), 96 threads = 3 warps each
+    int kw;                         // K-split index in the GEMMs: warps 0..7; warp 8 shadows warp 0 (results unused)
     uint64_t *full, *empty, *kvfull, *kvempty, *pbar, *xbar, *stepbar;
     uint32_t tile_seq, x_seq, kv_seq;
     uint32_t xbar_base;             // shared::cta address of xbar[0] (same offset in every CTA)
@@ -100,7 +109,7 @@ __device__ __forceinline__ const float* h_tile_acquire(HCtx& c) {
 __device__ __forceinline__ void h_tile_release(HCtx& c) {
     const uint32_t slot = c.tile_seq % H_RING;
     __syncwarp();
-    if (c.lane == 0) mbar_arrive(&c.empty[slot]);
+    if (c.lane == 0 && c.warp < 8) mbar_arrive(&c.empty[slot]);
     ++c.tile_seq;
 }
 // ---- sliced GEMM: out[g][col] = sum_k X[g][k] * tile[k][col], tile = [256 k][16 cols] fp32 ---------------
@@ -113,7 +122,7 @@ __device__ __forceinline__ void h_tile_release(HCtx& c) {
 // partial sums with a halving butterfly (4G shuffles) that leaves lane (j1, j0, r, cg) holding the warp
 // total of column 4cg + 2r + j0 for every row g; the eight warps are combined through shared memory.
 __device__ __forceinline__ void h_load_x(const HCtx& c, const float* Xs, int ldx, int koff, float (&xr)[4][H_GMAX]) {
-    const int kb = koff + 32 * c.warp + 8 * (c.lane >> 3) + ((c.lane >> 2) & 1);
+    const int kb = koff + 32 * c.kw + 8 * (c.lane >> 3) + ((c.lane >> 2) & 1);
     // rows g >= G are computed too (their buffers exist and hold finite values; nobody reads the results):
     // keeping the loops free of G-dependent branches keeps the shuffles below convergent
 #pragma unroll
@@ -123,7 +132,7 @@ __device__ __forceinline__ void h_load_x(const HCtx& c, const float* Xs, int ldx
 }
 __device__ __forceinline__ void h_tile_fma(const HCtx& c, const float* tile, const float (&xr)[4][H_GMAX],
                                            float (&acc)[H_GMAX][4]) {
-    const float* tw = tile + (32 * c.warp + 8 * (c.lane >> 3) + ((c.lane >> 2) & 1)) * 16 + 4 * (c.lane & 3);
+    const float* tw = tile + (32 * c.kw + 8 * (c.lane >> 3) + ((c.lane >> 2) & 1)) * 16 + 4 * (c.lane & 3);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const float4 w = *reinterpret_cast<const float4*>(tw + 32 * i);
@@ -159,7 +168,7 @@ __device__ __forceinline__ void h_warp_reduce(const HCtx& c, const float (&acc)[
 template <int NS, class F>
 __device__ __forceinline__ void h_reduce_apply(const HCtx& c, float (&tot)[NS][H_GMAX], F f) {
     float* red = reinterpret_cast<float*>(c.sm + HSmem::red);
-    if (c.lane < 16) {
+    if (c.lane < 16 && c.warp < 8) {
         const int col = 4 * (c.lane & 3) + 2 * ((c.lane >> 2) & 1) + ((c.lane >> 3) & 1);
 #pragma unroll
         for (int s = 0; s < NS; ++s)
@@ -168,7 +177,7 @@ __device__ __forceinline__ void h_reduce_apply(const HCtx& c, float (&tot)[NS][H
     }
     h_sync();
     const int n_out = NS * c.G * 16;
-    for (int idx = c.tid; idx < n_out; idx += 256) {
+    for (int idx = c.tid; idx < n_out; idx += H_CT) {
         const int col = idx & 15, sg = idx >> 4;
         const int s = sg / c.G, g = sg - s * c.G;
         float v = 0.f;
@@ -237,7 +246,7 @@ __device__ __forceinline__ void h_layer_norm(const HCtx& c, const float* w, cons
     h_sync();
 }
 __device__ __forceinline__ void h_group_sync(const HCtx& c) {
-    asm volatile("bar.sync %0, 128;" ::"r"(2 + c.grp) : "memory");
+    asm volatile("bar.sync %0, 96;" ::"r"(2 + c.grp) : "memory");
 }
 
 // single-query attention of this CTA's head for the row of thread group c.grp (cluster row `g`).
@@ -245,7 +254,7 @@ __device__ __forceinline__ void h_group_sync(const HCtx& c) {
 // (already in qkvs) is appended as key index nglobal.  The context slice goes to all 16 CTAs.
 __device__ void h_attend(HCtx& c, int g, int nglobal, bool extra) {
     float* scores = reinterpret_cast<float*>(c.sm + HSmem::scores) + c.grp * 1024;
-    float* ared = reinterpret_cast<float*>(c.sm + HSmem::ared) + c.grp * 128;
+    float* ared = reinterpret_cast<float*>(c.sm + HSmem::ared) + c.grp * 128;   // [3 warps][32] + softmax scratch at 96..
     const float* qs = reinterpret_cast<const float*>(c.sm + HSmem::qkvs) + (c.grp * 3 + 0) * 32;
     const float* ks = reinterpret_cast<const float*>(c.sm + HSmem::qkvs) + (c.grp * 3 + 1) * 32;
     const float* vs = reinterpret_cast<const float*>(c.sm + HSmem::qkvs) + (c.grp * 3 + 2) * 32;
@@ -263,7 +272,7 @@ __device__ void h_attend(HCtx& c, int g, int nglobal, bool extra) {
             h_group_sync(c);
         }
         if (i < ntiles) {
-            for (int j = c.gtid; j < nk; j += 128) {
+            for (int j = c.gtid; j < nk; j += H_GT) {
                 const float4* kr = reinterpret_cast<const float4*>(tb + j * 32);
                 float s = 0.f;
 #pragma unroll
@@ -281,27 +290,27 @@ __device__ void h_attend(HCtx& c, int g, int nglobal, bool extra) {
                 // softmax over all keys by the whole group: p = exp(s - max) / sum (fp32, as onmt MultiHeadedAttention)
                 h_group_sync(c);
                 float m = -INFINITY;
-                for (int j = c.gtid; j < nkeys; j += 128) m = fmaxf(m, scores[j]);
+                for (int j = c.gtid; j < nkeys; j += H_GT) m = fmaxf(m, scores[j]);
                 m = warp_max(m);
-                if (c.lane == 0) ared[c.gwarp] = m;
+                if (c.lane == 0) ared[96 + c.gwarp] = m;
                 h_group_sync(c);
-                m = fmaxf(fmaxf(ared[0], ared[1]), fmaxf(ared[2], ared[3]));
+                m = fmaxf(fmaxf(ared[96], ared[97]), ared[98]);
                 float sum = 0.f;
-                for (int j = c.gtid; j < nkeys; j += 128) {
+                for (int j = c.gtid; j < nkeys; j += H_GT) {
                     const float e = expf(scores[j] - m);
                     scores[j] = e;
                     sum += e;
                 }
                 sum = warp_sum(sum);
-                if (c.lane == 0) ared[4 + c.gwarp] = sum;
+                if (c.lane == 0) ared[100 + c.gwarp] = sum;
                 h_group_sync(c);
-                sum = (ared[4] + ared[5]) + (ared[6] + ared[7]);
-                for (int j = c.gtid; j < nkeys; j += 128) scores[j] = scores[j] / sum;
+                sum = (ared[100] + ared[101]) + ared[102];
+                for (int j = c.gtid; j < nkeys; j += H_GT) scores[j] = scores[j] / sum;
                 h_group_sync(c);
             }
             const float* ps = scores + tile * H_TK;
 #pragma unroll 4
-            for (int j = c.gwarp; j < nk; j += 4) acc = fmaf(ps[j], tb[j * 32 + c.lane], acc);
+            for (int j = c.gwarp; j < nk; j += 3) acc = fmaf(ps[j], tb[j * 32 + c.lane], acc);
         }
         h_group_sync(c);   // tile consumed
         if (c.gtid == 0) mbar_arrive(&c.kvempty[c.grp * 2 + slot]);
@@ -311,7 +320,7 @@ __device__ void h_attend(HCtx& c, int g, int nglobal, bool extra) {
     h_group_sync(c);
     if (c.gwarp == 0)
         h_bcast(c, HSmem::ctxbuf + (g * 256 + c.head * 32 + c.lane) * 4,
-                (ared[c.lane] + ared[32 + c.lane]) + (ared[64 + c.lane] + ared[96 + c.lane]));
+                (ared[c.lane] + ared[32 + c.lane]) + ared[64 + c.lane]);
 }
 
 __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a) {
@@ -325,14 +334,15 @@ __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a)
         c.rank = (int)r;
     }
     c.head = c.rank >> 1; c.half = c.rank & 1;
-    c.grp = (c.warp >> 2) & 1; c.gtid = c.tid & 127; c.gwarp = c.warp & 3;
+    c.grp = (c.warp < 9) ? c.warp / 3 : 0; c.gwarp = c.warp - 3 * c.grp; c.gtid = c.gwarp * 32 + c.lane;
+    c.kw = (c.warp < 8) ? c.warp : 0;
     const int cluster = blockIdx.x / H_CS;
     const int row0 = cluster * a.G;
     c.G = min(a.G, a.B - row0);
     c.tile_seq = 0; c.x_seq = 0; c.kv_seq = 0;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + HSmem::misc);
-    c.full = bars; c.empty = bars + H_RING; c.kvfull = bars + 2 * H_RING; c.kvempty = c.kvfull + 4;
-    c.pbar = c.kvempty + 4; c.xbar = c.pbar + 2; c.stepbar = c.xbar + 4;
+    c.full = bars; c.empty = bars + H_RING; c.kvfull = bars + 2 * H_RING; c.kvempty = c.kvfull + 2 * H_NG;
+    c.pbar = c.kvempty + 2 * H_NG; c.xbar = c.pbar + 2; c.stepbar = c.xbar + 4;
     c.xbar_base = smem_u32(&c.xbar[0]);
     int* s_tok = reinterpret_cast<int*>(c.stepbar + 1);
     int* s_fin = s_tok + H_GMAX;
@@ -341,7 +351,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a)
 
     if (c.tid == 0) {
         for (int i = 0; i < H_RING; ++i) { mbar_init(&c.full[i], 1); mbar_init(&c.empty[i], 8); }
-        for (int i = 0; i < 4; ++i) { mbar_init(&c.kvfull[i], 1); mbar_init(&c.kvempty[i], 1); }
+        for (int i = 0; i < 2 * H_NG; ++i) { mbar_init(&c.kvfull[i], 1); mbar_init(&c.kvempty[i], 1); }
         mbar_init(&c.pbar[0], 1); mbar_init(&c.pbar[1], 1);
         for (int i = 0; i < 4; ++i) mbar_init(&c.xbar[i], 1);
         mbar_init(c.stepbar, 1);
@@ -356,11 +366,11 @@ __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a)
     const float* wbase = a.wpack16 + (size_t)c.rank * (MNX_DEC_L * H_TILES_PER_LAYER + 1) * H_TILE_FLOATS;
     const float* pbase = a.ppack16 + (size_t)c.rank * MNX_DEC_L * H_PARAM_FLOATS;
 
-    if (c.warp == 8) {
+    if (c.warp == 9) {
         // ======================= producer: every global -> shared transfer, in consumption order =======================
         if (c.lane == 0) {
             const uint64_t keep = l2_policy_evict_last(), stream = l2_policy_evict_first();
-            uint32_t seq = 0, pseq = 0, step = 0, kvseq[2] = {0u, 0u};
+            uint32_t seq = 0, pseq = 0, step = 0, kvseq[H_NG] = {0u, 0u, 0u};
             auto weight_tile = [&](int index) {
                 const uint32_t slot = seq % H_RING, ph = (seq / H_RING) & 1u;
                 mbar_wait(&c.empty[slot], ph ^ 1u);
@@ -375,7 +385,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a)
                 const int nkeys = nglobal + (extra ? 1 : 0);
                 const int ntiles = (nkeys + H_TK - 1) / H_TK;
                 for (int i = 0; i < 2 * ntiles; ++i) {
-                    for (int p = 0; p < 2; ++p) {
+                    for (int p = 0; p < H_NG; ++p) {
                         if (!live[p]) continue;
                         const uint32_t s = kvseq[p] + (uint32_t)i, slot = s & 1u;
                         mbar_wait(&c.kvempty[p * 2 + slot], ((s >> 1) & 1u) ^ 1u);
@@ -392,16 +402,16 @@ __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a)
                         }
                     }
                 }
-                for (int p = 0; p < 2; ++p)
+                for (int p = 0; p < H_NG; ++p)
                     if (live[p]) kvseq[p] += (uint32_t)(2 * ntiles);
             };
             for (;;) {
                 mbar_wait(c.stepbar, step & 1u);
                 if (*reinterpret_cast<volatile int*>(s_go) == 0) break;
                 const int t = (int)step;
-                bool live[2];
-                int grow[2];
-                for (int p = 0; p < 2; ++p) {
+                bool live[H_NG];
+                int grow[H_NG];
+                for (int p = 0; p < H_NG; ++p) {
                     grow[p] = c.half + 2 * p;
                     live[p] = grow[p] < c.G && reinterpret_cast<volatile int*>(s_fin)[grow[p]] == 0;
                 }
@@ -416,8 +426,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a)
                     const int base = l * H_TILES_PER_LAYER;
                     weight_tile(base + 0); weight_tile(base + 1); weight_tile(base + 2);          // q, k, v
                     {
-                        const float* Kb[2], *Vb[2];
-                        for (int p = 0; p < 2; ++p) {
+                        const float* Kb[H_NG], *Vb[H_NG];
+                        for (int p = 0; p < H_NG; ++p) {
                             const size_t off = l * kv_layer + ((size_t)(row0 + grow[p]) * 8 + c.head) * a.T * 32;
                             Kb[p] = a.selfK + off; Vb[p] = a.selfV + off;
                         }
@@ -425,8 +435,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a)
                     }
                     weight_tile(base + 3); weight_tile(base + 4);                                  // Wo, Wq_ctx
                     {
-                        const float* Kb[2], *Vb[2];
-                        for (int p = 0; p < 2; ++p) {
+                        const float* Kb[H_NG], *Vb[H_NG];
+                        for (int p = 0; p < H_NG; ++p) {
                             const size_t off = (((size_t)l * a.B + row0 + grow[p]) * 8 + c.head) * (size_t)a.S * 32;
                             Kb[p] = a.crossK + off; Vb[p] = a.crossV + off;
                         }
@@ -440,7 +450,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a)
         }
         __syncwarp();
     } else {
-        // ======================= 8 compute warps =======================
+        // ======================= 9 compute warps =======================
         float* xbuf = reinterpret_cast<float*>(sm + HSmem::xbuf);
         float* nbuf = reinterpret_cast<float*>(sm + HSmem::nbuf);
         float* ctxbuf = reinterpret_cast<float*>(sm + HSmem::ctxbuf);
@@ -463,7 +473,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a)
             const int my_g = c.half + 2 * c.grp;                       // cluster row handled by this thread's group
             const bool my_row = my_g < c.G && s_fin[my_g] == 0;
             int n_my = 0;
-            for (int p = 0; p < 2; ++p) n_my += (c.half + 2 * p < c.G && s_fin[c.half + 2 * p] == 0) ? 1 : 0;
+            for (int p = 0; p < H_NG; ++p) n_my += (c.half + 2 * p < c.G && s_fin[c.half + 2 * p] == 0) ? 1 : 0;
             // ---- rank of each alive row among all alive rows of the batch (row-rank PE rule) ----
             if (c.warp == 0) {
                 int finished_before = 0;
@@ -482,7 +492,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a)
                 }
             }
             h_sync();
-            for (int i = c.tid; i < c.G * 256; i += 256) {
+            for (int i = c.tid; i < c.G * 256; i += H_CT) {
                 const int g = i >> 8, d = i & 255;
                 xbuf[i] = (s_fin[g] == 0) ? a.emb[s_tok[g] * 256 + d] * 16.0f + a.pe[(size_t)s_rank[g] * 256 + d] : 0.f;
             }
