@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmolnextr_b200.so")
+# MNX_LIB_PATH selects another build of the same library (A/B timing of kernel variants)
+LIB_PATH = os.environ.get("MNX_LIB_PATH") or os.path.join(_HERE, "lib", "libmolnextr_b200.so")
 
 MNX_OK = 0
 ENCODER_NONE, ENCODER_SWIN_B, ENCODER_CONVNEXT_B = 0, 1, 2

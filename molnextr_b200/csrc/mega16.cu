@@ -50,18 +50,11 @@ struct HSmem {
     static constexpr int qkvs = hbuf + H_GMAX * 1024 * 4;                      // [3 groups][3][32]
     static constexpr int red = qkvs + H_NG * 3 * 32 * 4;                       // [4 sets][8 warps][G][16]; scores alias
     static constexpr int scores = red;                                         // [3 groups][1024]
-    static constexpr int ared = red + H_NG * 1024 * 4;                         // [3 groups][160]: PV partials, softmax scratch, ctx row
-    // rows staged between the epilogue (one element per thread) and the 16-byte remote stores
-    static constexpr int stage_x = ared + H_NG * 160 * 4;                      // [G][16]   x1 / x2 / x3 slices
-    static constexpr int stage_h = stage_x + H_GMAX * 16 * 4;                  // [G][64]   FFN hidden slice; [G][16] logits
-    static constexpr int misc = stage_h + H_GMAX * 64 * 4;
+    static constexpr int ared = red + H_NG * 1024 * 4;
+    static constexpr int misc = ared + H_NG * 128 * 4;
     static constexpr int total = misc + 512;
 };
 static_assert(4 * 8 * H_GMAX * 16 * 4 <= H_NG * 1024 * 4, "reduction scratch must fit in the scores area");
-// activations that are all-gathered slice by slice are stored slice-major, [slice][row][cols of the slice], so
-// that the rows a CTA contributes are contiguous in every destination: one bulk copy per destination CTA
-#define H_XOFF(g, k) (((((k) >> 4) * H_GMAX) + (g)) * 16 + ((k) & 15))      // xbuf, lgbuf: 16 slices of 16 columns
-#define H_HOFF(g, k) (((((k) >> 6) * H_GMAX) + (g)) * 64 + ((k) & 63))      // hbuf: 16 slices of 64 columns
 static_assert(HSmem::total <= 232448, "shared memory budget exceeded");
 
 __device__ __forceinline__ uint32_t h_mapa(uint32_t local_addr, uint32_t cta) {
@@ -102,21 +95,11 @@ struct HCtx {
     int tid, lane, warp;
     int G;
     int grp, gtid, gwarp;           // attention group (0..2), 96 threads = 3 warps each
-    long long* prof;                // optional cycle stamps (MNX_DECODE_PROFILE): see h_mark
-    int pm, prof_on, fine;
     uint64_t *full, *empty, *kvfull, *kvempty, *pbar, *xbar, *stepbar;
     uint32_t tile_seq, x_seq, kv_seq;
     uint32_t xbar_base;             // shared::cta address of xbar[0] (same offset in every CTA)
 };
 
-// cycle stamp of cluster 0 / CTA 0 / thread 0 at (step 100, layer 1); `fine` marks are taken only inside the
-// phases that switch c.fine on
-__device__ __forceinline__ void h_mark(HCtx& c) {
-    if (c.prof_on && c.pm < 64) c.prof[c.pm++] = clock64();
-}
-__device__ __forceinline__ void h_mark_fine(HCtx& c) {
-    if (c.prof_on && c.fine && c.pm < 64) c.prof[c.pm++] = clock64();
-}
 __device__ __forceinline__ const float* h_tile_acquire(HCtx& c) {
     const uint32_t slot = c.tile_seq % H_RING, ph = (c.tile_seq / H_RING) & 1u;
     mbar_wait(&c.full[slot], ph);
@@ -216,11 +199,9 @@ __device__ __forceinline__ void h_gemm_shared_x(HCtx& c, const float* Xs, int ld
     for (int s = 0; s < NS; ++s) {
         float acc[H_GMAX][4] = {};
         const float* tile = h_tile_acquire(c);
-        h_mark_fine(c);
         h_tile_fma(c, tile, xr, acc);
         h_tile_release(c);
         h_warp_reduce(c, acc, tot[s]);
-        h_mark_fine(c);
     }
 }
 // asynchronous remote store that signals the destination CTA's current exchange barrier with its bytes
@@ -238,14 +219,20 @@ __device__ __forceinline__ void h_send4(const HCtx& c, int byte_off, uint32_t ds
                  "r"(h_mapa(c.xbar_base + 8u * (c.x_seq & 3u), dst_cta))
                  : "memory");
 }
-// all-gather form of h_reduce_apply: element (s, g, col) becomes val(s, g, col, sum); the CTA's rows
-// [G][NS*16] are staged at byte offset stage_off (one element per thread: the epilogue may be a GELU) and then
-// written to byte offset dst_off of EVERY CTA of the cluster (destinations are slice-major, see H_XOFF /
-// H_HOFF, so the staged rows map to one contiguous range per destination).
-template <int NS, class V>
-__device__ __forceinline__ void h_reduce_bcast(HCtx& c, float (&tot)[NS][H_GMAX], V val, int stage_off, int dst_off) {
+__device__ __forceinline__ void h_bcast(const HCtx& c, int byte_off, float v) {
+#pragma unroll
+    for (uint32_t d = 0; d < H_CS; ++d) h_send(c, byte_off, d, v);
+}
+// all-gather form of h_reduce_apply: element (s, g, col) becomes val(s, g, col, sum) and is written to byte
+// offset off(s, g) + 4 * col of EVERY CTA of the cluster with 16-byte remote stores (the DSMEM store path
+// moves ~20 B/clk per SM but only ~1 request/clk, so scalar stores were 4x slower).  One task = four adjacent
+// columns x 16 / DS destination CTAs; DS is chosen so that one pass over the threads covers all tasks.
+// Measured alternatives that were SLOWER on B200: staging the epilogue through shared memory to avoid the
+// DS-fold recomputation (one more block barrier per phase costs more than the recomputation), DSMEM bulk
+// copies (cp.async.bulk shared::cta -> shared::cluster takes ~1000 cycles to issue).
+template <int NS, int DS, class V, class O>
+__device__ __forceinline__ void h_reduce_bcast(const HCtx& c, float (&tot)[NS][H_GMAX], V val, O off) {
     float* red = reinterpret_cast<float*>(c.sm + HSmem::red);
-    float* stage = reinterpret_cast<float*>(c.sm + stage_off);
     if (c.lane < 16 && c.warp < 8) {
         const int col = 4 * (c.lane & 3) + 2 * ((c.lane >> 2) & 1) + ((c.lane >> 3) & 1);
 #pragma unroll
@@ -254,29 +241,26 @@ __device__ __forceinline__ void h_reduce_bcast(HCtx& c, float (&tot)[NS][H_GMAX]
             for (int g = 0; g < H_GMAX; ++g) red[((s * 8 + c.warp) * H_GMAX + g) * 16 + col] = tot[s][g];
     }
     h_sync();
-    h_mark_fine(c);
-    const int n_out = NS * c.G * 16;
-    for (int idx = c.tid; idx < n_out; idx += H_CT) {
-        const int col = idx & 15, sg = idx >> 4;
-        const int s = sg / c.G, g = sg - s * c.G;
-        float v = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) v += red[((s * 8 + w) * H_GMAX + g) * 16 + col];
-        stage[(g * NS + s) * 16 + col] = val(s, g, col, v);
-    }
-    h_sync();
-    h_mark_fine(c);
-    // one task = four adjacent columns x eight destination CTAs (16-byte st.async: the DSMEM store path takes
-    // about one request per clock whatever its width; a DSMEM bulk copy costs ~1000 cycles to issue)
-    const int n_task = n_out >> 1;
+    const int n_task = NS * c.G * 4 * DS;      // (set, row, column quad, destination group)
     for (int idx = c.tid; idx < n_task; idx += H_CT) {
-        const int dh = idx & 1, q = idx >> 1;
-        const float4 o = *reinterpret_cast<const float4*>(stage + 4 * q);
+        const int dq = idx % DS, q = idx / DS;
+        const int c4 = q & 3, sg = q >> 2;
+        const int s = sg / c.G, g = sg - s * c.G;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (uint32_t d = 0; d < 8; ++d) h_send4(c, dst_off + 16 * q, 8u * (uint32_t)dh + d, o);
+        for (int w = 0; w < 8; ++w) {
+            const float4 p = *reinterpret_cast<const float4*>(red + ((s * 8 + w) * H_GMAX + g) * 16 + 4 * c4);
+            v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+        }
+        const int col = 4 * c4;
+        const float4 o = make_float4(val(s, g, col, v.x), val(s, g, col + 1, v.y), val(s, g, col + 2, v.z), val(s, g, col + 3, v.w));
+        const int byte_off = off(s, g) + 16 * c4;
+#pragma unroll
+        for (uint32_t d = 0; d < 16 / DS; ++d) h_send4(c, byte_off, (uint32_t)dq * (16 / DS) + d, o);
     }
-    h_mark_fine(c);
-    h_sync();
+    // no barrier here: the caller waits on the exchange this all-gather feeds, which cannot complete before
+    // every thread of THIS CTA has issued its stores (each CTA is one of its own destinations), i.e. before
+    // every thread is done reading `red`
 }
 // finish an exchange in which this CTA receives `bytes_in` bytes in total.  Four barriers rotate: the
 // targeted q/k/v exchanges only synchronise a head's two CTAs, so a fast CTA can run up to two
@@ -289,10 +273,10 @@ __device__ __forceinline__ void h_exchange(HCtx& c, uint32_t bytes_in) {
 }
 __device__ __forceinline__ void h_layer_norm(const HCtx& c, const float* w, const float* b) {
     if (c.warp < c.G) {
-        const float* x = reinterpret_cast<const float*>(c.sm + HSmem::xbuf);
+        const float* x = reinterpret_cast<const float*>(c.sm + HSmem::xbuf) + c.warp * 256;
         float* n = reinterpret_cast<float*>(c.sm + HSmem::nbuf) + c.warp * 256;
-        float4 v0 = *reinterpret_cast<const float4*>(x + H_XOFF(c.warp, 4 * c.lane));          // k = 4 lane .. 4 lane + 3
-        float4 v1 = *reinterpret_cast<const float4*>(x + H_XOFF(c.warp, 128 + 4 * c.lane));    // k = 128 + 4 lane ..
+        float4 v0 = reinterpret_cast<const float4*>(x)[c.lane];
+        float4 v1 = reinterpret_cast<const float4*>(x)[c.lane + 32];
         const float sum = ((v0.x + v0.y) + (v0.z + v0.w)) + ((v1.x + v1.y) + (v1.z + v1.w));
         const float mean = warp_sum(sum) * (1.0f / 256.0f);
         v0.x -= mean; v0.y -= mean; v0.z -= mean; v0.w -= mean;
@@ -320,7 +304,7 @@ __device__ __forceinline__ void h_group_sync(const HCtx& c) {
 // (already in qkvs) is appended as key index nglobal.  The context slice goes to all 16 CTAs.
 __device__ void h_attend(HCtx& c, int g, int nglobal, bool extra) {
     float* scores = reinterpret_cast<float*>(c.sm + HSmem::scores) + c.grp * 1024;
-    float* ared = reinterpret_cast<float*>(c.sm + HSmem::ared) + c.grp * 160;   // [3 warps][32] + softmax scratch at 96..
+    float* ared = reinterpret_cast<float*>(c.sm + HSmem::ared) + c.grp * 128;   // [3 warps][32] + softmax scratch at 96..
     const float* qs = reinterpret_cast<const float*>(c.sm + HSmem::qkvs) + (c.grp * 3 + 0) * 32;
     const float* ks = reinterpret_cast<const float*>(c.sm + HSmem::qkvs) + (c.grp * 3 + 1) * 32;
     const float* vs = reinterpret_cast<const float*>(c.sm + HSmem::qkvs) + (c.grp * 3 + 2) * 32;
@@ -384,14 +368,9 @@ __device__ void h_attend(HCtx& c, int g, int nglobal, bool extra) {
     c.kv_seq += (uint32_t)(2 * ntiles);
     ared[c.gwarp * 32 + c.lane] = acc;
     h_group_sync(c);
-    if (c.gwarp == 0) ared[128 + c.lane] = (ared[c.lane] + ared[32 + c.lane]) + ared[64 + c.lane];
-    h_group_sync(c);
-    // the 32-float context row goes to all 16 CTAs as 8 quads x 16 destinations, spread over the group
-    for (int task = c.gtid; task < 8 * H_CS; task += H_GT) {
-        const int q = task & 7;
-        h_send4(c, HSmem::ctxbuf + (g * 256 + c.head * 32 + 4 * q) * 4, (uint32_t)(task >> 3),
-                *reinterpret_cast<const float4*>(ared + 128 + 4 * q));
-    }
+    if (c.gwarp == 0)
+        h_bcast(c, HSmem::ctxbuf + (g * 256 + c.head * 32 + c.lane) * 4,
+                (ared[c.lane] + ared[32 + c.lane]) + ared[64 + c.lane]);
 }
 
 __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a) {
@@ -410,7 +389,6 @@ __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a)
     const int row0 = cluster * a.G;
     c.G = min(a.G, a.B - row0);
     c.tile_seq = 0; c.x_seq = 0; c.kv_seq = 0;
-    c.prof = a.prof; c.pm = 0; c.prof_on = 0; c.fine = 0;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + HSmem::misc);
     c.full = bars; c.empty = bars + H_RING; c.kvfull = bars + 2 * H_RING; c.kvempty = c.kvfull + 2 * H_NG;
     c.pbar = c.kvempty + 2 * H_NG; c.xbar = c.pbar + 2; c.stepbar = c.xbar + 4;
@@ -529,7 +507,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a)
         float* lgbuf = reinterpret_cast<float*>(sm + HSmem::lgbuf);
         const float* fp = reinterpret_cast<const float*>(sm + HSmem::finalp);
         uint32_t pseq = 0;
-#define H_MARK() h_mark(c)
+        int pm = 0;
+#define H_MARK() do { if (a.prof && t == 100 && l == 1 && blockIdx.x == 0 && c.tid == 0 && pm < 64) a.prof[pm++] = clock64(); } while (0)
         for (int t = 0;; ++t) {
             int n_alive = 0;
             for (int g = 0; g < c.G; ++g) n_alive += (s_fin[g] == 0) ? 1 : 0;
@@ -564,12 +543,11 @@ __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a)
             h_sync();
             for (int i = c.tid; i < c.G * 256; i += H_CT) {
                 const int g = i >> 8, d = i & 255;
-                xbuf[H_XOFF(g, d)] = (s_fin[g] == 0) ? a.emb[s_tok[g] * 256 + d] * 16.0f + a.pe[(size_t)s_rank[g] * 256 + d] : 0.f;
+                xbuf[i] = (s_fin[g] == 0) ? a.emb[s_tok[g] * 256 + d] * 16.0f + a.pe[(size_t)s_rank[g] * 256 + d] : 0.f;
             }
             h_sync();
 
             for (int l = 0; l < MNX_DEC_L; ++l) {
-                c.prof_on = (a.prof != nullptr) && t == 100 && l == 1 && blockIdx.x == 0 && c.tid == 0;
                 mbar_wait(&c.pbar[pseq & 1u], (pseq >> 1) & 1u);
                 const float* P = reinterpret_cast<const float*>(sm + HSmem::params + (pseq & 1u) * H_PARAM_FLOATS * 4);
                 ++pseq;
@@ -605,9 +583,9 @@ __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a)
                 {
                     float acc[1][H_GMAX];
                     h_gemm_shared_x<1>(c, ctxbuf, 256, acc);
-                    h_reduce_bcast<1>(c, acc,
-                        [&](int, int g, int col, float v) { return (v + P[HP_BO + col]) + xbuf[H_XOFF(g, c.rank * 16 + col)]; },
-                        HSmem::stage_x, HSmem::xbuf + H_XOFF(0, c.rank * 16) * 4);
+                    h_reduce_bcast<1, 4>(c, acc,
+                        [&](int, int g, int col, float v) { return (v + P[HP_BO + col]) + xbuf[g * 256 + c.rank * 16 + col]; },
+                        [&](int, int g) { return HSmem::xbuf + (g * 256 + c.rank * 16) * 4; });
                 }
                 H_MARK();   // 6: Wo gemm
                 h_exchange(c, (uint32_t)c.G * 1024u);                     // x1
@@ -633,25 +611,22 @@ __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a)
                 {
                     float acc[1][H_GMAX];
                     h_gemm_shared_x<1>(c, ctxbuf, 256, acc);
-                    h_reduce_bcast<1>(c, acc,
-                        [&](int, int g, int col, float v) { return (v + P[HP_BOC + col]) + xbuf[H_XOFF(g, c.rank * 16 + col)]; },
-                        HSmem::stage_x, HSmem::xbuf + H_XOFF(0, c.rank * 16) * 4);
+                    h_reduce_bcast<1, 4>(c, acc,
+                        [&](int, int g, int col, float v) { return (v + P[HP_BOC + col]) + xbuf[g * 256 + c.rank * 16 + col]; },
+                        [&](int, int g) { return HSmem::xbuf + (g * 256 + c.rank * 16) * 4; });
                 }
                 H_MARK();   // 12: Wo_c gemm
                 h_exchange(c, (uint32_t)c.G * 1024u);                     // x2
                 H_MARK();   // 13: x2 exchange
                 // ---------- feed forward ----------
                 h_layer_norm(c, P + HP_LNFW, P + HP_LNFB);
-                c.fine = 1;
-                h_mark_fine(c);
                 {
                     float acc[4][H_GMAX];
                     h_gemm_shared_x<4>(c, nbuf, 256, acc);
-                    h_reduce_bcast<4>(c, acc,
+                    h_reduce_bcast<4, 2>(c, acc,
                         [&](int j, int, int col, float v) { return gelu_erf(v + P[HP_B1 + j * 16 + col]); },
-                        HSmem::stage_h, HSmem::hbuf + H_HOFF(0, c.rank * 64) * 4);
+                        [&](int j, int g) { return HSmem::hbuf + (g * 1024 + c.rank * 64 + j * 16) * 4; });
                 }
-                c.fine = 0;
                 H_MARK();   // 14: LN + W1
                 h_exchange(c, (uint32_t)c.G * 4096u);                     // FFN hidden
                 H_MARK();   // 15: h exchange
@@ -664,22 +639,16 @@ __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a)
 #pragma unroll 1
                         for (int j = 0; j < 4; ++j) {
                             float xr[4][H_GMAX];
-                            {   // activations of k-chunk j from the slice-major FFN hidden buffer
-                                const int kb = 256 * j + 32 * c.warp + 8 * (c.lane >> 3) + ((c.lane >> 2) & 1);
-#pragma unroll
-                                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                                    for (int g = 0; g < H_GMAX; ++g) xr[i][g] = hbuf[H_HOFF(g, kb + 2 * i)];
-                            }
+                            h_load_x(c, hbuf, 1024, 256 * j, xr);
                             const float* tile = h_tile_acquire(c);
                             h_tile_fma(c, tile, xr, a4);
                             h_tile_release(c);
                         }
                         h_warp_reduce(c, a4, acc[0]);
                     }
-                    h_reduce_bcast<1>(c, acc,
-                        [&](int, int g, int col, float v) { return (v + P[HP_B2 + col]) + xbuf[H_XOFF(g, c.rank * 16 + col)]; },
-                        HSmem::stage_x, HSmem::xbuf + H_XOFF(0, c.rank * 16) * 4);
+                    h_reduce_bcast<1, 4>(c, acc,
+                        [&](int, int g, int col, float v) { return (v + P[HP_B2 + col]) + xbuf[g * 256 + c.rank * 16 + col]; },
+                        [&](int, int g) { return HSmem::xbuf + (g * 256 + c.rank * 16) * 4; });
                 }
                 H_MARK();   // 16: W2
                 h_exchange(c, (uint32_t)c.G * 1024u);                     // x3
@@ -690,9 +659,9 @@ __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a)
             {
                 float acc[1][H_GMAX];
                 h_gemm_shared_x<1>(c, nbuf, 256, acc);
-                h_reduce_bcast<1>(c, acc,
+                h_reduce_bcast<1, 4>(c, acc,
                     [&](int, int, int col, float v) { return v + fp[512 + c.rank * 16 + col]; },
-                    HSmem::stage_h, HSmem::lgbuf + H_XOFF(0, c.rank * 16) * 4);
+                    [&](int, int g) { return HSmem::lgbuf + (g * 256 + c.rank * 16) * 4; });
             }
             h_exchange(c, (uint32_t)c.G * 1024u);
             // ---------- log_softmax, grammar mask, argmax (identically in every CTA) ----------
@@ -703,7 +672,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) decode_mega16_kernel(MegaArgs a)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int v = i * 32 + c.lane;
-                    lg[i] = (v < a.g.vocab) ? lgbuf[H_XOFF(g, v)] : -INFINITY;
+                    lg[i] = (v < a.g.vocab) ? lgbuf[g * 256 + v] : -INFINITY;
                     m = fmaxf(m, lg[i]);
                 }
                 m = warp_max(m);
