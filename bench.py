@@ -251,8 +251,11 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
+            t0 = time.perf_counter()
             out = fn()
             gather(out)
+            if os.environ.get("MNX_BENCH_DEBUG"):
+                print(f"[debug] step wall {1e3 * (time.perf_counter() - t0):.2f} ms", file=sys.stderr)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -294,6 +297,7 @@ def run_ours(args):
         names = {1: "cross_attn", 2: "self_attn_t240", 3: "ln1_qkv", 4: "sum_ln_w1_gelu", 5: "w2_partials", 6: "pick"}
         extra["kernel_us"] = {n: 1000.0 * eng.time_kernel(k, 100) for k, n in names.items()}
         extra["mega_ms"] = eng.time_kernel(7, 2)     # the persistent cluster decode kernel alone (CUDA events)
+        extra["decode_path"] = int(eng.time_kernel(1003, 1))   # 3 = 16-CTA clusters (mega16.cu), 2 = 8-CTA clusters (mega.cu)
         # ---- ConvNeXt-B encoder (north_star's named dwconv target), same batch, separate engine ----
         try:
             eng.close()
@@ -319,7 +323,8 @@ def run_ours(args):
         total_imgs = BATCH * world * args.steps
         value = total_imgs / (ms_dev / 1000.0)
         e2e_value = total_imgs / (ms_e2e / 1000.0)
-        # dominant kernel (84 % of the step in profiles/): decode_mega_kernel, the whole greedy decode in one launch.
+        # dominant kernel (83 % of the step in profiles/r1b_summary.md): the persistent cluster decode kernel, the whole
+        # greedy decode in one launch (decode_mega16_kernel at bs = 32: seven 16-CTA clusters of <= 5 rows).
         # Algorithmic bytes per launch: per step the 22.1 MB of fp32 decoder weights once, the
         # memory-bank K/V of every row (1 769 472 B) and the self-attention cache read so far (2*6*1024 B per position).
         w_bytes = 4 * (6 * (4 * 65536 + 2 * 65536 + 2 * 262144) + 256 * 229)
@@ -349,13 +354,16 @@ def run_ours(args):
                     "h2d_bytes_per_step": BATCH * 3 * H * W * 4, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "decode_mega_kernel (persistent cluster decode: 480 steps x 6 layers, one launch)",
+            "roofline": {"kernel": ("decode_mega16_kernel" if extra.get("decode_path") == 3 else "decode_mega_kernel") +
+                                   " (persistent cluster decode: 480 steps x 6 layers, one launch)",
                          "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": 79.04e9, "peak_source": peak_src + " (sustained copy)",
+                         "frac": achieved / peaks["hbm_gbs"],
+                         "traffic": 52.08e9 if extra.get("decode_path") == 3 else 79.04e9, "peak_source": peak_src + " (sustained copy)",
                          "algorithmic_bytes_per_launch": mega_bytes, "launch_ms": extra["mega_ms"],
                          "timing": "CUDA events around 2 launches of the kernel alone on its launch stream, right after "
                                    "the timed region, same K/V buffers; traffic = dram__bytes_read+write of the ncu "
-                                   "--set full capture in profiles/ (same command, bs=32)"},
+                                   "--set full capture in profiles/ (r1b_mega16 / r1_mega, same command, bs=32); the kernel is "
+                                   "latency-bound (serial chain of ~50 cluster exchanges per step), see DESIGN.md 4.3"},
             "roofline_other": roofline_other(extra, peaks, clocks, xattn_bytes, xattn_s),
             "encoder": {"ms": extra["encoder_ms"], "tflops": enc_tflops, "peak_tflops": peaks["bf16_tflops_sustained"],
                         "frac": enc_tflops / peaks["bf16_tflops_sustained"], "flops_per_image": 94.16e9},

@@ -63,6 +63,7 @@ class Engine:
         self.max_batch, self.max_height, self.max_width = max_batch, max_height, max_width
         self.encoder_dim = encoder_dim
         self.max_beam = max_beam
+        self._host_out: Dict[int, Dict[str, torch.Tensor]] = {}
         enc_sd = checkpoint.get("encoder")
         self.encoder_kind = encoder_kind_of(enc_sd)
         offset, maxx, maxy = self.tok.grammar_rule()
@@ -220,21 +221,28 @@ class Engine:
         return {"ids": ids, "lens": lens, "logp": logp, "atom_idx": atom_idx, "n_atoms": n_atoms, "edges": edges}
 
     def predict_host(self, images: torch.Tensor):
-        """Same through host buffers: H2D of the images and D2H of every result inside the call."""
+        """Same through host buffers: H2D of the images and D2H of every result inside the call.
+        The result tensors are pinned staging buffers owned by the engine (allocating pinned memory
+        costs tens of milliseconds): they are overwritten by the next predict_host call with the
+        same batch size -- copy what must outlive it."""
         assert not images.is_cuda and images.dtype == torch.float32
         images = images.contiguous()
         B, _, H, W = images.shape
-        pin = dict(pin_memory=True)
-        ids = torch.empty((B, MAX_LEN), dtype=torch.int32, **pin)
-        lens = torch.empty((B,), dtype=torch.int32, **pin)
-        logp = torch.empty((B, MAX_LEN), dtype=torch.float32, **pin)
-        atom_idx = torch.empty((B, MAX_ATOMS), dtype=torch.int32, **pin)
-        n_atoms = torch.empty((B,), dtype=torch.int32, **pin)
-        edges = torch.empty((B, MAX_ATOMS, MAX_ATOMS), dtype=torch.uint8, **pin)
-        self._check(self.lib.mnx_predict_host(self.h, self._p(images), B, H, W, self._p(ids), self._p(lens),
-                                              self._p(logp), self._p(atom_idx), self._p(n_atoms), self._p(edges)),
+        out = self._host_out.get(B)
+        if out is None:
+            pin = dict(pin_memory=True)
+            out = {"ids": torch.empty((B, MAX_LEN), dtype=torch.int32, **pin),
+                   "lens": torch.empty((B,), dtype=torch.int32, **pin),
+                   "logp": torch.empty((B, MAX_LEN), dtype=torch.float32, **pin),
+                   "atom_idx": torch.empty((B, MAX_ATOMS), dtype=torch.int32, **pin),
+                   "n_atoms": torch.empty((B,), dtype=torch.int32, **pin),
+                   "edges": torch.empty((B, MAX_ATOMS, MAX_ATOMS), dtype=torch.uint8, **pin)}
+            self._host_out[B] = out
+        self._check(self.lib.mnx_predict_host(self.h, self._p(images), B, H, W, self._p(out["ids"]), self._p(out["lens"]),
+                                              self._p(out["logp"]), self._p(out["atom_idx"]), self._p(out["n_atoms"]),
+                                              self._p(out["edges"])),
                     "mnx_predict_host")
-        return {"ids": ids, "lens": lens, "logp": logp, "atom_idx": atom_idx, "n_atoms": n_atoms, "edges": edges}
+        return dict(out)
 
     # ------------------------------------------------------------------ introspection
     def launch_count(self) -> int:
