@@ -1,5 +1,6 @@
 """GPU: the shapes beyond the fixtures -- many rows (several clusters, partially filled last cluster,
-rows finishing at different steps => the row-rank positional-encoding rule across clusters), a
+rows finishing at different steps => the row-rank positional-encoding rule across clusters; B = 33 puts
+five rows on a 16-CTA cluster, i.e. all three attention groups of a CTA are in use), a
 non-square feature map, and the 1024x1024 high-resolution configuration (BASELINE.json configs[4])."""
 import numpy as np
 import pytest
@@ -12,7 +13,7 @@ from tests.helpers import seeded_features, seeded_images
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("B,path", [(37, "cluster"), (23, "cluster16"), (37, "graph")])
+@pytest.mark.parametrize("B,path", [(37, "cluster"), (23, "cluster16"), (33, "cluster16"), (37, "graph")])
 def test_many_rows_match_oracle(B, path, monkeypatch):
     from molnextr_b200.engine import Engine
     from oracle import restate
