@@ -48,14 +48,17 @@ struct ConvNextState {
 
 // ------------------------------------------------------------------------------------------
 // depthwise 7x7 (pad 3) + bias + LayerNorm over channels -> bf16
-// One CTA = TILE x TILE output pixels x ALL channels.  Channels are processed 64 at a time (lane = a
-// PAIR of channels, arithmetic on packed fp32x2 FFMA2): the (TILE+6)^2 x 64 input halo tile and the
-// 49 x 64 weight tile of chunk i+1 are fetched by TMA (4-D / 2-D tensor maps; out-of-bounds zero fill is
-// the conv's zero padding) while chunk i is convolved with a register sliding window along x (one
-// 8-byte shared-memory read per 7 FFMA2).  Conv outputs wait in shared memory as bf16 -- the GEMM
-// operand precision -- while their fp32 sum / sum of squares accumulate in registers; once every
-// channel of a pixel is known the warp that owns the pixel row normalises it and writes bf16 rows
-// (the fc1 GEMM's A operand).
+// One CTA = 8 x 8 output pixels x ALL channels, 4 warps; warp w owns output rows 2w and 2w+1.  Channels are
+// processed 64 at a time (lane = a PAIR of channels, arithmetic on packed fp32x2 FFMA2): the 14 x 14 x 64
+// input halo tile and the 49 x 64 weight tile of a chunk are fetched by TMA (4-D / 2-D tensor maps;
+// out-of-bounds zero fill is the conv's zero padding).  The kernel is bounded by shared-memory bytes per FMA,
+// so every input row that is read (14 x 8 bytes per lane) feeds BOTH output rows of the warp (kernel rows ky
+// and ky-1; the previous weight row stays in registers): 21 shared loads per 112 FFMA2 instead of per 56.
+// Shared memory is a single 62.5 KB stage, so three CTAs share an SM and one CTA's TMA wait is hidden behind
+// the others' arithmetic.  Conv outputs go to `out` un-normalised as bf16 -- the GEMM operand precision --
+// while their fp32 sum / sum of squares accumulate in registers; once every channel of a pixel is known the
+// thread that wrote an element re-reads it (same thread: no fence needed, L2-resident), normalises it and
+// writes it back (the fc1 GEMM's A operand).
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     unsigned long long r;
@@ -66,105 +69,133 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     return *reinterpret_cast<float2*>(&r);
 }
 
-template <int TILE, int C>
-__global__ void __launch_bounds__(TILE * 32) dwconv_ln_kernel(const __grid_constant__ CUtensorMap tmap_x,
-                                                              const __grid_constant__ CUtensorMap tmap_w, int H, int W,
-                                                              const float* __restrict__ dw_b,
-                                                              const float* __restrict__ ln_w,
-                                                              const float* __restrict__ ln_b, float eps,
-                                                              __nv_bfloat16* __restrict__ out) {
-    constexpr int IN = TILE + 6;
-    constexpr int IN_FLOATS = IN * IN * 64;
-    constexpr int W_FLOATS = 49 * 64;
+#define DW_TILE 8
+#define DW_IN (DW_TILE + 6)
+#define DW_IN_FLOATS (DW_IN * DW_IN * 64)
+#define DW_W_FLOATS (49 * 64)
+#define DW_SMEM ((DW_IN_FLOATS + DW_W_FLOATS) * 4 + 16 + 128)
+
+template <int C>
+__global__ void __launch_bounds__(128, 3) dwconv_ln_kernel(const __grid_constant__ CUtensorMap tmap_x,
+                                                           const __grid_constant__ CUtensorMap tmap_w, int H, int W,
+                                                           const float* __restrict__ dw_b,
+                                                           const float* __restrict__ ln_w,
+                                                           const float* __restrict__ ln_b, float eps,
+                                                           __nv_bfloat16* __restrict__ out) {
     constexpr int NCHUNK = C / 64;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-    float* in_buf = reinterpret_cast<float*>(sm);                                   // [2][IN][IN][64]
-    float* w_buf = in_buf + 2 * IN_FLOATS;                                          // [2][49][64]
-    __nv_bfloat16* obuf = reinterpret_cast<__nv_bfloat16*>(w_buf + 2 * W_FLOATS);   // [TILE*TILE][C]
-    uint64_t* bar = reinterpret_cast<uint64_t*>(obuf + (size_t)TILE * TILE * C);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;                    // warp = output row of the tile
-    const int tiles_x = (W + TILE - 1) / TILE;
+    extern __shared__ __align__(128) uint8_t smem_raw[];           // (no integer round trip: keeps LDS, not generic LD)
+    float* in_buf = reinterpret_cast<float*>(smem_raw);            // [14][14][64]
+    float* w_buf = in_buf + DW_IN_FLOATS;                          // [49][64]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(w_buf + DW_W_FLOATS);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tiles_x = (W + DW_TILE - 1) / DW_TILE;
     const int b = blockIdx.y;
     const int ty = blockIdx.x / tiles_x, tx = blockIdx.x % tiles_x;
-    const int y0 = ty * TILE, x0 = tx * TILE;
+    const int y0 = ty * DW_TILE, x0 = tx * DW_TILE;
+    const int yA = y0 + 2 * warp;                                  // this warp's first output row
 
     if (threadIdx.x == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
+        mbar_init(bar, 1);
         fence_barrier_init();
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_x)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w)) : "memory");
     }
     __syncthreads();
     auto issue = [&](int chunk) {
-        uint64_t* bb = &bar[chunk & 1];
-        mbar_arrive_expect_tx(bb, (IN_FLOATS + W_FLOATS) * 4);
+        mbar_arrive_expect_tx(bar, (DW_IN_FLOATS + DW_W_FLOATS) * 4);
         asm volatile(
             "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
-                smem_u32(in_buf + (chunk & 1) * IN_FLOATS)),
-            "l"(reinterpret_cast<uint64_t>(&tmap_x)), "r"(smem_u32(bb)), "r"(chunk * 64), "r"(x0 - 3), "r"(y0 - 3), "r"(b)
+                smem_u32(in_buf)),
+            "l"(reinterpret_cast<uint64_t>(&tmap_x)), "r"(smem_u32(bar)), "r"(chunk * 64), "r"(x0 - 3), "r"(y0 - 3), "r"(b)
             : "memory");
         asm volatile(
             "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-                smem_u32(w_buf + (chunk & 1) * W_FLOATS)),
-            "l"(reinterpret_cast<uint64_t>(&tmap_w)), "r"(smem_u32(bb)), "r"(chunk * 64), "r"(0)
+                smem_u32(w_buf)),
+            "l"(reinterpret_cast<uint64_t>(&tmap_w)), "r"(smem_u32(bar)), "r"(chunk * 64), "r"(0)
             : "memory");
     };
     if (threadIdx.x == 0) issue(0);
 
-    float psum[TILE], psq[TILE];   // this lane's share of each pixel's channel sum / sum of squares
+    float psum[2][DW_TILE], psq[2][DW_TILE];   // this lane's share of each pixel's channel sum / sum of squares
 #pragma unroll
-    for (int ox = 0; ox < TILE; ++ox) psum[ox] = psq[ox] = 0.f;
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int ox = 0; ox < DW_TILE; ++ox) psum[r][ox] = psq[r][ox] = 0.f;
 
+    const float2* tin = reinterpret_cast<const float2*>(in_buf);
+    const float2* tw = reinterpret_cast<const float2*>(w_buf);
 #pragma unroll 1
     for (int chunk = 0; chunk < NCHUNK; ++chunk) {
-        if (threadIdx.x == 0 && chunk + 1 < NCHUNK) issue(chunk + 1);
         const int c = chunk * 64 + 2 * lane;
         const float2 bias = *reinterpret_cast<const float2*>(dw_b + c);
-        mbar_wait(&bar[chunk & 1], (uint32_t)(chunk >> 1) & 1u);
-        const float2* tin = reinterpret_cast<const float2*>(in_buf + (chunk & 1) * IN_FLOATS);
-        const float2* tw = reinterpret_cast<const float2*>(w_buf + (chunk & 1) * W_FLOATS);
-        float2 acc[TILE];
+        mbar_wait(bar, (uint32_t)chunk & 1u);
+        float2 acc0[DW_TILE], acc1[DW_TILE];
 #pragma unroll
-        for (int ox = 0; ox < TILE; ++ox) acc[ox] = bias;
+        for (int ox = 0; ox < DW_TILE; ++ox) acc0[ox] = acc1[ox] = bias;
+        float2 wprev[7];
 #pragma unroll
-        for (int ky = 0; ky < 7; ++ky) {
-            float2 row[IN];
+        for (int ir = 0; ir < 8; ++ir) {       // input row 2*warp + ir of the halo tile: ky = ir for row A, ir - 1 for row B
+            float2 row[DW_IN];
 #pragma unroll
-            for (int ix = 0; ix < IN; ++ix) row[ix] = tin[((warp + ky) * IN + ix) * 32 + lane];
+            for (int ix = 0; ix < DW_IN; ++ix) row[ix] = tin[((2 * warp + ir) * DW_IN + ix) * 32 + lane];
+            float2 wcur[7];
+            if (ir < 7) {
+#pragma unroll
+                for (int kx = 0; kx < 7; ++kx) wcur[kx] = tw[(ir * 7 + kx) * 32 + lane];
+            }
 #pragma unroll
             for (int kx = 0; kx < 7; ++kx) {
-                const float2 wv = tw[(ky * 7 + kx) * 32 + lane];
+                if (ir < 7) {
 #pragma unroll
-                for (int ox = 0; ox < TILE; ++ox) acc[ox] = ffma2(row[ox + kx], wv, acc[ox]);
+                    for (int ox = 0; ox < DW_TILE; ++ox) acc0[ox] = ffma2(row[ox + kx], wcur[kx], acc0[ox]);
+                }
+                if (ir > 0) {
+#pragma unroll
+                    for (int ox = 0; ox < DW_TILE; ++ox) acc1[ox] = ffma2(row[ox + kx], wprev[kx], acc1[ox]);
+                }
+            }
+            if (ir < 7) {
+#pragma unroll
+                for (int kx = 0; kx < 7; ++kx) wprev[kx] = wcur[kx];
             }
         }
+        __syncthreads();   // everyone is done with the stage: refill it while the results are written out
+        if (threadIdx.x == 0 && chunk + 1 < NCHUNK) issue(chunk + 1);
 #pragma unroll
-        for (int ox = 0; ox < TILE; ++ox) {
-            psum[ox] += acc[ox].x + acc[ox].y;
-            psq[ox] = fmaf(acc[ox].x, acc[ox].x, fmaf(acc[ox].y, acc[ox].y, psq[ox]));
-            *reinterpret_cast<__nv_bfloat162*>(obuf + (size_t)(warp * TILE + ox) * C + c) = __floats2bfloat162_rn(acc[ox].x, acc[ox].y);
+        for (int ox = 0; ox < DW_TILE; ++ox) {
+            psum[0][ox] += acc0[ox].x + acc0[ox].y;
+            psq[0][ox] = fmaf(acc0[ox].x, acc0[ox].x, fmaf(acc0[ox].y, acc0[ox].y, psq[0][ox]));
+            psum[1][ox] += acc1[ox].x + acc1[ox].y;
+            psq[1][ox] = fmaf(acc1[ox].x, acc1[ox].x, fmaf(acc1[ox].y, acc1[ox].y, psq[1][ox]));
+            const int x = x0 + ox;
+            if (x < W) {
+                if (yA < H)
+                    *reinterpret_cast<__nv_bfloat162*>(out + (((size_t)b * H + yA) * W + x) * C + c) = __floats2bfloat162_rn(acc0[ox].x, acc0[ox].y);
+                if (yA + 1 < H)
+                    *reinterpret_cast<__nv_bfloat162*>(out + (((size_t)b * H + yA + 1) * W + x) * C + c) = __floats2bfloat162_rn(acc1[ox].x, acc1[ox].y);
+            }
         }
-        __syncthreads();   // everyone is done with this input / weight buffer before it is refilled (chunk + 2)
     }
-    // LayerNorm over C for each pixel of the warp's row (statistics from the unrounded fp32 conv outputs)
+    // LayerNorm over C for the warp's 16 pixels (statistics from the unrounded fp32 conv outputs); every thread
+    // re-reads exactly the elements it wrote
 #pragma unroll
-    for (int ox = 0; ox < TILE; ++ox) {
-        const float mean = warp_sum(psum[ox]) * (1.0f / (float)C);
-        const float var = fmaxf(warp_sum(psq[ox]) * (1.0f / (float)C) - mean * mean, 0.f);
-        const float rstd = 1.0f / sqrtf(var + eps);
-        const int y = y0 + warp, x = x0 + ox;
-        if (y >= H || x >= W) continue;
-        const __nv_bfloat16* v = obuf + (size_t)(warp * TILE + ox) * C;
-        __nv_bfloat16* o = out + (((size_t)b * H + y) * W + x) * C;
+    for (int r = 0; r < 2; ++r) {
 #pragma unroll
-        for (int i = lane * 2; i < C; i += 64) {
-            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(v + i));
-            const float2 g = *reinterpret_cast<const float2*>(ln_w + i);
-            const float2 be = *reinterpret_cast<const float2*>(ln_b + i);
-            *reinterpret_cast<__nv_bfloat162*>(o + i) =
-                __floats2bfloat162_rn((f.x - mean) * rstd * g.x + be.x, (f.y - mean) * rstd * g.y + be.y);
+        for (int ox = 0; ox < DW_TILE; ++ox) {
+            const float mean = warp_sum(psum[r][ox]) * (1.0f / (float)C);
+            const float var = fmaxf(warp_sum(psq[r][ox]) * (1.0f / (float)C) - mean * mean, 0.f);
+            const float rstd = 1.0f / sqrtf(var + eps);
+            const int y = yA + r, x = x0 + ox;
+            if (y >= H || x >= W) continue;
+            __nv_bfloat16* o = out + (((size_t)b * H + y) * W + x) * C;
+#pragma unroll
+            for (int i = lane * 2; i < C; i += 64) {
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(o + i));
+                const float2 g = *reinterpret_cast<const float2*>(ln_w + i);
+                const float2 be = *reinterpret_cast<const float2*>(ln_b + i);
+                *reinterpret_cast<__nv_bfloat162*>(o + i) =
+                    __floats2bfloat162_rn((f.x - mean) * rstd * g.x + be.x, (f.y - mean) * rstd * g.y + be.y);
+            }
         }
     }
 }
@@ -250,11 +281,6 @@ static int cn_bf16(mnx_engine* e, const std::string& key, std::initializer_list<
     return cn_bf16_vec(e, *v, out);
 }
 
-template <int TILE>
-static size_t dw_smem(int C) {
-    return (size_t)(2 * (TILE + 6) * (TILE + 6) * 64 + 2 * 49 * 64) * 4 + (size_t)TILE * TILE * C * 2 + 16 + 128;
-}
-
 int convnext_finalize(mnx_engine* e, ConvNextState** out, const mnx_config& cfg) {
     CN_CUDA(e, gemm_tc_configure());
     if (!g_cn_encode) {
@@ -264,10 +290,10 @@ int convnext_finalize(mnx_engine* e, ConvNextState** out, const mnx_config& cfg)
         if (qres != cudaDriverEntryPointSuccess || !fn) { mnx_set_error(e, "cuTensorMapEncodeTiled unavailable"); return MNX_ERR_CUDA; }
         g_cn_encode = reinterpret_cast<PFN_encodeTiled>(fn);
     }
-    CN_CUDA(e, cudaFuncSetAttribute(dwconv_ln_kernel<8, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem<8>(128)));
-    CN_CUDA(e, cudaFuncSetAttribute(dwconv_ln_kernel<8, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem<8>(256)));
-    CN_CUDA(e, cudaFuncSetAttribute(dwconv_ln_kernel<8, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem<8>(512)));
-    CN_CUDA(e, cudaFuncSetAttribute(dwconv_ln_kernel<4, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem<4>(1024)));
+    CN_CUDA(e, cudaFuncSetAttribute(dwconv_ln_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM));
+    CN_CUDA(e, cudaFuncSetAttribute(dwconv_ln_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM));
+    CN_CUDA(e, cudaFuncSetAttribute(dwconv_ln_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM));
+    CN_CUDA(e, cudaFuncSetAttribute(dwconv_ln_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM));
     if (cfg.max_height % 32 != 0 || cfg.max_width % 32 != 0) {
         mnx_set_error(e, "ConvNeXt-B needs image bounds that are multiples of 32");
         return MNX_ERR_INVALID;
@@ -336,14 +362,14 @@ static cudaError_t cn_gemm(const __nv_bfloat16* A, const __nv_bfloat16* W, long 
     return gemm_tc_launch(p, s);
 }
 
-template <int TILE, int C>
+template <int C>
 static int launch_dwconv_t(mnx_engine* e, const float* x, int B, int H, int W, const CnBlockW& w, __nv_bfloat16* out,
                            cudaStream_t s) {
     CUtensorMap map, wmap;
     {
         const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-        const cuuint32_t box[4] = {64, (cuuint32_t)(TILE + 6), (cuuint32_t)(TILE + 6), 1};
+        const cuuint32_t box[4] = {64, DW_IN, DW_IN, 1};
         const cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = g_cn_encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -360,18 +386,18 @@ static int launch_dwconv_t(mnx_engine* e, const float* x, int B, int H, int W, c
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { mnx_set_error(e, "cuTensorMapEncodeTiled failed for the dwconv weights"); return MNX_ERR_CUDA; }
     }
-    const int tiles = ((H + TILE - 1) / TILE) * ((W + TILE - 1) / TILE);
-    dwconv_ln_kernel<TILE, C><<<dim3(tiles, B), TILE * 32, dw_smem<TILE>(C), s>>>(map, wmap, H, W, w.dw_b, w.ln_w, w.ln_b, 1e-6f, out);
+    const int tiles = ((H + DW_TILE - 1) / DW_TILE) * ((W + DW_TILE - 1) / DW_TILE);
+    dwconv_ln_kernel<C><<<dim3(tiles, B), 128, DW_SMEM, s>>>(map, wmap, H, W, w.dw_b, w.ln_w, w.ln_b, 1e-6f, out);
     CN_CUDA(e, cudaGetLastError());
     return MNX_OK;
 }
 static int launch_dwconv(mnx_engine* e, const float* x, int B, int H, int W, int C, const CnBlockW& w, __nv_bfloat16* out,
                          cudaStream_t s) {
     switch (C) {
-        case 128: return launch_dwconv_t<8, 128>(e, x, B, H, W, w, out, s);
-        case 256: return launch_dwconv_t<8, 256>(e, x, B, H, W, w, out, s);
-        case 512: return launch_dwconv_t<8, 512>(e, x, B, H, W, w, out, s);
-        default: return launch_dwconv_t<4, 1024>(e, x, B, H, W, w, out, s);
+        case 128: return launch_dwconv_t<128>(e, x, B, H, W, w, out, s);
+        case 256: return launch_dwconv_t<256>(e, x, B, H, W, w, out, s);
+        case 512: return launch_dwconv_t<512>(e, x, B, H, W, w, out, s);
+        default: return launch_dwconv_t<1024>(e, x, B, H, W, w, out, s);
     }
 }
 
