@@ -311,6 +311,7 @@ __device__ void h_attend(HCtx& c, int g, int nglobal, bool extra) {
     const int nkeys = nglobal + (extra ? 1 : 0);
     const int ntiles = (nkeys + H_TK - 1) / H_TK;
     float acc = 0.f;
+    float mloc = -INFINITY;      // running maximum of the scores this thread computed (saves a pass and a barrier)
     for (int i = 0; i < 2 * ntiles; ++i) {
         const uint32_t seq = c.kv_seq + (uint32_t)i, slot = seq & 1u;
         mbar_wait(&c.kvfull[c.grp * 2 + slot], (seq >> 1) & 1u);
@@ -334,16 +335,14 @@ __device__ void h_attend(HCtx& c, int g, int nglobal, bool extra) {
                     s = fmaf(qv.z, kv.z, s); s = fmaf(qv.w, kv.w, s);
                 }
                 scores[tile * H_TK + j] = s;
+                mloc = fmaxf(mloc, s);
             }
         } else {
             if (i == ntiles) {
                 // softmax over all keys by the whole group: p = exp(s - max) / sum (fp32, as onmt MultiHeadedAttention)
-                h_group_sync(c);
-                float m = -INFINITY;
-                for (int j = c.gtid; j < nkeys; j += H_GT) m = fmaxf(m, scores[j]);
-                m = warp_max(m);
+                float m = warp_max(mloc);
                 if (c.lane == 0) ared[96 + c.gwarp] = m;
-                h_group_sync(c);
+                h_group_sync(c);                       // also: every score is in shared memory
                 m = fmaxf(fmaxf(ared[96], ared[97]), ared[98]);
                 float sum = 0.f;
                 for (int j = c.gtid; j < nkeys; j += H_GT) {

@@ -98,3 +98,23 @@ def test_greedy_bs256_shard_prefix_invariance_and_grammar():
         off = ~np.eye(k, dtype=bool)
         assert (e[off] == sw[off]).all()
     eng.close()
+
+
+def test_highres_bs8_1024_prefix_invariance():
+    """configs[4]: bs = 8 at 1024 x 1024 (S = 1024 memory positions, Swin windows padded at every stage)."""
+    from molnextr_b200.engine import Engine
+    from tests.helpers import seeded_images
+    ck = synth.synthetic_checkpoint(0, "sensitised")
+    eng = Engine(ck, max_batch=8, max_height=1024, max_width=1024)
+    x = seeded_images(9, 8, 1024, 1024).cuda()
+    eng.predict(x)
+    big, dt = _timed(lambda: eng.predict(x))
+    print(f"bs=8 1024x1024: {dt * 1e3:.1f} ms, {eng.last_decode_steps()} steps, {8 / dt:.1f} img/s")
+    small = eng.predict(x[:2])
+    torch.cuda.synchronize()
+    for k in ("ids", "lens", "n_atoms", "atom_idx"):
+        assert torch.equal(big[k][:2], small[k]), k
+    ids, lens = big["ids"].cpu().numpy(), big["lens"].cpu().numpy()
+    for i in range(8):
+        _check_grammar(ids[i], int(lens[i]))
+    eng.close()
