@@ -7,3 +7,4 @@ timeout 1500 python -m pytest tests -q -m gpu --deselect tests/test_gpu_beam.py 
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee gpurun_out/smoke.log
 timeout 600 python bench.py --steps 5 --warmup 3 2> gpurun_out/bench.err | tee gpurun_out/bench.json | cut -c1-400
 tail -3 gpurun_out/bench.err
+timeout 600 python bench.py --impl reference --steps 2 --warmup 3 2>> gpurun_out/bench.err | tee gpurun_out/bench_ref.json | cut -c1-300
