@@ -297,7 +297,8 @@ def run_ours(args):
         names = {1: "cross_attn", 2: "self_attn_t240", 3: "ln1_qkv", 4: "sum_ln_w1_gelu", 5: "w2_partials", 6: "pick"}
         extra["kernel_us"] = {n: 1000.0 * eng.time_kernel(k, 100) for k, n in names.items()}
         extra["mega_ms"] = eng.time_kernel(7, 2)     # the persistent cluster decode kernel alone (CUDA events)
-        extra["decode_path"] = int(eng.time_kernel(1003, 1))   # 3 = 16-CTA clusters (mega16.cu), 2 = 8-CTA clusters (mega.cu)
+        # 3 = 16-CTA clusters, 3 x 3-warp groups (mega16.cu); 5 = 16-CTA clusters, 2 x 4-warp groups (mega16s.cu); 2 = 8-CTA clusters
+        extra["decode_path"] = int(eng.time_kernel(1003, 1))
         # ---- ConvNeXt-B encoder (north_star's named dwconv target), same batch, separate engine ----
         try:
             eng.close()
@@ -354,11 +355,11 @@ def run_ours(args):
                     "h2d_bytes_per_step": BATCH * 3 * H * W * 4, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": ("decode_mega16_kernel" if extra.get("decode_path") == 3 else "decode_mega_kernel") +
+            "roofline": {"kernel": {3: "decode_mega16_kernel", 5: "decode_mega16s_kernel"}.get(extra.get("decode_path"), "decode_mega_kernel") +
                                    " (persistent cluster decode: 480 steps x 6 layers, one launch)",
                          "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"],
-                         "traffic": 52.08e9 if extra.get("decode_path") == 3 else 79.04e9, "peak_source": peak_src + " (sustained copy)",
+                         "traffic": 52.08e9 if extra.get("decode_path") in (3, 5) else 79.04e9, "peak_source": peak_src + " (sustained copy)",
                          "algorithmic_bytes_per_launch": mega_bytes, "launch_ms": extra["mega_ms"],
                          "timing": "CUDA events around 2 launches of the kernel alone on its launch stream, right after "
                                    "the timed region, same K/V buffers; traffic = dram__bytes_read+write of the ncu "

@@ -73,7 +73,7 @@ struct mnx_engine {
     float *logp = nullptr, *hidden = nullptr;
     // persistent cluster decode kernel (mega.cu)
     const float *wpack = nullptr, *ppack = nullptr, *finalp = nullptr, *wpack16 = nullptr, *ppack16 = nullptr;
-    int max_clusters16 = 0;
+    int max_clusters16 = 0, max_clusters16s = 0;
     unsigned int* row_state = nullptr;
     int* steps_run_dev = nullptr;
     long long* prof_dev = nullptr;
@@ -199,6 +199,7 @@ extern "C" int mnx_create(const mnx_config* cfg, mnx_engine** out) {
     if (c == cudaSuccess) c = dec_configure();
     if (c == cudaSuccess) c = mega_configure(&e->max_clusters);
     if (c == cudaSuccess) c = mega16_configure(&e->max_clusters16);
+    if (c == cudaSuccess) c = mega16s_configure(&e->max_clusters16s);
     if (const char* env = getenv("MNX_DECODE_PATH")) {
         if (!strcmp(env, "graph")) e->decode_path = 1;
         else if (!strcmp(env, "cluster")) e->decode_path = 2;
@@ -574,15 +575,18 @@ static int decode_internal(mnx_engine* e, const float* features, int B, int S, c
     // persistent cluster kernels when every cluster (<= 4 rows each) can be co-resident: prefer 16-CTA clusters
     // (half the per-SM byte stream), then 8-CTA clusters, else the multi-kernel graph path
     const int usable16 = e->max_clusters16 < 8 ? e->max_clusters16 : 8;
+    const int usable16s = e->max_clusters16s < 8 ? e->max_clusters16s : 8;
     const int usable8 = e->max_clusters < 16 ? e->max_clusters : 16;
-    const bool fits16 = usable16 > 0 && B <= usable16 * MG16_GMAX_H;
+    const bool fits16s = usable16s > 0 && B <= usable16s * MG16S_GMAX_H;   // small-batch configuration (4-warp groups)
+    const bool fits16 = fits16s || (usable16 > 0 && B <= usable16 * MG16_GMAX_H);
     const bool fits8 = usable8 > 0 && B <= usable8 * MG_GMAX_H;
     if (e->decode_path == 3 && !fits16) return fail(e, MNX_ERR_CAPACITY, "16-CTA cluster path forced but %d rows do not fit %d clusters", B, usable16);
     if (e->decode_path == 2 && !fits8) return fail(e, MNX_ERR_CAPACITY, "8-CTA cluster path forced but %d rows do not fit %d clusters", B, usable8);
     const bool use16 = (e->decode_path == 3) || (e->decode_path == 0 && fits16);
     const bool use8 = !use16 && ((e->decode_path == 2) || (e->decode_path == 0 && fits8));
+    const bool use16s = use16 && fits16s;
     if (use16 || use8) {
-        const int usable = use16 ? usable16 : usable8;
+        const int usable = use16s ? usable16s : use16 ? usable16 : usable8;
         const int G = (B + usable - 1) / usable;
         const int clusters = (B + G - 1) / G;
         CUDA_TRY(e, cudaMemsetAsync(e->row_state, 0, sizeof(unsigned) * B, s));
@@ -595,9 +599,9 @@ static int decode_internal(mnx_engine* e, const float* features, int B, int S, c
         a.ids = e->ids; a.logp = e->logp; a.hidden = e->hidden; a.lens = e->lens;
         a.row_state = e->row_state; a.steps_run = e->steps_run_dev; a.g = e->g;
         a.prof = getenv("MNX_DECODE_PROFILE") ? e->prof_dev : nullptr;
-        CUDA_TRY(e, use16 ? mega16_launch(a, clusters, s) : mega_launch(a, clusters, s));
+        CUDA_TRY(e, use16s ? mega16s_launch(a, clusters, s) : use16 ? mega16_launch(a, clusters, s) : mega_launch(a, clusters, s));
         e->launches += 1;
-        e->last_path = use16 ? 3 : 2;
+        e->last_path = use16s ? 5 : use16 ? 3 : 2;
         int steps = 0;
         CUDA_TRY(e, cudaMemcpyAsync(&steps, e->steps_run_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(e, cudaStreamSynchronize(s));
@@ -821,9 +825,10 @@ extern "C" int mnx_time_kernel(mnx_engine* e, int32_t which, int32_t iters, floa
     if (which >= 100) return encoder_time_kernel(e, e->enc, which, iters, ms, s);
     if (e->last_B == 0) return fail(e, MNX_ERR_INVALID, "run a decode first: timing uses its shapes and caches");
     if (which == 7) {   // the persistent cluster decode kernel alone, on the K/V of the last call
-        if (e->last_path != 2 && e->last_path != 3) return fail(e, MNX_ERR_INVALID, "last decode did not use a cluster kernel");
-        const bool use16 = e->last_path == 3;
-        const int usable = use16 ? (e->max_clusters16 < 8 ? e->max_clusters16 : 8) : (e->max_clusters < 16 ? e->max_clusters : 16);
+        if (e->last_path != 2 && e->last_path != 3 && e->last_path != 5) return fail(e, MNX_ERR_INVALID, "last decode did not use a cluster kernel");
+        const bool use16 = e->last_path == 3, use16s = e->last_path == 5;
+        const int usable = use16s ? (e->max_clusters16s < 8 ? e->max_clusters16s : 8)
+                                  : use16 ? (e->max_clusters16 < 8 ? e->max_clusters16 : 8) : (e->max_clusters < 16 ? e->max_clusters : 16);
         const int B = e->last_B, S = e->last_S, T = e->cfg.max_len;
         const int G = (B + usable - 1) / usable, clusters = (B + G - 1) / G;
         MegaArgs a{};
@@ -840,7 +845,7 @@ extern "C" int mnx_time_kernel(mnx_engine* e, int32_t which, int32_t iters, floa
             CUDA_TRY(e, cudaMemsetAsync(e->row_state, 0, sizeof(unsigned) * B, s));
             CUDA_TRY(e, cudaMemsetAsync(e->steps_run_dev, 0, sizeof(int), s));
             cudaEventRecord(e0, s);
-            CUDA_TRY(e, use16 ? mega16_launch(a, clusters, s) : mega_launch(a, clusters, s));
+            CUDA_TRY(e, use16s ? mega16s_launch(a, clusters, s) : use16 ? mega16_launch(a, clusters, s) : mega_launch(a, clusters, s));
             cudaEventRecord(e1, s);
             CUDA_TRY(e, cudaStreamSynchronize(s));
             float t = 0.f;

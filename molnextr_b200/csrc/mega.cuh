@@ -9,6 +9,7 @@ namespace mnx {
 #define MG_PARAM_FLOATS_H 1920
 #define MG_GMAX_H 4      // rows per 8-CTA cluster (mega.cu)
 #define MG16_GMAX_H 5    // rows per 16-CTA cluster (mega16.cu)
+#define MG16S_GMAX_H 4   // rows per 16-CTA cluster, small-batch configuration (mega16s.cu)
 
 struct MegaArgs {
     const float* wpack;
@@ -37,5 +38,7 @@ cudaError_t mega_configure(int* max_clusters);
 cudaError_t mega_launch(const MegaArgs& a, int clusters, cudaStream_t s);
 cudaError_t mega16_configure(int* max_clusters);
 cudaError_t mega16_launch(const MegaArgs& a, int clusters, cudaStream_t s);
+cudaError_t mega16s_configure(int* max_clusters);     // <= 28 rows: two 4-warp attention groups, G <= 4 (mega16s.cu)
+cudaError_t mega16s_launch(const MegaArgs& a, int clusters, cudaStream_t s);
 
 }  // namespace mnx
