@@ -359,11 +359,11 @@ def run_ours(args):
                                    " (persistent cluster decode: 480 steps x 6 layers, one launch)",
                          "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"],
-                         "traffic": 52.08e9 if extra.get("decode_path") in (3, 5) else 79.04e9, "peak_source": peak_src + " (sustained copy)",
+                         "traffic": 52.46e9 if extra.get("decode_path") in (3, 5) else 79.04e9, "peak_source": peak_src + " (sustained copy)",
                          "algorithmic_bytes_per_launch": mega_bytes, "launch_ms": extra["mega_ms"],
                          "timing": "CUDA events around 2 launches of the kernel alone on its launch stream, right after "
                                    "the timed region, same K/V buffers; traffic = dram__bytes_read+write of the ncu "
-                                   "--set full capture in profiles/ (r1b_mega16 / r1_mega, same command, bs=32); the kernel is "
+                                   "--set full capture in profiles/ (r1c_mega16 / r1_mega, same command, bs=32); the kernel is "
                                    "latency-bound (serial chain of ~50 cluster exchanges per step), see DESIGN.md 4.3"},
             "roofline_other": roofline_other(extra, peaks, clocks, xattn_bytes, xattn_s),
             "encoder": {"ms": extra["encoder_ms"], "tflops": enc_tflops, "peak_tflops": peaks["bf16_tflops_sustained"],
