@@ -324,7 +324,7 @@ def run_ours(args):
         total_imgs = BATCH * world * args.steps
         value = total_imgs / (ms_dev / 1000.0)
         e2e_value = total_imgs / (ms_e2e / 1000.0)
-        # dominant kernel (83 % of the step in profiles/r1b_summary.md): the persistent cluster decode kernel, the whole
+        # dominant kernel (83 % of the step in profiles/r1c_summary.md): the persistent cluster decode kernel, the whole
         # greedy decode in one launch (decode_mega16_kernel at bs = 32: seven 16-CTA clusters of <= 5 rows).
         # Algorithmic bytes per launch: per step the 22.1 MB of fp32 decoder weights once, the
         # memory-bank K/V of every row (1 769 472 B) and the self-attention cache read so far (2*6*1024 B per position).
