@@ -14,6 +14,8 @@
  *        <- molnextr.__init__/_get_model + loading()          MolNexTR/model.py:40-48,83-95,17-28
  *           (state-dict keys are the reference's own; unlike `strict=False` there, a
  *            missing or unexpected key is an error here)
+ *   mnx_preprocess        <- get_transforms(...)(image=...) + CropWhite
+ *                            MolNexTR/dataset.py:158-185, MolNexTR/data_aug.py:98-143, MolNexTR/model.py:104
  *   mnx_encode            <- Encoder.forward                  MolNexTR/components.py:162-174
  *                            (Swin-B: MolNexTR/models/transformers.py:504-515;
  *                             ConvNeXt-B: timm forward_features, components.py:121-126)
@@ -87,6 +89,20 @@ const char* mnx_last_error(const mnx_engine* e);
 int mnx_load_tensor(mnx_engine* e, const char* name, const void* host_data,
                     const int64_t* shape, int32_t ndim, int32_t is_int64);
 int mnx_finalize_weights(mnx_engine* e);
+
+/* upstream of the hot path ------------------------------ */
+/* The reference's inference transform on the device, bit-exact with its OpenCV 8-bit code paths:
+ * CropWhite(pad) -> Resize(out_size, out_size, INTER_LINEAR) -> ToGray -> Normalize -> CHW fp32
+ * (MolNexTR/dataset.py:158-185 get_transforms, MolNexTR/data_aug.py:98-143 CropWhite, applied per
+ * image at MolNexTR/model.py:104).
+ * rgb        device uint8: B packed HxWx3 RGB images, image i at byte offset offsets[i]
+ * offsets / heights / widths   HOST arrays of length B
+ * mean255, inv_std255          HOST float[3]: mean*255 and 1/(std*255) exactly as the caller's numpy
+ *                              float32 arithmetic produced them (the kernel does (g - m) * d in fp32)
+ * images     device fp32 (B, 3, out_size, out_size): the tensor mnx_encode / mnx_predict take */
+int mnx_preprocess(mnx_engine* e, const uint8_t* rgb, const int64_t* offsets, const int32_t* heights,
+                   const int32_t* widths, int32_t B, int32_t pad, int32_t out_size, const float* mean255,
+                   const float* inv_std255, float* images, void* cuda_stream);
 
 /* hot path --------------------------------------------------------------------------- */
 /* images: device fp32 NCHW (B,3,H,W), already normalised.  features: device fp32

@@ -35,6 +35,9 @@ cudaError_t dec_edges(const float* hidden, const int* atom_idx, const int* n_ato
                       cudaStream_t s, int* launches);
 cudaError_t dec_time_kernel(int which, int iters, const DecBuffers& b, const DecWeights& w, const Grammar& g,
                             int step, float* ms, cudaStream_t s);
+// preprocess.cu
+cudaError_t pp_run(const uint8_t* rgb, const unsigned long long* offsets, const int* hs, const int* ws, int n, int pad, int S,
+                   const float* mean255, const float* inv_std255, int* bbox, float* out, cudaStream_t s, int* launches);
 }  // namespace mnx
 
 using namespace mnx;
@@ -86,6 +89,7 @@ struct mnx_engine {
     float* images = nullptr;
     int *atom_idx = nullptr, *n_atoms = nullptr;
     uint8_t* edges = nullptr;
+    int* pp_bbox = nullptr;   // [max_batch][4] crop boxes of mnx_preprocess
     // graph of STEPS_PER_GRAPH decode steps for one (B, S)
     cudaGraphExec_t graph = nullptr;
     int graph_B = -1, graph_S = -1, graph_nodes = 0;
@@ -496,6 +500,7 @@ static int alloc_workspaces(mnx_engine* e) {
     CUDA_TRY(e, dev_alloc(e, &e->atom_idx, B * KA));
     CUDA_TRY(e, dev_alloc(e, &e->n_atoms, B));
     CUDA_TRY(e, dev_alloc(e, &e->edges, B * KA * KA));
+    CUDA_TRY(e, dev_alloc(e, &e->pp_bbox, B * 4));
     if (e->cfg.encoder_kind != MNX_ENCODER_NONE)
         CUDA_TRY(e, dev_alloc(e, &e->images, B * 3 * (size_t)e->cfg.max_height * e->cfg.max_width));
     void* cls = nullptr;
@@ -751,6 +756,27 @@ extern "C" int mnx_encode(mnx_engine* e, const float* images, int32_t B, int32_t
     int rc = encoder_forward(e, e->enc, images, B, H, W, features, (cudaStream_t)cuda_stream, &nl);
     e->launches += nl;
     return rc;
+}
+
+extern "C" int mnx_preprocess(mnx_engine* e, const uint8_t* rgb, const int64_t* offsets, const int32_t* heights,
+                              const int32_t* widths, int32_t B, int32_t pad, int32_t out_size, const float* mean255,
+                              const float* inv_std255, float* images, void* cuda_stream) {
+    if (!e || !rgb || !offsets || !heights || !widths || !mean255 || !inv_std255 || !images)
+        return fail(e, MNX_ERR_INVALID, "mnx_preprocess: null argument");
+    if (!e->finalized) return fail(e, MNX_ERR_INVALID, "weights not finalized");
+    if (B < 1 || B > e->cfg.max_batch) return fail(e, MNX_ERR_CAPACITY, "batch %d exceeds max_batch %d", B, e->cfg.max_batch);
+    if (pad < 0 || out_size < 1) return fail(e, MNX_ERR_INVALID, "mnx_preprocess: bad pad / out_size");
+    std::vector<unsigned long long> off(B);
+    for (int i = 0; i < B; ++i) {
+        if (heights[i] < 1 || widths[i] < 1 || offsets[i] < 0) return fail(e, MNX_ERR_INVALID, "image %d has a bad size or offset", i);
+        off[i] = (unsigned long long)offsets[i];
+    }
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    int nl = 0;
+    CUDA_TRY(e, pp_run(rgb, off.data(), heights, widths, B, pad, out_size, mean255, inv_std255, e->pp_bbox, images,
+                       (cudaStream_t)cuda_stream, &nl));
+    e->launches += nl;
+    return MNX_OK;
 }
 
 extern "C" int mnx_predict(mnx_engine* e, const float* images, int32_t B, int32_t H, int32_t W, int32_t* ids,

@@ -121,6 +121,33 @@ class Engine:
     def _p(t: Optional[torch.Tensor]) -> C.c_void_p:
         return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
+    # ------------------------------------------------------------------ upstream: preprocessing on the device
+    def preprocess(self, images, size: int = 384, pad: int = 50) -> torch.Tensor:
+        """The reference's inference transform (dataset.py:158-185 + data_aug.CropWhite) for a list of RGB
+        uint8 HxWx3 arrays of any size -> cuda fp32 (B, 3, size, size), bit-exact with the cv2 path in
+        molnextr_b200/preprocess.py.  One pinned packed upload of the raw bytes, three kernels."""
+        from .preprocess import MEAN, STD
+        B = len(images)
+        hs = np.array([im.shape[0] for im in images], np.int32)
+        ws = np.array([im.shape[1] for im in images], np.int32)
+        sizes = hs.astype(np.int64) * ws.astype(np.int64) * 3
+        offsets = np.zeros(B, np.int64)
+        offsets[1:] = np.cumsum((sizes[:-1] + 15) // 16 * 16)
+        total = int(offsets[-1] + sizes[-1])
+        packed = torch.empty((total,), dtype=torch.uint8, pin_memory=True)
+        pk = packed.numpy()
+        for im, o, n in zip(images, offsets, sizes):
+            assert im.dtype == np.uint8 and im.ndim == 3 and im.shape[2] == 3
+            pk[o:o + n] = np.ascontiguousarray(im).reshape(-1)
+        dev = packed.to(self.device, non_blocking=True)
+        mean255 = (MEAN * 255.0).astype(np.float32)
+        inv = (1.0 / (STD * 255.0)).astype(np.float32)
+        out = torch.empty((B, 3, size, size), device=self.device, dtype=torch.float32)
+        self._check(self.lib.mnx_preprocess(self.h, self._p(dev), C.c_void_p(offsets.ctypes.data), C.c_void_p(hs.ctypes.data),
+                                            C.c_void_p(ws.ctypes.data), B, pad, size, C.c_void_p(mean255.ctypes.data),
+                                            C.c_void_p(inv.ctypes.data), self._p(out), self._stream()), "mnx_preprocess")
+        return out
+
     # ------------------------------------------------------------------ hot path
     def seq_len(self, H: int, W: int) -> int:
         if self.encoder_kind == _cabi.ENCODER_SWIN_B:

@@ -72,7 +72,8 @@ class molnextr:
         # its rank inside its mini-batch, so chunks of `batch_size` are kept as is
         for idx in range(0, len(input_images), batch_size):
             batch = input_images[idx:idx + batch_size]
-            images = torch.stack([self.transform(image=im)["image"] for im in batch], dim=0).to(self.device)
+            # CropWhite -> Resize -> ToGray -> Normalize on the device (bit-exact with self.transform, the cv2 path)
+            images = self.engine.preprocess([np.ascontiguousarray(im) for im in batch], size=self.input_size)
             features, hiddens = self.encoder(images)
             predictions += self.decoder.decode(features, hiddens)
         node_coords = [p["chartok_coords"]["coords"] for p in predictions]
