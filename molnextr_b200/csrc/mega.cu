@@ -150,8 +150,11 @@ __device__ __forceinline__ void tile_fma(const MegaCtx& c, const float* tile, co
     }
 }
 // cross-warp reduction of the 8 k-splits of NS accumulator sets at once, then f(set, row, value) is
-// called by one warp per (set, row) pair with lane = output column.  Two compute_syncs.
-template <int NS, class F>
+// called by one warp per (set, row) pair with lane = output column.  Two compute_syncs; the trailing one is
+// dropped (TAIL_SYNC = false) when f broadcasts into every CTA and the caller waits on that exchange next:
+// the exchange cannot complete before every thread of THIS CTA has issued its stores (each CTA is one of
+// its own destinations), i.e. before everybody is done reading `red`.
+template <int NS, bool TAIL_SYNC = true, class F>
 __device__ __forceinline__ void reduce_apply(const MegaCtx& c, const float (&acc)[NS][MG_GMAX], F f) {
     float* red = reinterpret_cast<float*>(c.sm + MegaSmem::red);
 #pragma unroll
@@ -167,7 +170,7 @@ __device__ __forceinline__ void reduce_apply(const MegaCtx& c, const float (&acc
         for (int w = 0; w < 8; ++w) v += red[((s * 8 + w) * MG_GMAX + g) * 32 + c.lane];
         f(s, g, v);
     }
-    compute_sync();
+    if (TAIL_SYNC) compute_sync();
 }
 
 // write one float into the same shared-memory location of all 8 CTAs of the cluster.  The store is
@@ -258,6 +261,7 @@ __device__ void attend_run(MegaCtx& c, int g, const float* Kb, const float* Vb, 
     const int nkeys = nglobal + (extra ? 1 : 0);
     const int ntiles = (nkeys + MG_TK - 1) / MG_TK;
     float acc = 0.f;
+    float mloc = -INFINITY;      // running maximum of this thread's scores (saves a pass; measured on mega16)
     for (int i = 0; i < 2 * ntiles; ++i) {
         const uint32_t seq = c.kv_seq + (uint32_t)i;
         mbar_wait(&c.kvbar[c.grp * 2 + (seq & 1u)], (seq >> 1) & 1u);
@@ -281,15 +285,18 @@ __device__ void attend_run(MegaCtx& c, int g, const float* Kb, const float* Vb, 
                     s = fmaf(qv.z, kv.z, s); s = fmaf(qv.w, kv.w, s);
                 }
                 scores[tile * MG_TK + j] = s;
+                mloc = fmaxf(mloc, s);
             }
         } else {
             if (i == ntiles) {
                 // softmax over all keys by the group's first warp (shuffles only), p = exp(s - max) / sum
-                group_sync(c);
+                {   // group maximum: the two warps exchange their maxima through the scratch row
+                    const float wm = warp_max(mloc);
+                    if (c.lane == 0) ared[c.gwarp] = wm;
+                }
+                group_sync(c);                         // also: every score is in shared memory
                 if (c.gwarp == 0) {
-                    float m = -INFINITY;
-                    for (int j = c.lane; j < nkeys; j += 32) m = fmaxf(m, scores[j]);
-                    m = warp_max(m);
+                    const float m = fmaxf(ared[0], ared[1]);
                     float sum = 0.f;
                     for (int j = c.lane; j < nkeys; j += 32) {
                         const float e = expf(scores[j] - m);
@@ -499,7 +506,7 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(MG_THREADS, 1) decod
                     const float* tile = tile_acquire(c);
                     tile_fma(c, tile, ctxbuf, 256, 0, acc[0]);
                     tile_release(c);
-                    reduce_apply<1>(c, acc, [&](int, int g, float v) {
+                    reduce_apply<1, false>(c, acc, [&](int, int g, float v) {
                         const int col = c.h * 32 + c.lane;
                         bcast_store(c, MegaSmem::xbuf + (g * 256 + col) * 4, (v + P[P_BO + c.lane]) + xbuf[g * 256 + col]);
                     });
@@ -527,7 +534,7 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(MG_THREADS, 1) decod
                     const float* tile = tile_acquire(c);
                     tile_fma(c, tile, ctxbuf, 256, 0, acc[0]);
                     tile_release(c);
-                    reduce_apply<1>(c, acc, [&](int, int g, float v) {
+                    reduce_apply<1, false>(c, acc, [&](int, int g, float v) {
                         const int col = c.h * 32 + c.lane;
                         bcast_store(c, MegaSmem::xbuf + (g * 256 + col) * 4, (v + P[P_BOC + c.lane]) + xbuf[g * 256 + col]);
                     });
@@ -545,7 +552,7 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(MG_THREADS, 1) decod
                         tile_fma(c, tile, nbuf, 256, 0, acc[j]);
                         tile_release(c);
                     }
-                    reduce_apply<4>(c, acc, [&](int j, int g, float v) {
+                    reduce_apply<4, false>(c, acc, [&](int j, int g, float v) {
                         bcast_store(c, MegaSmem::hbuf + (g * 1024 + c.h * 128 + j * 32 + c.lane) * 4,
                                     gelu_erf(v + P[P_B1 + j * 32 + c.lane]));
                     });
@@ -561,7 +568,7 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(MG_THREADS, 1) decod
                         tile_fma(c, tile, hbuf, 1024, 256 * j, acc[0]);
                         tile_release(c);
                     }
-                    reduce_apply<1>(c, acc, [&](int, int g, float v) {
+                    reduce_apply<1, false>(c, acc, [&](int, int g, float v) {
                         const int col = c.h * 32 + c.lane;
                         bcast_store(c, MegaSmem::xbuf + (g * 256 + col) * 4, (v + P[P_B2 + c.lane]) + xbuf[g * 256 + col]);
                     });
@@ -578,7 +585,7 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(MG_THREADS, 1) decod
                 const float* tile = tile_acquire(c);
                 tile_fma(c, tile, nbuf, 256, 0, acc[0]);
                 tile_release(c);
-                reduce_apply<1>(c, acc, [&](int, int g, float v) {
+                reduce_apply<1, false>(c, acc, [&](int, int g, float v) {
                     bcast_store(c, MegaSmem::lgbuf + (g * 256 + c.h * 32 + c.lane) * 4, v + fp[512 + c.h * 32 + c.lane]);
                 });
             }
