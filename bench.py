@@ -9,9 +9,11 @@ One "step" = one pass of the hot path over one batch of 32 synthetic 384x384 ima
 seeded synthetic checkpoint, <eos> suppressed so every row runs the full 480 decode steps
 (fixed work).  Prints ONE JSON line (rank 0).
 
-  value : images/s with the batch already resident in HBM (Engine.predict), device-timed
-  e2e   : images/s through the host-buffer C-ABI call (mnx_predict_host): H2D of the images and
-          D2H of every result inside the timed region
+  value : images/s with the batches already resident in HBM, device-timed over K consecutive batches
+          through Engine.predict_pipelined (2-deep: the encoder of batch i+1 overlaps the persistent
+          decode kernel of batch i); `latency` holds the batch-by-batch numbers (Engine.predict)
+  e2e   : the same from pinned HOST buffers: H2D of every batch's images and D2H of every result inside
+          the timed region
   roofline     : the decoder cross-attention kernel (north_star's named HBM target), timed with
                  CUDA events on its launch stream right after the timed region, same shapes
   cpu_baseline : the CPU oracle (a port of the reference's PyTorch path) on the host cores, on a
@@ -263,19 +265,38 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    def timed_pipeline(batches, host):
+        """K consecutive batches through Engine.predict_pipelined: every step's work (encoder, decode, bond head,
+        and in host mode its H2D / D2H) is inside the timed region; steps overlap 2-deep."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for out in eng.predict_pipelined(batches, host=host):
+            gather(out)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
     # ---- device-resident arm ----
     for _ in range(args.warmup):
         gather(eng.predict(x_dev))
+    eng.predict_pipelined([x_dev] * max(2, args.warmup))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    ms_latency = timed(lambda: eng.predict(x_dev), args.steps)          # batch by batch (single-batch latency)
     l0 = eng.launch_count()
-    ms_dev = timed(lambda: eng.predict(x_dev), args.steps)
+    ms_dev = timed_pipeline([x_dev] * args.steps, host=False)
     launches = eng.launch_count() - l0
     steps_run = eng.last_decode_steps()
     # ---- host-buffer arm (H2D + D2H inside) ----
     eng.predict_host(x_host)
-    ms_e2e = timed(lambda: eng.predict_host(x_host), args.steps)
+    eng.predict_pipelined([x_host] * max(2, args.warmup), host=True)
+    ms_e2e = timed_pipeline([x_host] * args.steps, host=True)
+    ms_e2e_latency = timed(lambda: eng.predict_host(x_host), args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- phase breakdown + isolated kernel timings (rank 0, after the timed region) ----
@@ -349,10 +370,16 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "bf16 encoder GEMMs (fp32 accumulate), f32 decoder", "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_gpu_batch": BATCH, "global_batch": BATCH * world, "decode_steps": steps_run,
                        "encoder": "swin_base", "parallelism": f"dp{world}",
+                       "pipeline": "the K timed steps run through Engine.predict_pipelined: the encoder of step i+1 (second "
+                                   "stream, GEMM grids capped at 32 CTAs) overlaps the persistent decode kernel of step i, "
+                                   "which occupies 112 of the 148 SMs; batch-by-batch numbers are under `latency`",
                        "l2": "no explicit flush: one step streams 0.19 GB of bf16 encoder weights, >1 GB of "
                              "activations and a 246 MB KV cache, far above the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": BATCH * 3 * H * W * 4, "d2h_bytes_per_step": d2h},
+            "latency": {"ms_per_batch": ms_latency / args.steps, "images_per_s": total_imgs / (ms_latency / 1000.0),
+                        "ms_per_batch_host_buffers": ms_e2e_latency / args.steps,
+                        "note": "Engine.predict / predict_host batch by batch, no overlap between steps"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": {3: "decode_mega16_kernel", 5: "decode_mega16s_kernel"}.get(extra.get("decode_path"), "decode_mega_kernel") +

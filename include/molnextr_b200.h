@@ -163,6 +163,14 @@ int mnx_predict_host(mnx_engine* e, const float* images_host, int32_t B, int32_t
                      int32_t* ids_host, int32_t* lens_host, float* token_logp_host,
                      int32_t* atom_idx_host, int32_t* n_atoms_host, uint8_t* edges_host);
 
+/* pipelining across batches -------------------------------------------------------------- */
+/* For batches of <= 60 rows the decode is one persistent kernel on ~112 of the 148 SMs and
+ * mnx_decode_greedy / mnx_predict return without synchronising the host.  A caller that has the next batch
+ * ready can therefore enqueue its mnx_encode on a second (lower-priority) stream right away; this call caps
+ * the encoder GEMMs' persistent grid at n CTAs (0 = one per SM) so that they fit on the SMs the decode kernel
+ * leaves free instead of queueing behind it.  Process-wide setting.  See Engine.predict_pipelined. */
+int mnx_set_encoder_cta_limit(mnx_engine* e, int32_t n);
+
 /* introspection ------------------------------------------------------------------------ */
 /* number of kernel launches issued by this handle since creation (graph nodes counted
  * per replay); used by bench.py for `gpu_launches`. */
@@ -172,7 +180,7 @@ int64_t mnx_launch_count(const mnx_engine* e);
  * step t, -1 where image b was no longer decoded.  Synchronises the device. */
 #define MNX_MAX_BEAM 8
 int mnx_beam_trace(mnx_engine* e, int32_t* trace_host, int32_t B);
-/* steps executed by the last decode (<= max_len) */
+/* steps executed by the last decode (<= max_len); waits for it if it is still running */
 int32_t mnx_last_decode_steps(const mnx_engine* e);
 /* time one internal phase in isolation for the roofline report: fills ms with the mean
  * device time of `iters` launches of kernel `which` on the shapes of the last call

@@ -104,6 +104,7 @@ struct mnx_engine {
     int* h_done = nullptr;   // pinned
     int64_t launches = 0;
     int last_steps = 0;
+    bool steps_pending = false;   // cluster paths return without synchronising: steps are read back on demand
     int last_B = 0, last_S = 0, last_path = 0;
     EncoderState enc{};
 };
@@ -607,10 +608,10 @@ static int decode_internal(mnx_engine* e, const float* features, int B, int S, c
         CUDA_TRY(e, use16s ? mega16s_launch(a, clusters, s) : use16 ? mega16_launch(a, clusters, s) : mega_launch(a, clusters, s));
         e->launches += 1;
         e->last_path = use16s ? 5 : use16 ? 3 : 2;
-        int steps = 0;
-        CUDA_TRY(e, cudaMemcpyAsync(&steps, e->steps_run_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(e, cudaStreamSynchronize(s));
-        e->last_steps = steps;
+        // no host synchronisation: the whole decode is one kernel, so the call is asynchronous like any other
+        // launch on `s` (lets the caller overlap the next batch's encoder with it); mnx_last_decode_steps
+        // reads the step count back on demand
+        e->steps_pending = true;
         e->last_B = B; e->last_S = S;
         return MNX_OK;
     }
@@ -628,6 +629,7 @@ static int decode_internal(mnx_engine* e, const float* features, int B, int S, c
     CUDA_TRY(e, cudaMemcpyAsync(&hs, e->st, sizeof(DecState), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(e, cudaStreamSynchronize(s));
     e->last_steps = hs.steps_run;
+    e->steps_pending = false;
     e->last_B = B; e->last_S = S;
     return MNX_OK;
 }
@@ -713,6 +715,7 @@ extern "C" int mnx_decode_beam(mnx_engine* e, const float* features, int32_t B, 
     CUDA_TRY(e, cudaMemcpyAsync(&hs, e->st, sizeof(DecState), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(e, cudaStreamSynchronize(s));
     e->last_steps = hs.steps_run;
+    e->steps_pending = false;
     e->last_B = 0; e->last_S = S;   // isolated kernel timing (mnx_time_kernel) is defined on greedy shapes only
     return MNX_OK;
 }
@@ -831,7 +834,24 @@ extern "C" int mnx_beam_trace(mnx_engine* e, int32_t* trace_host, int32_t B) {
 }
 
 extern "C" int64_t mnx_launch_count(const mnx_engine* e) { return e ? e->launches : 0; }
-extern "C" int32_t mnx_last_decode_steps(const mnx_engine* e) { return e ? e->last_steps : 0; }
+extern "C" int32_t mnx_last_decode_steps(const mnx_engine* ce) {
+    mnx_engine* e = const_cast<mnx_engine*>(ce);
+    if (!e) return 0;
+    if (e->steps_pending) {      // cluster paths: wait for the decode kernel and fetch its step count
+        int steps = 0;
+        cudaSetDevice(e->cfg.device);
+        if (cudaMemcpy(&steps, e->steps_run_dev, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess) e->last_steps = steps;
+        e->steps_pending = false;
+    }
+    return e->last_steps;
+}
+
+namespace mnx { void gemm_tc_set_cta_limit(int n); }
+extern "C" int mnx_set_encoder_cta_limit(mnx_engine* e, int32_t n) {
+    if (!e || n < 0) return fail(e, MNX_ERR_INVALID, "mnx_set_encoder_cta_limit: bad argument");
+    mnx::gemm_tc_set_cta_limit(n);
+    return MNX_OK;
+}
 
 extern "C" int mnx_time_kernel(mnx_engine* e, int32_t which, int32_t iters, float* ms, void* cuda_stream) {
     if (!e || !ms || iters < 1) return fail(e, MNX_ERR_INVALID, "mnx_time_kernel: bad argument");

@@ -110,3 +110,25 @@ def test_predict_end_to_end_vs_reference_fixture(engine_cache):
             print(f"row {i}: diverges at step {t}, reference top-2 gap {gap:.4f}")
             assert gap <= LOGP_TOL, f"row {i} diverged at step {t} where the reference margin is {gap:.3f}"
     print(f"{exact_rows}/{cfg['b']} rows bit-exact end to end")
+
+
+def test_pipelined_batches_equal_batch_by_batch():
+    """Engine.predict_pipelined (encoder of batch i+1 overlapped with the persistent decode kernel of
+    batch i on two streams) must return exactly what predict returns batch by batch, device and host mode."""
+    from molnextr_b200.engine import Engine
+    ck = synth.synthetic_checkpoint(0, "sensitised")
+    eng = Engine(ck, max_batch=4)
+    xs = [seeded_images(100 + i, 4 if i != 2 else 3, 384, 384) for i in range(4)]
+    ref = [{k: v.cpu() for k, v in eng.predict(x.cuda()).items()} for x in xs]
+    got = eng.predict_pipelined([x.cuda() for x in xs])
+    torch.cuda.synchronize()
+    got_host = eng.predict_pipelined([x.pin_memory() for x in xs], host=True)
+    for r, g, h in zip(ref, got, got_host):
+        for k in ("ids", "lens", "n_atoms", "atom_idx", "edges"):
+            if k in ("atom_idx", "edges"):      # entries beyond n_atoms are unspecified scratch
+                for i, n in enumerate(r["n_atoms"].tolist()):
+                    a, b, c = (t[k][i][:n] if k == "atom_idx" else t[k][i][:n, :n] for t in (r, g, h))
+                    assert torch.equal(a, b.cpu()) and torch.equal(a, c), k
+            else:
+                assert torch.equal(r[k], g[k].cpu()) and torch.equal(r[k], h[k]), k
+    eng.close()
