@@ -160,6 +160,38 @@ def cpu_reference_sample(n_enc_images: int, n_dec_steps: int):
     return BATCH / full, desc, t_enc + t_dec
 
 
+def eager_port_sample(dev, n_enc_images: int = 8, n_dec_steps: int = 24):
+    """The same port of the reference's PyTorch path, run EAGERLY on `dev` (BASELINE.md's second bar: "stock
+    PyTorch-eager of the reference modules on the same B200"): ~1650 ATen dispatches and three host syncs per
+    decode step.  Bounded sample scaled like cpu_reference_sample.  Returns (images/s, description)."""
+    from molnextr_b200 import synth
+    from oracle import restate
+    ck = synth.synthetic_checkpoint(0, "fixed480")
+    enc = {k: v.to(dev) for k, v in ck["encoder"].items()}
+    dec = {k: v.to(dev) for k, v in ck["decoder"].items()}
+    g = torch.Generator(device="cpu").manual_seed(0)
+    x = torch.randn((BATCH, 3, H, W), generator=g).to(dev)
+    sync = torch.cuda.synchronize if torch.device(dev).type == "cuda" else (lambda: None)
+    with torch.no_grad():
+        f1 = restate.swin_b_features(enc, x[:1])                           # warm-up (cuBLAS / cuDNN handles)
+        restate.greedy_decode(dec, f1.repeat(BATCH, 1, 1).contiguous(), max_len=2)
+        sync()
+        t0 = time.perf_counter()
+        f_part = restate.swin_b_features(enc, x[:n_enc_images])
+        sync()
+        t_enc = time.perf_counter() - t0
+        feats = f_part.repeat((BATCH + n_enc_images - 1) // n_enc_images, 1, 1)[:BATCH].contiguous()
+        t0 = time.perf_counter()
+        restate.greedy_decode(dec, feats, max_len=n_dec_steps)
+        sync()
+        t_dec = time.perf_counter() - t0
+    full = t_enc * (BATCH / n_enc_images) + t_dec * (T_MAX / n_dec_steps)
+    desc = (f"the same fp32 torch port run eagerly on {dev}: Swin-B on {n_enc_images} of {BATCH} images ({t_enc * 1e3:.0f} ms) + "
+            f"greedy decode of all {BATCH} rows for {n_dec_steps} of {T_MAX} steps ({t_dec * 1e3:.0f} ms), scaled linearly "
+            f"({full:.2f} s per batch)")
+    return BATCH / full, desc
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -364,6 +396,11 @@ def run_ours(args):
                    "kind": "port", "sample": cpu_desc}
         except Exception as ex:  # the baseline must never take the bench line down
             cpu = {"value": None, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+        try:
+            ev, edesc = eager_port_sample(dev)
+            cpu["same_port_eager_on_gpu"] = {"value": ev, "unit": "images/s", "sample": edesc}
+        except Exception as ex:
+            cpu["same_port_eager_on_gpu"] = {"value": None, "sample": f"failed: {ex}"}
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",

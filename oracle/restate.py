@@ -61,11 +61,11 @@ def _window_reverse(win: torch.Tensor, ws: int, H: int, W: int) -> torch.Tensor:
     return x.permute(0, 1, 3, 2, 4, 5).contiguous().view(B, H, W, -1)
 
 
-def swin_shift_mask(Hp: int, Wp: int, ws: int, shift: int) -> Optional[torch.Tensor]:
+def swin_shift_mask(Hp: int, Wp: int, ws: int, shift: int, device=None) -> Optional[torch.Tensor]:
     """(nW, ws*ws, ws*ws) additive mask, 0 / -100  (transformers.py:220-243)."""
     if shift == 0:
         return None
-    img = torch.zeros((1, Hp, Wp, 1))
+    img = torch.zeros((1, Hp, Wp, 1), device=device)
     cnt = 0
     for h in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
         for w in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
@@ -89,7 +89,7 @@ def _swin_block(sd: SD, p: str, x: torch.Tensor, H: int, W: int, heads: int, shi
     if shift > 0:
         x = torch.roll(x, shifts=(-shift, -shift), dims=(1, 2))
     xw = _window_partition(x, ws).view(-1, ws * ws, C)
-    mask = swin_shift_mask(Hp, Wp, ws, shift)
+    mask = swin_shift_mask(Hp, Wp, ws, shift, device=x.device)
     # WindowAttention.forward, transformers.py:147-178
     B_, N, _ = xw.shape
     hd = C // heads
@@ -285,7 +285,7 @@ def decoder_step(dec_sd: SD, tokens: torch.Tensor, mem: torch.Tensor, state: Dec
     if pe.size(0) < R:
         raise RuntimeError(f"Sequence is {R} but PositionalEncoding is limited to {pe.size(0)}")
     x = emb_w[tokens].view(R, 1, DEC_DIM) * math.sqrt(DEC_DIM) + pe[:R]
-    src_pad_mask = torch.zeros((R, 1, mem.size(1)), dtype=torch.bool)
+    src_pad_mask = torch.zeros((R, 1, mem.size(1)), dtype=torch.bool, device=mem.device)
     for l in range(DEC_LAYERS):
         p = f"{_P}decoder.transformer_layers.{l}."
         cache = state.layers[l]
@@ -304,7 +304,7 @@ def decoder_step(dec_sd: SD, tokens: torch.Tensor, mem: torch.Tensor, state: Dec
 def grammar_mask(tokens: torch.Tensor, offset: int, maxx: int, maxy: int) -> torch.Tensor:
     """CharTokenizer.get_output_mask (tokenization.py:383-392) for each INPUT token: True = blocked."""
     V = offset + maxx + maxy
-    ids = torch.arange(V).unsqueeze(0)
+    ids = torch.arange(V, device=tokens.device).unsqueeze(0)
     t = tokens.view(-1, 1)
     is_x = (t >= offset) & (t < offset + maxx)
     is_y = t >= offset + maxx
@@ -327,11 +327,12 @@ def greedy_decode(dec_sd: SD, features: torch.Tensor, max_len: int = 480,
     mem = memory_bank(sd, features)
     state = DecoderState()
     w_out, b_out = sd[_P + "output_layer.weight"], sd[_P + "output_layer.bias"]
-    alive_seq = torch.full((B, 1), SOS_ID, dtype=torch.long)
-    alive_logp = torch.zeros((B, 0))
+    dev = features.device      # the restatement runs wherever its inputs live (bench.py's eager-GPU baseline)
+    alive_seq = torch.full((B, 1), SOS_ID, dtype=torch.long, device=dev)
+    alive_logp = torch.zeros((B, 0), device=dev)
     alive_hidden = None
     alive_lp_rec = [] if record_logprobs else None
-    orig_idx = torch.arange(B)
+    orig_idx = torch.arange(B, device=dev)
     results: List[Optional[dict]] = [None] * B
     with torch.no_grad():
         for step in range(max_len):
