@@ -258,6 +258,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
         dist.init_process_group(backend="nccl", device_id=dev)
 
     ck = synth.synthetic_checkpoint(0, "fixed480")
