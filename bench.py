@@ -214,7 +214,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t_all,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def roofline_other(extra, peaks, clocks, xattn_bytes, xattn_s):
@@ -258,7 +258,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
         dist.init_process_group(backend="nccl", device_id=dev)
 
     ck = synth.synthetic_checkpoint(0, "fixed480")
@@ -436,14 +435,33 @@ def run_ours(args):
             "decode": {"ms": extra["decode_ms"], "us_per_step": extra["decode_us_per_step"], "kernel_us_graph_path": extra["kernel_us"]},
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     eng.close()
 
 
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line, but native libraries write to file descriptor 1 behind Python's
+    back (NCCL prints "NCCL version ..." there when NCCL_DEBUG is VERSION / WARN, whatever NCCL_DEBUG_FILE
+    says).  Keep a private duplicate of the real stdout for the JSON line and point fd 1 at stderr."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
