@@ -315,7 +315,9 @@ def run_ours(args):
     # ---- device-resident arm ----
     for _ in range(args.warmup):
         gather(eng.predict(x_dev))
-    eng.predict_pipelined([x_dev] * max(2, args.warmup))
+    # untimed pass of the same shape as the timed one: device allocator pools (and, in host mode below, the
+    # engine's pinned result buffers, one set per batch of a call) exist before the timed region starts
+    eng.predict_pipelined([x_dev] * max(args.steps, args.warmup))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -326,7 +328,7 @@ def run_ours(args):
     steps_run = eng.last_decode_steps()
     # ---- host-buffer arm (H2D + D2H inside) ----
     eng.predict_host(x_host)
-    eng.predict_pipelined([x_host] * max(2, args.warmup), host=True)
+    eng.predict_pipelined([x_host] * max(args.steps, args.warmup), host=True)
     ms_e2e = timed_pipeline([x_host] * args.steps, host=True)
     ms_e2e_latency = timed(lambda: eng.predict_host(x_host), args.steps)
     clocks = sampler.stop() if rank == 0 else None
