@@ -35,3 +35,17 @@ def test_crop_box_follows_cropwhite():
     img[7, 11] = (255, 254, 255)
     img[30, 50] = (0, 0, 0)
     assert preprocess_np.crop_box(img) == (7, 31, 11, 51)
+
+
+def test_resize_restatement_fuzz_against_cv2():
+    """Random source sizes (upscaling, downscaling, extreme aspect ratios, 1-pixel sides) and destination sizes."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 700), st.integers(1, 700), st.sampled_from([(384, 384), (96, 96), (37, 53), (1, 1)]), st.integers(0, 2**31 - 1))
+    def check(h, w, dst, seed):
+        img = np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+        ref = cv2.resize(img, dst, interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(preprocess_np.resize_linear_u8(img, dst[0], dst[1]), ref), (h, w, dst)
+
+    check()
