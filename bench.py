@@ -317,19 +317,26 @@ def run_ours(args):
         gather(eng.predict(x_dev))
     # untimed pass of the same shape as the timed one: device allocator pools (and, in host mode below, the
     # engine's pinned result buffers, one set per batch of a call) exist before the timed region starts
-    eng.predict_pipelined([x_dev] * max(args.steps, args.warmup))
+    pipeline_note = None
+    try:
+        eng.predict_pipelined([x_dev] * max(args.steps, args.warmup))
+    except Exception as ex:      # keep a bench line even if the two-stream path is unusable on this box
+        pipeline_note = f"predict_pipelined failed ({ex}); value / e2e are the batch-by-batch numbers"
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms_latency = timed(lambda: eng.predict(x_dev), args.steps)          # batch by batch (single-batch latency)
     l0 = eng.launch_count()
-    ms_dev = timed_pipeline([x_dev] * args.steps, host=False)
+    ms_dev = timed_pipeline([x_dev] * args.steps, host=False) if pipeline_note is None else timed(lambda: eng.predict(x_dev), args.steps)
     launches = eng.launch_count() - l0
     steps_run = eng.last_decode_steps()
     # ---- host-buffer arm (H2D + D2H inside) ----
     eng.predict_host(x_host)
-    eng.predict_pipelined([x_host] * max(args.steps, args.warmup), host=True)
-    ms_e2e = timed_pipeline([x_host] * args.steps, host=True)
+    if pipeline_note is None:
+        eng.predict_pipelined([x_host] * max(args.steps, args.warmup), host=True)
+        ms_e2e = timed_pipeline([x_host] * args.steps, host=True)
+    else:
+        ms_e2e = timed(lambda: eng.predict_host(x_host), args.steps)
     ms_e2e_latency = timed(lambda: eng.predict_host(x_host), args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -411,7 +418,8 @@ def run_ours(args):
                        "encoder": "swin_base", "parallelism": f"dp{world}",
                        "pipeline": "the K timed steps run through Engine.predict_pipelined: the encoder of step i+1 (second "
                                    "stream, GEMM grids capped at 32 CTAs) overlaps the persistent decode kernel of step i, "
-                                   "which occupies 112 of the 148 SMs; batch-by-batch numbers are under `latency`",
+                                   "which occupies 112 of the 148 SMs; batch-by-batch numbers are under `latency`"
+                                   if pipeline_note is None else pipeline_note,
                        "l2": "no explicit flush: one step streams 0.19 GB of bf16 encoder weights, >1 GB of "
                              "activations and a 246 MB KV cache, far above the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
