@@ -4,8 +4,9 @@
  * One engine handle per GPU.  The handle owns the repacked weights and every workspace
  * (KV caches, memory K/V, activations, CUDA graphs); the caller owns all input / output
  * buffers and passes plain device pointers plus the CUDA stream to run on.  No torch types
- * cross this boundary.  One call in flight per handle (the reference decoder is not
- * re-entrant either: its KV cache is a module attribute, MolNexTR/models/decoder.py:287).
+ * cross this boundary.  One call in flight per handle AND context (the reference decoder is not
+ * re-entrant either: its KV cache is a module attribute, MolNexTR/models/decoder.py:287); see
+ * mnx_reserve_contexts for keeping several batches in flight.
  *
  * Each entry point names the reference interface it replaces (paths relative to the
  * reference repository root):
@@ -164,11 +165,29 @@ int mnx_predict_host(mnx_engine* e, const float* images_host, int32_t B, int32_t
                      int32_t* atom_idx_host, int32_t* n_atoms_host, uint8_t* edges_host);
 
 /* pipelining across batches -------------------------------------------------------------- */
-/* For batches of <= 60 rows the decode is one persistent kernel on ~112 of the 148 SMs and
- * mnx_decode_greedy / mnx_predict return without synchronising the host.  A caller that has the next batch
- * ready can therefore enqueue its mnx_encode on a second (lower-priority) stream right away; this call caps
- * the encoder GEMMs' persistent grid at n CTAs (0 = one per SM) so that they fit on the SMs the decode kernel
- * leaves free instead of queueing behind it.  Process-wide setting.  See Engine.predict_pipelined. */
+/* The reference processes one mini-batch at a time (`for idx in range(0, len(input_images), batch_size)`,
+ * MolNexTR/model.py:102-109; eval loop main.py:273-293).  The cluster decode kernels are single persistent
+ * launches that never synchronise the host, so a caller with more batches ready can keep several in flight:
+ *
+ *   mnx_reserve_contexts(e, n)  allocate n complete sets of per-call device buffers (KV caches, memory-bank
+ *                               K/V, ids / hidden / bond-head scratch).  Context 0 exists after finalize.
+ *   mnx_set_context(e, i)       every later call on this handle enqueues its work on context i's buffers.
+ *                               Calls that use different contexts may run concurrently on different streams;
+ *                               two calls on the SAME context must be ordered by the caller (same stream).
+ *                               The encoder has one activation workspace: mnx_encode calls must be ordered
+ *                               among themselves (one encoder stream).
+ *   mnx_set_decode_path(e, p)   0 = automatic (lowest single-batch latency: 16-CTA clusters of <= 5 rows on
+ *                               ~112 SMs), 1 = multi-kernel graph path, 2 = 8-CTA clusters of <= 4 rows,
+ *                               3 = 16-CTA clusters, 6 = throughput kernel (8-CTA clusters of <= 16 rows: a
+ *                               batch of 32 occupies 16 SMs, so ~4-8 batches decode side by side with the
+ *                               encoder of the next ones).  Results are identical on every path.
+ *   mnx_set_encoder_cta_limit(e, n)  cap the persistent grid of THIS handle's encoder GEMMs at n CTAs
+ *                               (0 = one per SM) so that they fit on the SMs running decode kernels leave free
+ *                               instead of queueing behind them.
+ * See Engine.predict_pipelined for the host-side schedule. */
+int mnx_reserve_contexts(mnx_engine* e, int32_t n);
+int mnx_set_context(mnx_engine* e, int32_t i);
+int mnx_set_decode_path(mnx_engine* e, int32_t path);
 int mnx_set_encoder_cta_limit(mnx_engine* e, int32_t n);
 
 /* introspection ------------------------------------------------------------------------ */

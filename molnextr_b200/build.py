@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmolnextr_b200.so")
-SOURCES = ["engine.cu", "decoder.cu", "mega.cu", "mega16.cu", "mega16s.cu", "encoder.cu", "swin.cu", "gemm_tc.cu", "convnext.cu", "preprocess.cu"]
+SOURCES = ["engine.cu", "decoder.cu", "mega.cu", "mega16.cu", "mega16s.cu", "wide.cu", "encoder.cu", "swin.cu", "gemm_tc.cu", "convnext.cu", "preprocess.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

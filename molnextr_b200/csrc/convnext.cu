@@ -44,6 +44,7 @@ struct ConvNextState {
     __nv_bfloat16 *abuf = nullptr, *hbuf = nullptr;
     size_t max_tokens = 0;
     int last_B = 0, last_H = 0, last_W = 0;
+    int cta_limit = 0;   // cap of the persistent GEMM grids for the forward in progress (EncoderState::cta_limit)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -356,8 +357,9 @@ int convnext_finalize(mnx_engine* e, ConvNextState** out, const mnx_config& cfg)
 void convnext_destroy(ConvNextState* st) { delete st; }
 
 static cudaError_t cn_gemm(const __nv_bfloat16* A, const __nv_bfloat16* W, long long M, int N, int K, int epi,
-                           const float* bias, const float* gamma, void* out, cudaStream_t s) {
+                           const float* bias, const float* gamma, void* out, cudaStream_t s, int cta_limit) {
     GemmParams p{};
+    p.cta_limit = cta_limit;
     p.A = A; p.W = W; p.M = (int)M; p.N = N; p.K = K; p.epilogue = epi; p.bias = bias; p.gamma = gamma; p.out = out;
     return gemm_tc_launch(p, s);
 }
@@ -402,7 +404,8 @@ static int launch_dwconv(mnx_engine* e, const float* x, int B, int H, int W, int
 }
 
 int convnext_forward(mnx_engine* e, ConvNextState* st, const float* images, int B, int H, int W, float* features,
-                     cudaStream_t s, int* launches) {
+                     cudaStream_t s, int* launches, int cta_limit) {
+    st->cta_limit = cta_limit;
     if (H % 32 != 0 || W % 32 != 0) {
         mnx_set_error(e, "ConvNeXt-B path needs H and W to be multiples of 32");
         return MNX_ERR_INVALID;
@@ -423,7 +426,7 @@ int convnext_forward(mnx_engine* e, ConvNextState* st, const float* images, int 
                                                                          st->down[stage].ln_b, 1e-6f, st->abuf);
             CN_CUDA(e, cudaGetLastError()); ++nl;
             float* dst = (stage == 3) ? features : x_other;     // the last stage lives in the caller's buffer
-            CN_CUDA(e, cn_gemm(st->abuf, st->down[stage].w, M2, C, 4 * Ci, GEMM_EPI_F32, st->down[stage].b, nullptr, dst, s)); ++nl;
+            CN_CUDA(e, cn_gemm(st->abuf, st->down[stage].w, M2, C, 4 * Ci, GEMM_EPI_F32, st->down[stage].b, nullptr, dst, s, st->cta_limit)); ++nl;
             if (stage == 3) { x = features; } else { float* t = x; x = x_other; x_other = t; }
             Hc = H2; Wc = W2;
         }
@@ -432,8 +435,8 @@ int convnext_forward(mnx_engine* e, ConvNextState* st, const float* images, int 
             const CnBlockW& w = st->blocks[stage][j];
             CN_TRY(launch_dwconv(e, x, B, Hc, Wc, C, w, st->abuf, s));
             ++nl;
-            CN_CUDA(e, cn_gemm(st->abuf, w.fc1_w, M, 4 * C, C, GEMM_EPI_GELU_BF16, w.fc1_b, nullptr, st->hbuf, s)); ++nl;
-            CN_CUDA(e, cn_gemm(st->hbuf, w.fc2_w, M, C, 4 * C, GEMM_EPI_RESADD_F32, w.fc2_b, w.gamma, x, s)); ++nl;
+            CN_CUDA(e, cn_gemm(st->abuf, w.fc1_w, M, 4 * C, C, GEMM_EPI_GELU_BF16, w.fc1_b, nullptr, st->hbuf, s, st->cta_limit)); ++nl;
+            CN_CUDA(e, cn_gemm(st->hbuf, w.fc2_w, M, C, 4 * C, GEMM_EPI_RESADD_F32, w.fc2_b, w.gamma, x, s, st->cta_limit)); ++nl;
         }
     }
     st->last_B = B; st->last_H = H; st->last_W = W;

@@ -5,12 +5,12 @@ namespace mnx {
 
 int swin_finalize(mnx_engine* e, SwinState** st, const mnx_config& cfg);
 int swin_forward(mnx_engine* e, SwinState* st, const float* images, int B, int H, int W, float* features,
-                 cudaStream_t s, int* launches);
+                 cudaStream_t s, int* launches, int cta_limit);
 int swin_time_kernel(mnx_engine* e, SwinState* st, int which, int iters, float* ms, cudaStream_t s);
 void swin_destroy(SwinState* st);
 int convnext_finalize(mnx_engine* e, ConvNextState** st, const mnx_config& cfg);
 int convnext_forward(mnx_engine* e, ConvNextState* st, const float* images, int B, int H, int W, float* features,
-                     cudaStream_t s, int* launches);
+                     cudaStream_t s, int* launches, int cta_limit);
 void convnext_destroy(ConvNextState* st);
 int convnext_time_kernel(mnx_engine* e, ConvNextState* st, int which, int iters, float* ms, cudaStream_t s);
 
@@ -34,8 +34,8 @@ int encoder_finalize(mnx_engine* e, EncoderState& st, const mnx_config& cfg) {
 
 int encoder_forward(mnx_engine* e, EncoderState& st, const float* images, int B, int H, int W, float* features,
                     cudaStream_t s, int* launches) {
-    if (st.kind == MNX_ENCODER_SWIN_B) return swin_forward(e, st.swin, images, B, H, W, features, s, launches);
-    if (st.kind == MNX_ENCODER_CONVNEXT_B) return convnext_forward(e, st.cnx, images, B, H, W, features, s, launches);
+    if (st.kind == MNX_ENCODER_SWIN_B) return swin_forward(e, st.swin, images, B, H, W, features, s, launches, st.cta_limit);
+    if (st.kind == MNX_ENCODER_CONVNEXT_B) return convnext_forward(e, st.cnx, images, B, H, W, features, s, launches, st.cta_limit);
     mnx_set_error(e, "unknown encoder kind");
     return MNX_ERR_INVALID;
 }

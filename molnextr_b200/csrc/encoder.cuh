@@ -31,6 +31,7 @@ struct EncoderState {
     int kind = MNX_ENCODER_NONE;
     SwinState* swin = nullptr;
     ConvNextState* cnx = nullptr;
+    int cta_limit = 0;      // cap of the persistent GEMM grids of this engine's encoder (0 = one CTA per SM)
 };
 
 int encoder_seq_len(int kind, int H, int W);

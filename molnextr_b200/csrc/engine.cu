@@ -56,6 +56,20 @@ struct HostTensor {
     }
 };
 
+struct CtxPtrs {
+    DecState* st;
+    int *alive, *cur_tok, *finished;
+    float *xa, *xb, *q, *part, *part2, *hbuf;
+    float *selfK, *selfV, *crossK, *crossV, *membank;
+    int *ids, *lens;
+    float *logp, *hidden;
+    unsigned int* row_state;
+    int *steps_run_dev, *ticket;
+    float *hg, *AB, *prob, *features;
+    int *atom_idx, *n_atoms;
+    uint8_t* edges;
+};
+
 struct mnx_engine {
     mnx_config cfg{};
     std::string err;
@@ -77,11 +91,22 @@ struct mnx_engine {
     // persistent cluster decode kernel (mega.cu)
     const float *wpack = nullptr, *ppack = nullptr, *finalp = nullptr, *wpack16 = nullptr, *ppack16 = nullptr;
     int max_clusters16 = 0, max_clusters16s = 0;
+    const float* wpackW = nullptr;       // wide.cu weight slots
+    int max_clusters_w = 0;
+    int* ticket = nullptr;               // wide.cu cluster-order ticket
     unsigned int* row_state = nullptr;
     int* steps_run_dev = nullptr;
     long long* prof_dev = nullptr;
     int max_clusters = 0;
-    int decode_path = 0;   // 0 auto, 1 force multi-kernel graph path, 2 force 8-CTA cluster kernel, 3 force 16-CTA cluster kernel
+    int decode_path = 0;   // 0 auto, 1 force multi-kernel graph path, 2 force 8-CTA cluster kernel, 3 force 16-CTA cluster kernel,
+                           // 6 force the throughput kernel (wide.cu: 8-CTA clusters of <= 16 rows)
+    bool decode_profile = false;   // MNX_DECODE_PROFILE, read once at create
+    // decode contexts: complete sets of per-call device buffers, so that several batches can be in flight on
+    // different streams (Engine.predict_pipelined).  Context 0 is allocated at finalize; the flat pointer fields
+    // of this struct always hold the CURRENT context (mnx_set_context copies a saved set over them).
+    std::vector<struct CtxPtrs> ctxs;
+    int cur_ctx = 0;
+    int num_sms = 0;
     // bond head
     float *hg = nullptr, *AB = nullptr, *prob = nullptr;
     // predict-path staging
@@ -100,7 +125,7 @@ struct mnx_engine {
     cudaGraphExec_t graph_beam = nullptr;
     int gb_B = -1, gb_S = -1, gb_K = -1, gb_NB = -1, gb_nodes = 0;
     int last_beam_B = 0;
-    cudaStream_t cap_stream = nullptr;   // capture-only stream (the legacy default stream cannot be captured)
+    cudaStream_t cap_stream = nullptr;   // engine-owned non-blocking stream: graph capture and mnx_predict_host
     int* h_done = nullptr;   // pinned
     int64_t launches = 0;
     int last_steps = 0;
@@ -205,10 +230,14 @@ extern "C" int mnx_create(const mnx_config* cfg, mnx_engine** out) {
     if (c == cudaSuccess) c = mega_configure(&e->max_clusters);
     if (c == cudaSuccess) c = mega16_configure(&e->max_clusters16);
     if (c == cudaSuccess) c = mega16s_configure(&e->max_clusters16s);
+    if (c == cudaSuccess) c = wide_configure(&e->max_clusters_w);
+    e->num_sms = prop.multiProcessorCount;
+    e->decode_profile = getenv("MNX_DECODE_PROFILE") != nullptr;
     if (const char* env = getenv("MNX_DECODE_PATH")) {
         if (!strcmp(env, "graph")) e->decode_path = 1;
         else if (!strcmp(env, "cluster")) e->decode_path = 2;
         else if (!strcmp(env, "cluster16")) e->decode_path = 3;
+        else if (!strcmp(env, "wide")) e->decode_path = 6;
     }
     if (c == cudaSuccess) c = cudaMallocHost(&e->h_done, sizeof(int));
     if (c == cudaSuccess) c = cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking);
@@ -315,6 +344,23 @@ static int finalize_decoder(mnx_engine* e) {
         for (int k = 0; k < 256; ++k)
             for (int c = 0; c < 16; ++c) dst[k * 16 + c] = Wm[(size_t)(row0 + c) * in_dim + k0 + k];
     };
+    // throughput kernel (wide.cu): [8 heads][L*14 + 1] slots of 8192 floats, k-pair interleaved for packed f32x2 FMAs.
+    // Column-parallel slot (q, k, v, Wq_ctx, W1 x4, vocabulary): [128 kp][32 cols][2].  Row-parallel slot (Wo, Wo_ctx,
+    // W2 x4 k-chunks): [2 halves][16 kp][128 cols][2], k = this head's context features / this CTA's FFN columns.
+    const size_t SLOTW = 8192;
+    std::vector<float> wpackW((size_t)8 * NTILE * SLOTW, 0.f);
+    auto put_col = [&](int h, int l, int t, const std::vector<float>& Wm, int in_dim, int row0) {
+        float* dst = wpackW.data() + ((size_t)h * NTILE + (size_t)l * TPL + t) * SLOTW;
+        for (int k = 0; k < 256; ++k)
+            for (int c = 0; c < 32; ++c) dst[((k >> 1) * 32 + c) * 2 + (k & 1)] = Wm[(size_t)(row0 + c) * in_dim + k];
+    };
+    auto put_row = [&](int h, int l, int t, const std::vector<float>& Wm, int in_dim, int k0) {
+        float* dst = wpackW.data() + ((size_t)h * NTILE + (size_t)l * TPL + t) * SLOTW;
+        for (int half = 0; half < 2; ++half)
+            for (int k = 0; k < 32; ++k)
+                for (int c = 0; c < 128; ++c)
+                    dst[half * 4096 + ((k >> 1) * 128 + c) * 2 + (k & 1)] = Wm[(size_t)(half * 128 + c) * in_dim + k0 + k];
+    };
     for (int l = 0; l < MNX_DEC_L; ++l) {
         const std::string L = P + "decoder.transformer_layers." + std::to_string(l) + ".";
         DecLayerW& w = e->dw.layer[l];
@@ -375,6 +421,12 @@ static int finalize_decoder(mnx_engine* e) {
                 pp[1856 + c] = b2->f[h * 32 + c];
             }
             for (int c = 0; c < 128; ++c) pp[1728 + c] = b1->f[h * 128 + c];
+            put_col(h, l, 0, sq->f, D, h * 32); put_col(h, l, 1, sk->f, D, h * 32); put_col(h, l, 2, sv->f, D, h * 32);
+            put_row(h, l, 3, so->f, D, h * 32);
+            put_col(h, l, 4, cq->f, D, h * 32);
+            put_row(h, l, 5, co->f, D, h * 32);
+            for (int j = 0; j < 4; ++j) put_col(h, l, 6 + j, w1->f, D, h * 128 + j * 32);
+            for (int j = 0; j < 4; ++j) put_row(h, l, 10 + j, w2->f, MNX_DEC_FF, h * 128 + j * 32);
         }
         for (int i = 0; i < 16; ++i) {
             put_tile16(i, l, 0, sq->f, D, i * 16, 0);
@@ -420,6 +472,13 @@ static int finalize_decoder(mnx_engine* e) {
             for (int k = 0; k < 256; ++k)
                 for (int c = 0; c < 16; ++c) dst[k * 16 + c] = (i * 16 + c < V) ? ow->f[(size_t)(i * 16 + c) * D + k] : 0.f;
         }
+        for (int h = 0; h < 8; ++h) {
+            float* dst = wpackW.data() + ((size_t)h * NTILE + (size_t)MNX_DEC_L * TPL) * SLOTW;
+            for (int k = 0; k < 256; ++k)
+                for (int c = 0; c < 32; ++c)
+                    dst[((k >> 1) * 32 + c) * 2 + (k & 1)] = (h * 32 + c < V) ? ow->f[(size_t)(h * 32 + c) * D + k] : 0.f;
+        }
+        UP(e->wpackW, wpackW);
         UP(e->wpack, wpack); UP(e->ppack, ppack); UP(e->finalp, fin);
         UP(e->wpack16, wpack16); UP(e->ppack16, ppack16);
     }
@@ -446,10 +505,10 @@ static int finalize_decoder(mnx_engine* e) {
     return MNX_OK;
 }
 
-static int alloc_workspaces(mnx_engine* e) {
-    // B = images per call; R = decoder rows per call (images x beams under beam search)
+// per-context device buffers (everything one predict / decode call writes), allocated into the flat fields of `e`;
+// R = decoder rows (images x beams for context 0 of a beam-search handle, images otherwise)
+static int alloc_context(mnx_engine* e, size_t R) {
     const size_t B = e->cfg.max_batch, T = e->cfg.max_len, S = e->S_max, KA = e->cfg.max_atoms;
-    const size_t R = B * (e->cfg.max_beam > 1 ? e->cfg.max_beam : 1);
     CUDA_TRY(e, dev_alloc(e, &e->st, 1));
     CUDA_TRY(e, dev_alloc(e, &e->alive, 2 * R));
     CUDA_TRY(e, dev_alloc(e, &e->cur_tok, R));
@@ -469,6 +528,43 @@ static int alloc_workspaces(mnx_engine* e) {
     CUDA_TRY(e, dev_alloc(e, &e->lens, B));
     CUDA_TRY(e, dev_alloc(e, &e->logp, B * T));
     CUDA_TRY(e, dev_alloc(e, &e->hidden, R * T * 256));
+    CUDA_TRY(e, dev_alloc(e, &e->row_state, B));
+    CUDA_TRY(e, dev_alloc(e, &e->steps_run_dev, 1));
+    CUDA_TRY(e, dev_alloc(e, &e->ticket, 1));
+    CUDA_TRY(e, dev_alloc(e, &e->hg, B * KA * 256));
+    CUDA_TRY(e, dev_alloc(e, &e->AB, B * KA * 512));
+    CUDA_TRY(e, dev_alloc(e, &e->prob, B * KA * KA * 8));
+    CUDA_TRY(e, dev_alloc(e, &e->features, B * S * (size_t)e->cfg.encoder_dim));
+    CUDA_TRY(e, dev_alloc(e, &e->atom_idx, B * KA));
+    CUDA_TRY(e, dev_alloc(e, &e->n_atoms, B));
+    CUDA_TRY(e, dev_alloc(e, &e->edges, B * KA * KA));
+    return MNX_OK;
+}
+static CtxPtrs capture_context(const mnx_engine* e) {
+    return CtxPtrs{e->st, e->alive, e->cur_tok, e->finished, e->xa, e->xb, e->q, e->part, e->part2, e->hbuf,
+                   e->selfK, e->selfV, e->crossK, e->crossV, e->membank, e->ids, e->lens, e->logp, e->hidden,
+                   e->row_state, e->steps_run_dev, e->ticket, e->hg, e->AB, e->prob, e->features,
+                   e->atom_idx, e->n_atoms, e->edges};
+}
+static void apply_context(mnx_engine* e, const CtxPtrs& c) {
+    e->st = c.st; e->alive = c.alive; e->cur_tok = c.cur_tok; e->finished = c.finished;
+    e->xa = c.xa; e->xb = c.xb; e->q = c.q; e->part = c.part; e->part2 = c.part2; e->hbuf = c.hbuf;
+    e->selfK = c.selfK; e->selfV = c.selfV; e->crossK = c.crossK; e->crossV = c.crossV; e->membank = c.membank;
+    e->ids = c.ids; e->lens = c.lens; e->logp = c.logp; e->hidden = c.hidden;
+    e->row_state = c.row_state; e->steps_run_dev = c.steps_run_dev; e->ticket = c.ticket;
+    e->hg = c.hg; e->AB = c.AB; e->prob = c.prob; e->features = c.features;
+    e->atom_idx = c.atom_idx; e->n_atoms = c.n_atoms; e->edges = c.edges;
+    e->edge_hidden = e->hidden;
+}
+
+static int alloc_workspaces(mnx_engine* e) {
+    // B = images per call; R = decoder rows per call (images x beams under beam search)
+    const size_t B = e->cfg.max_batch, T = e->cfg.max_len;
+    const size_t R = B * (e->cfg.max_beam > 1 ? e->cfg.max_beam : 1);
+    int rc = alloc_context(e, R);
+    if (rc != MNX_OK) return rc;
+    e->ctxs.assign(1, capture_context(e));
+    e->cur_ctx = 0;
     e->edge_hidden = e->hidden;
     if (e->cfg.max_beam > 1) {
         BeamBuffers& m = e->bm;
@@ -490,23 +586,42 @@ static int alloc_workspaces(mnx_engine* e) {
         CUDA_TRY(e, dev_alloc(e, &m.trace, T * B * MNX_MAX_BEAM));
         CUDA_TRY(e, dev_alloc(e, &e->hid_best, B * T * 256));
     }
-    CUDA_TRY(e, dev_alloc(e, &e->row_state, B));
-    CUDA_TRY(e, dev_alloc(e, &e->steps_run_dev, 1));
     CUDA_TRY(e, dev_alloc(e, &e->prof_dev, 64));
     CUDA_TRY(e, cudaMemset(e->prof_dev, 0, 64 * sizeof(long long)));
-    CUDA_TRY(e, dev_alloc(e, &e->hg, B * KA * 256));
-    CUDA_TRY(e, dev_alloc(e, &e->AB, B * KA * 512));
-    CUDA_TRY(e, dev_alloc(e, &e->prob, B * KA * KA * 8));
-    CUDA_TRY(e, dev_alloc(e, &e->features, B * S * (size_t)e->cfg.encoder_dim));
-    CUDA_TRY(e, dev_alloc(e, &e->atom_idx, B * KA));
-    CUDA_TRY(e, dev_alloc(e, &e->n_atoms, B));
-    CUDA_TRY(e, dev_alloc(e, &e->edges, B * KA * KA));
     CUDA_TRY(e, dev_alloc(e, &e->pp_bbox, B * 4));
     if (e->cfg.encoder_kind != MNX_ENCODER_NONE)
         CUDA_TRY(e, dev_alloc(e, &e->images, B * 3 * (size_t)e->cfg.max_height * e->cfg.max_width));
     void* cls = nullptr;
     CUDA_TRY(e, mnx_upload_raw(e, e->cls_host.data(), e->cls_host.size(), &cls));
     e->d_cls = (uint8_t*)cls;
+    return MNX_OK;
+}
+
+extern "C" int mnx_reserve_contexts(mnx_engine* e, int32_t n) {
+    if (!e || n < 1 || n > 64) return fail(e, MNX_ERR_INVALID, "mnx_reserve_contexts: n must be in [1,64]");
+    if (!e->finalized) return fail(e, MNX_ERR_INVALID, "weights not finalized");
+    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    const CtxPtrs cur = capture_context(e);
+    while ((int)e->ctxs.size() < n) {
+        int rc = alloc_context(e, e->cfg.max_batch);
+        if (rc != MNX_OK) { apply_context(e, cur); return rc; }
+        e->ctxs.push_back(capture_context(e));
+    }
+    apply_context(e, cur);
+    return MNX_OK;
+}
+
+extern "C" int mnx_set_context(mnx_engine* e, int32_t i) {
+    if (!e || i < 0 || i >= (int)e->ctxs.size()) return fail(e, MNX_ERR_INVALID, "mnx_set_context: context %d not reserved", i);
+    apply_context(e, e->ctxs[i]);
+    e->cur_ctx = i;
+    return MNX_OK;
+}
+
+extern "C" int mnx_set_decode_path(mnx_engine* e, int32_t path) {
+    if (!e || (path != 0 && path != 1 && path != 2 && path != 3 && path != 6))
+        return fail(e, MNX_ERR_INVALID, "mnx_set_decode_path: path must be 0 (auto), 1 (graph), 2 (cluster8), 3 (cluster16) or 6 (wide)");
+    e->decode_path = path;
     return MNX_OK;
 }
 
@@ -588,26 +703,36 @@ static int decode_internal(mnx_engine* e, const float* features, int B, int S, c
     const bool fits8 = usable8 > 0 && B <= usable8 * MG_GMAX_H;
     if (e->decode_path == 3 && !fits16) return fail(e, MNX_ERR_CAPACITY, "16-CTA cluster path forced but %d rows do not fit %d clusters", B, usable16);
     if (e->decode_path == 2 && !fits8) return fail(e, MNX_ERR_CAPACITY, "8-CTA cluster path forced but %d rows do not fit %d clusters", B, usable8);
-    const bool use16 = (e->decode_path == 3) || (e->decode_path == 0 && fits16);
-    const bool use8 = !use16 && ((e->decode_path == 2) || (e->decode_path == 0 && fits8));
+    const int nclw = (B + MGW_GMAX_H - 1) / MGW_GMAX_H;
+    const bool fitsw = nclw <= e->max_clusters_w && T <= MGW_MAX_KEYS_H + 1 && S <= MGW_MAX_KEYS_H;
+    if (e->decode_path == 6 && !fitsw)
+        return fail(e, MNX_ERR_CAPACITY, "throughput decode kernel forced but B=%d S=%d T=%d does not fit (%d clusters resident, <= %d keys)",
+                    B, S, T, e->max_clusters_w, MGW_MAX_KEYS_H);
+    const bool usew = e->decode_path == 6;
+    const bool use16 = !usew && ((e->decode_path == 3) || (e->decode_path == 0 && fits16));
+    const bool use8 = !usew && !use16 && ((e->decode_path == 2) || (e->decode_path == 0 && fits8));
     const bool use16s = use16 && fits16s;
-    if (use16 || use8) {
-        const int usable = use16s ? usable16s : use16 ? usable16 : usable8;
+    if (e->cur_ctx != 0 && !(usew || use16 || use8))
+        return fail(e, MNX_ERR_INVALID, "the multi-kernel graph path runs in context 0 only");
+    if (usew || use16 || use8) {
+        const int usable = usew ? nclw : use16s ? usable16s : use16 ? usable16 : usable8;
         const int G = (B + usable - 1) / usable;
         const int clusters = (B + G - 1) / G;
         CUDA_TRY(e, cudaMemsetAsync(e->row_state, 0, sizeof(unsigned) * B, s));
         CUDA_TRY(e, cudaMemsetAsync(e->steps_run_dev, 0, sizeof(int), s));
+        CUDA_TRY(e, cudaMemsetAsync(e->ticket, 0, sizeof(int), s));
         MegaArgs a{};
         a.wpack = e->wpack; a.ppack = e->ppack; a.wpack16 = e->wpack16; a.ppack16 = e->ppack16;
+        a.wpackW = e->wpackW; a.ticket = e->ticket;
         a.finalp = e->finalp; a.emb = e->dw.emb; a.pe = e->dw.pe;
         a.selfK = e->selfK; a.selfV = e->selfV; a.crossK = e->crossK; a.crossV = e->crossV;
         a.B = B; a.S = S; a.T = T; a.G = G;
         a.ids = e->ids; a.logp = e->logp; a.hidden = e->hidden; a.lens = e->lens;
         a.row_state = e->row_state; a.steps_run = e->steps_run_dev; a.g = e->g;
-        a.prof = getenv("MNX_DECODE_PROFILE") ? e->prof_dev : nullptr;
-        CUDA_TRY(e, use16s ? mega16s_launch(a, clusters, s) : use16 ? mega16_launch(a, clusters, s) : mega_launch(a, clusters, s));
+        a.prof = e->decode_profile ? e->prof_dev : nullptr;
+        CUDA_TRY(e, usew ? wide_launch(a, clusters, s) : use16s ? mega16s_launch(a, clusters, s) : use16 ? mega16_launch(a, clusters, s) : mega_launch(a, clusters, s));
         e->launches += 1;
-        e->last_path = use16s ? 5 : use16 ? 3 : 2;
+        e->last_path = usew ? 6 : use16s ? 5 : use16 ? 3 : 2;
         // no host synchronisation: the whole decode is one kernel, so the call is asynchronous like any other
         // launch on `s` (lets the caller overlap the next batch's encoder with it); mnx_last_decode_steps
         // reads the step count back on demand
@@ -815,7 +940,7 @@ extern "C" int mnx_predict_host(mnx_engine* e, const float* images_host, int32_t
     if (B < 1 || B > e->cfg.max_batch || H > e->cfg.max_height || W > e->cfg.max_width)
         return fail(e, MNX_ERR_CAPACITY, "request (%d,%d,%d) exceeds the sizes given at create", B, H, W);
     CUDA_TRY(e, cudaSetDevice(e->cfg.device));
-    cudaStream_t s = nullptr;   // legacy default stream
+    cudaStream_t s = e->cap_stream;   // engine-owned non-blocking stream (never the legacy default stream)
     CUDA_TRY(e, cudaMemcpyAsync(e->images, images_host, sizeof(float) * (size_t)B * 3 * H * W, cudaMemcpyHostToDevice, s));
     int rc = mnx_predict(e, e->images, B, H, W, ids_host, lens_host, token_logp_host, atom_idx_host, n_atoms_host,
                          edges_host, s);
@@ -846,16 +971,16 @@ extern "C" int32_t mnx_last_decode_steps(const mnx_engine* ce) {
     return e->last_steps;
 }
 
-namespace mnx { void gemm_tc_set_cta_limit(int n); }
 extern "C" int mnx_set_encoder_cta_limit(mnx_engine* e, int32_t n) {
     if (!e || n < 0) return fail(e, MNX_ERR_INVALID, "mnx_set_encoder_cta_limit: bad argument");
-    mnx::gemm_tc_set_cta_limit(n);
+    e->enc.cta_limit = n;      // per handle: picked up by the next mnx_encode / mnx_predict of THIS engine
     return MNX_OK;
 }
 
 extern "C" int mnx_time_kernel(mnx_engine* e, int32_t which, int32_t iters, float* ms, void* cuda_stream) {
     if (!e || !ms || iters < 1) return fail(e, MNX_ERR_INVALID, "mnx_time_kernel: bad argument");
     if (which == 1002) { *ms = (float)e->max_clusters16; return MNX_OK; }
+    if (which == 1004) { *ms = (float)e->max_clusters_w; return MNX_OK; }
     if (which == 1003) { *ms = (float)e->last_path; return MNX_OK; }
     if (which == 1000) { *ms = (float)e->max_clusters; return MNX_OK; }   // introspection: co-resident 8-CTA clusters
     if (which == 1001) {   // dump the cycle stamps recorded by the last profiled cluster decode (MNX_DECODE_PROFILE=1)
@@ -871,14 +996,15 @@ extern "C" int mnx_time_kernel(mnx_engine* e, int32_t which, int32_t iters, floa
     if (which >= 100) return encoder_time_kernel(e, e->enc, which, iters, ms, s);
     if (e->last_B == 0) return fail(e, MNX_ERR_INVALID, "run a decode first: timing uses its shapes and caches");
     if (which == 7) {   // the persistent cluster decode kernel alone, on the K/V of the last call
-        if (e->last_path != 2 && e->last_path != 3 && e->last_path != 5) return fail(e, MNX_ERR_INVALID, "last decode did not use a cluster kernel");
-        const bool use16 = e->last_path == 3, use16s = e->last_path == 5;
-        const int usable = use16s ? (e->max_clusters16s < 8 ? e->max_clusters16s : 8)
-                                  : use16 ? (e->max_clusters16 < 8 ? e->max_clusters16 : 8) : (e->max_clusters < 16 ? e->max_clusters : 16);
+        if (e->last_path != 2 && e->last_path != 3 && e->last_path != 5 && e->last_path != 6) return fail(e, MNX_ERR_INVALID, "last decode did not use a cluster kernel");
+        const bool use16 = e->last_path == 3, use16s = e->last_path == 5, usew = e->last_path == 6;
         const int B = e->last_B, S = e->last_S, T = e->cfg.max_len;
+        const int usable = usew ? (B + MGW_GMAX_H - 1) / MGW_GMAX_H : use16s ? (e->max_clusters16s < 8 ? e->max_clusters16s : 8)
+                                  : use16 ? (e->max_clusters16 < 8 ? e->max_clusters16 : 8) : (e->max_clusters < 16 ? e->max_clusters : 16);
         const int G = (B + usable - 1) / usable, clusters = (B + G - 1) / G;
         MegaArgs a{};
         a.wpack = e->wpack; a.ppack = e->ppack; a.wpack16 = e->wpack16; a.ppack16 = e->ppack16;
+        a.wpackW = e->wpackW; a.ticket = e->ticket;
         a.finalp = e->finalp; a.emb = e->dw.emb; a.pe = e->dw.pe;
         a.selfK = e->selfK; a.selfV = e->selfV; a.crossK = e->crossK; a.crossV = e->crossV;
         a.B = B; a.S = S; a.T = T; a.G = G;
@@ -890,8 +1016,9 @@ extern "C" int mnx_time_kernel(mnx_engine* e, int32_t which, int32_t iters, floa
         for (int i = 0; i < iters; ++i) {
             CUDA_TRY(e, cudaMemsetAsync(e->row_state, 0, sizeof(unsigned) * B, s));
             CUDA_TRY(e, cudaMemsetAsync(e->steps_run_dev, 0, sizeof(int), s));
+            CUDA_TRY(e, cudaMemsetAsync(e->ticket, 0, sizeof(int), s));
             cudaEventRecord(e0, s);
-            CUDA_TRY(e, use16s ? mega16s_launch(a, clusters, s) : use16 ? mega16_launch(a, clusters, s) : mega_launch(a, clusters, s));
+            CUDA_TRY(e, usew ? wide_launch(a, clusters, s) : use16s ? mega16s_launch(a, clusters, s) : use16 ? mega16_launch(a, clusters, s) : mega_launch(a, clusters, s));
             cudaEventRecord(e1, s);
             CUDA_TRY(e, cudaStreamSynchronize(s));
             float t = 0.f;

@@ -282,9 +282,6 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static PFN_encodeTiled g_encode = nullptr;
-static int g_num_sms = 148;
-static int g_cta_limit = 0;     // > 0: cap the persistent grid (encoder sharing the GPU with a running decode kernel)
-void gemm_tc_set_cta_limit(int n) { g_cta_limit = n > 0 ? n : 0; }
 
 cudaError_t gemm_tc_configure() {
     if (g_encode == nullptr) {
@@ -295,9 +292,6 @@ cudaError_t gemm_tc_configure() {
         if (qres != cudaDriverEntryPointSuccess || fn == nullptr) return cudaErrorNotSupported;
         g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
     }
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
     return cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
 }
 
@@ -322,7 +316,10 @@ cudaError_t gemm_tc_launch(const GemmParams& p, cudaStream_t s) {
     if (!make_map(&mw, p.W, (uint64_t)p.N, (uint64_t)p.K, BN)) return cudaErrorInvalidValue;
     GemmKernelArgs g{p.M, p.N, p.K, p.epilogue, p.bias, p.gamma, p.row_map, p.out};
     const int total_tiles = (p.N / BN) * ((p.M + BM - 1) / BM);
-    const int cap = (g_cta_limit > 0 && g_cta_limit < g_num_sms) ? g_cta_limit : g_num_sms;
+    int dev = 0, num_sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);     // cached by the runtime
+    const int cap = (p.cta_limit > 0 && p.cta_limit < num_sms) ? p.cta_limit : num_sms;
     const int grid = total_tiles < cap ? total_tiles : cap;
     gemm_tc_kernel<<<grid, GEMM_THREADS, SMEM_BYTES, s>>>(ma, mw, g);
     return cudaGetLastError();

@@ -24,13 +24,12 @@ struct GemmParams {
     const float* gamma;       // [N] or nullptr
     const int* row_map;       // [M] destination row (or -1 = drop) or nullptr
     void* out;                // bf16 [M][N] / fp32 [M][N] / fp32 residual stream [*][N]
+    int cta_limit;            // > 0: cap the persistent grid at this many CTAs (0 = one per SM): lets the encoder of the
+                              // next batch run on the SMs that concurrently running persistent decode kernels leave free
 };
 
 // Launches the kernel on `s`.  Returns cudaErrorInvalidValue for unsupported shapes.
 cudaError_t gemm_tc_launch(const GemmParams& p, cudaStream_t s);
-// cap the number of CTAs of the persistent kernel (0 = one per SM): lets the encoder of the next batch run on
-// the SMs a concurrently running persistent decode kernel leaves free
-void gemm_tc_set_cta_limit(int n);
 // one-time per-device setup (driver entry point for tensor maps, smem opt-in)
 cudaError_t gemm_tc_configure();
 

@@ -16,6 +16,8 @@ struct MegaArgs {
     const float* ppack;
     const float* wpack16;   // 16-CTA-cluster variant: [16][L*14 + 1][256*16]
     const float* ppack16;   // [16][L][1728]
+    const float* wpackW;    // wide kernel (wide.cu): [8][L*14 + 1] slots of 8192 floats, see finalize_decoder
+    int* ticket;            // wide kernel: cluster-order ticket counter, zeroed before every launch
     const float* finalp;
     const float* emb;
     const float* pe;
@@ -40,5 +42,9 @@ cudaError_t mega16_configure(int* max_clusters);
 cudaError_t mega16_launch(const MegaArgs& a, int clusters, cudaStream_t s);
 cudaError_t mega16s_configure(int* max_clusters);     // <= 28 rows: two 4-warp attention groups, G <= 4 (mega16s.cu)
 cudaError_t mega16s_launch(const MegaArgs& a, int clusters, cudaStream_t s);
+#define MGW_GMAX_H 16    // rows per 8-CTA cluster, throughput kernel (wide.cu)
+#define MGW_MAX_KEYS_H 512   // keys one attention of wide.cu can score (16 sub-tiles of 32): needs T <= 513 and S <= 512
+cudaError_t wide_configure(int* max_clusters);
+cudaError_t wide_launch(const MegaArgs& a, int clusters, cudaStream_t s);
 
 }  // namespace mnx

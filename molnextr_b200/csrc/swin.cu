@@ -45,6 +45,7 @@ struct SwinState {
     int* row_map = nullptr;                          // [2][max Mw]
     size_t max_tokens = 0;
     int last_B = 0, last_H = 0, last_W = 0;
+    int cta_limit = 0;   // cap of the persistent GEMM grids for the forward in progress (EncoderState::cta_limit)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -507,15 +508,17 @@ int swin_finalize(mnx_engine* e, SwinState** out, const mnx_config& cfg) {
 void swin_destroy(SwinState* st) { delete st; }
 
 static cudaError_t gemm(const __nv_bfloat16* A, const __nv_bfloat16* W, long long M, int N, int K, int epi,
-                        const float* bias, const int* row_map, void* out, cudaStream_t s) {
+                        const float* bias, const int* row_map, void* out, cudaStream_t s, int cta_limit) {
     GemmParams p{};
+    p.cta_limit = cta_limit;
     p.A = A; p.W = W; p.M = (int)M; p.N = N; p.K = K; p.epilogue = epi; p.bias = bias; p.row_map = row_map; p.out = out;
     return gemm_tc_launch(p, s);
 }
 
 int swin_forward(mnx_engine* e, SwinState* st, const float* images, int B, int H, int W, float* features,
-                 cudaStream_t s, int* launches) {
+                 cudaStream_t s, int* launches, int cta_limit) {
     int nl = 0;
+    st->cta_limit = cta_limit;
     int Hc = (H + 3) / 4, Wc = (W + 3) / 4;
     {
         const long long ntok = (long long)B * Hc * Wc;
@@ -547,16 +550,16 @@ int swin_forward(mnx_engine* e, SwinState* st, const float* images, int B, int H
             // norm1 -> (pad, roll, window partition) -> bf16
             ln_rows_kernel<true><<<(unsigned)((Mw + 7) / 8), 256, 0, s>>>(x, map0, Mw, C, w.ln1_w, w.ln1_b, 1e-5f, st->abuf);
             SW_CUDA(e, cudaGetLastError()); ++nl;
-            SW_CUDA(e, gemm(st->abuf, w.qkv_w, Mw, 3 * C, C, GEMM_EPI_BF16, w.qkv_b, nullptr, st->qkv, s)); ++nl;
+            SW_CUDA(e, gemm(st->abuf, w.qkv_w, Mw, 3 * C, C, GEMM_EPI_BF16, w.qkv_b, nullptr, st->qkv, s, st->cta_limit)); ++nl;
             window_attn_kernel<<<dim3((unsigned)(Mw / WIN), nH), 288, 0, s>>>(st->qkv, C, nH, w.rpb_t, Hp, Wp, shift, st->attn);
             SW_CUDA(e, cudaGetLastError()); ++nl;
             // proj + window_reverse + un-roll + crop + residual
-            SW_CUDA(e, gemm(st->attn, w.proj_w, Mw, C, C, GEMM_EPI_RESADD_F32, w.proj_b, map0, x, s)); ++nl;
+            SW_CUDA(e, gemm(st->attn, w.proj_w, Mw, C, C, GEMM_EPI_RESADD_F32, w.proj_b, map0, x, s, st->cta_limit)); ++nl;
             // norm2 -> fc1 (GELU) -> fc2 + residual
             ln_rows_kernel<true><<<(unsigned)((M + 7) / 8), 256, 0, s>>>(x, nullptr, M, C, w.ln2_w, w.ln2_b, 1e-5f, st->abuf);
             SW_CUDA(e, cudaGetLastError()); ++nl;
-            SW_CUDA(e, gemm(st->abuf, w.fc1_w, M, 4 * C, C, GEMM_EPI_GELU_BF16, w.fc1_b, nullptr, st->hbuf, s)); ++nl;
-            SW_CUDA(e, gemm(st->hbuf, w.fc2_w, M, C, 4 * C, GEMM_EPI_RESADD_F32, w.fc2_b, nullptr, x, s)); ++nl;
+            SW_CUDA(e, gemm(st->abuf, w.fc1_w, M, 4 * C, C, GEMM_EPI_GELU_BF16, w.fc1_b, nullptr, st->hbuf, s, st->cta_limit)); ++nl;
+            SW_CUDA(e, gemm(st->hbuf, w.fc2_w, M, C, 4 * C, GEMM_EPI_RESADD_F32, w.fc2_b, nullptr, x, s, st->cta_limit)); ++nl;
         }
         if (stage < 3) {
             const int H2 = (Hc + 1) / 2, W2 = (Wc + 1) / 2;
@@ -564,7 +567,7 @@ int swin_forward(mnx_engine* e, SwinState* st, const float* images, int B, int H
             merge_ln_kernel<<<(unsigned)((M2 + 7) / 8), 256, 0, s>>>(x, B, Hc, Wc, C, st->merge[stage].ln_w,
                                                                     st->merge[stage].ln_b, 1e-5f, st->abuf);
             SW_CUDA(e, cudaGetLastError()); ++nl;
-            SW_CUDA(e, gemm(st->abuf, st->merge[stage].red_w, M2, 2 * C, 4 * C, GEMM_EPI_F32, nullptr, nullptr, x_other, s)); ++nl;
+            SW_CUDA(e, gemm(st->abuf, st->merge[stage].red_w, M2, 2 * C, 4 * C, GEMM_EPI_F32, nullptr, nullptr, x_other, s, st->cta_limit)); ++nl;
             float* t = x; x = x_other; x_other = t;
             Hc = H2; Wc = W2;
         }

@@ -3,6 +3,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -66,6 +67,7 @@ class Engine:
         self._host_out: Dict[int, Dict[str, torch.Tensor]] = {}
         self._pipe_streams = None
         self._host_pool: Dict[tuple, Dict[str, torch.Tensor]] = {}
+        self._decode_path = self.DECODE_PATHS.get(os.environ.get("MNX_DECODE_PATH", "auto"), 0)   # mirrors mnx_create
         enc_sd = checkpoint.get("encoder")
         self.encoder_kind = encoder_kind_of(enc_sd)
         offset, maxx, maxy = self.tok.grammar_rule()
@@ -119,6 +121,11 @@ class Engine:
     def _stream(self) -> C.c_void_p:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _same_device(self, *tensors):
+        for t in tensors:
+            if t is not None and t.is_cuda and t.device != self.device:
+                raise EngineError(f"tensor on {t.device} passed to an engine that lives on {self.device}")
+
     @staticmethod
     def _p(t: Optional[torch.Tensor]) -> C.c_void_p:
         return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
@@ -162,6 +169,7 @@ class Engine:
     def encode(self, images: torch.Tensor) -> torch.Tensor:
         """Encoder.forward (components.py:162-174): fp32 NCHW cuda tensor -> (B,S,1024)."""
         assert images.is_cuda and images.dtype == torch.float32 and images.dim() == 4 and images.size(1) == 3
+        self._same_device(images)
         images = images.contiguous()
         B, _, H, W = images.shape
         feats = torch.empty((B, self.seq_len(H, W), self.encoder_dim), device=images.device, dtype=torch.float32)
@@ -171,6 +179,7 @@ class Engine:
     def decode_greedy(self, features: torch.Tensor, return_hidden: bool = False):
         """TransformerDecoderAR.decode with GreedySearch (components.py:253-334)."""
         assert features.is_cuda and features.dtype == torch.float32
+        self._same_device(features)
         features = features.contiguous().view(features.size(0), -1, features.size(-1))
         B, S, _ = features.shape
         dev = features.device
@@ -225,6 +234,7 @@ class Engine:
     def edges(self, atom_idx: torch.Tensor, n_atoms: torch.Tensor, hidden: Optional[torch.Tensor] = None,
               return_scores: bool = False):
         """GraphPredictor + get_edge_prediction (components.py:365-400) for every image of the batch."""
+        self._same_device(atom_idx, n_atoms, hidden)
         B = atom_idx.size(0)
         edges = torch.zeros((B, MAX_ATOMS, MAX_ATOMS), device=atom_idx.device, dtype=torch.uint8)
         score = torch.zeros((B, MAX_ATOMS, MAX_ATOMS), device=atom_idx.device, dtype=torch.float32) if return_scores else None
@@ -235,6 +245,7 @@ class Engine:
     def predict(self, images: torch.Tensor):
         """encoder -> greedy decode -> atom scan -> bond head, device tensors in and out."""
         assert images.is_cuda and images.dtype == torch.float32
+        self._same_device(images)
         images = images.contiguous()
         B, _, H, W = images.shape
         dev = images.device
@@ -248,6 +259,16 @@ class Engine:
                                          self._p(atom_idx), self._p(n_atoms), self._p(edges), self._stream()),
                     "mnx_predict")
         return {"ids": ids, "lens": lens, "logp": logp, "atom_idx": atom_idx, "n_atoms": n_atoms, "edges": edges}
+
+    def empty_result(self):
+        """Zero-row result with the dtypes / trailing shapes of `predict` (a rank with an empty shard, parallel.py)."""
+        dev = self.device
+        return {"ids": torch.empty((0, MAX_LEN), device=dev, dtype=torch.int32),
+                "lens": torch.empty((0,), device=dev, dtype=torch.int32),
+                "logp": torch.empty((0, MAX_LEN), device=dev, dtype=torch.float32),
+                "atom_idx": torch.empty((0, MAX_ATOMS), device=dev, dtype=torch.int32),
+                "n_atoms": torch.empty((0,), device=dev, dtype=torch.int32),
+                "edges": torch.empty((0, MAX_ATOMS, MAX_ATOMS), device=dev, dtype=torch.uint8)}
 
     def predict_host(self, images: torch.Tensor):
         """Same through host buffers: H2D of the images and D2H of every result inside the call.
@@ -280,72 +301,114 @@ class Engine:
         out["edges"] = self.edges(out["atom_idx"], out["n_atoms"])
         return out
 
-    def predict_pipelined(self, batches, host: bool = False, encoder_ctas: int = 32):
-        """Greedy predictions for consecutive image batches with a 2-deep pipeline: for batches of <= 60
-        rows the decode is ONE persistent kernel on ~112 of the 148 SMs and is launched without host
-        synchronisation, so the encoder of batch i+1 (lower-priority stream, GEMM grids capped at
-        `encoder_ctas` CTAs) runs on the SMs the decode of batch i leaves idle.  Results are identical to
-        calling `predict` batch by batch.  `batches`: iterable of fp32 (B,3,H,W) tensors -- cuda tensors, or
-        with host=True pinned host tensors (H2D inside, results returned as pinned host tensors; D2H inside).
+    def predict_pipelined(self, batches, host: bool = False, depth: int = 0, encoder_ctas: int = 0):
+        """Greedy predictions for consecutive image batches, several batches in flight (the reference handles its
+        mini-batches one after the other: model.py:102-109, main.py:273-293).
+
+        Each batch decodes with the throughput kernel (csrc/wide.cu: one persistent launch, 8-CTA clusters of
+        <= 16 rows, i.e. 16 SMs for a batch of 32) in its own decode context on its own high-priority stream;
+        `depth` batches decode side by side while a lower-priority stream runs the encoders of the following
+        batches with their persistent GEMM grids capped at `encoder_ctas` CTAs (default: the SMs the decode
+        kernels leave free).  Results are identical to calling `predict` batch by batch -- every batch keeps its
+        own row ranks.  `batches`: iterable of fp32 (B,3,H,W) tensors -- cuda tensors, or with
+        host=True pinned host tensors (H2D inside; results are returned as pinned host tensors, D2H inside; those
+        buffers are owned by the engine and REUSED by the next predict_pipelined(host=True) call with the same
+        batch sizes: copy what must outlive it).
         Returns a list of result dicts (ids, lens, logp, atom_idx, n_atoms, edges)."""
-        cur = torch.cuda.current_stream(self.device)
-        if self._pipe_streams is None:
-            # torch: priority -1 = high, 0 = low
-            self._pipe_streams = (torch.cuda.Stream(self.device, priority=0), torch.cuda.Stream(self.device, priority=-1))
-        enc, dec = self._pipe_streams
-        enc.wait_stream(cur)
-        dec.wait_stream(cur)
-        outs, keep = [], []
-
-        def encode_on(x, limit):
-            self._check(self.lib.mnx_set_encoder_cta_limit(self.h, limit), "mnx_set_encoder_cta_limit")
-            with torch.cuda.stream(enc):
-                xd = x if x.is_cuda else x.to(self.device, non_blocking=True)
-                f = self.encode(xd)
-                f.record_stream(dec)
-                ev = torch.cuda.Event()
-                ev.record(enc)
-            keep.append(xd)
-            return f, ev
-
-        it = iter(batches)
-        x = next(it, None)
-        if x is None:
+        batches = list(batches)
+        if not batches:
             return []
+        B0 = max(int(x.shape[0]) for x in batches)
+        H0, W0 = int(batches[0].shape[2]), int(batches[0].shape[3])
+        n_clusters = (B0 + 15) // 16
+        max_cl = int(self.time_kernel(1004, 1))
+        num_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        wide_ok = 0 < n_clusters <= max_cl and self.seq_len(H0, W0) <= 512
+        if not wide_ok:
+            depth = 1
+        elif depth <= 0:
+            # decode and encoder share the SMs: ~44 % of them to `depth` decode kernels balances the two at bs = 32
+            depth = max(1, min(max_cl // n_clusters, int(0.45 * num_sms) // (8 * n_clusters)))
+        depth = min(depth, len(batches))
+        if encoder_ctas <= 0:
+            encoder_ctas = max(16, num_sms - depth * 8 * n_clusters) if wide_ok else 32
+        cur = torch.cuda.current_stream(self.device)
+        if self._pipe_streams is None or len(self._pipe_streams[1]) < depth:
+            # torch: priority -1 = high, 0 = low
+            old = self._pipe_streams[1] if self._pipe_streams else []
+            self._pipe_streams = (self._pipe_streams[0] if self._pipe_streams else torch.cuda.Stream(self.device, priority=0),
+                                  old + [torch.cuda.Stream(self.device, priority=-1) for _ in range(depth - len(old))])
+        enc, decs = self._pipe_streams[0], self._pipe_streams[1][:depth]
+        enc.wait_stream(cur)
+        for d in decs:
+            d.wait_stream(cur)
+        outs, keep = [], []
+        prev_path = self._decode_path
+        if wide_ok:
+            self.reserve_contexts(depth)
+            self.set_decode_path("wide")
         try:
-            item = encode_on(x, 0)                      # nothing else is running yet: every SM
-            while item is not None:
-                f, ev = item
+            for i, x in enumerate(batches):
+                dec = decs[i % depth]
+                # the first encoders find the GPU empty: every SM; later ones share it with `depth` decode kernels
+                self._check(self.lib.mnx_set_encoder_cta_limit(self.h, 0 if i == 0 else encoder_ctas), "mnx_set_encoder_cta_limit")
+                with torch.cuda.stream(enc):
+                    xd = x if x.is_cuda else x.to(self.device, non_blocking=True)
+                    f = self.encode(xd)
+                    f.record_stream(dec)
+                    ev = torch.cuda.Event()
+                    ev.record(enc)
+                keep.append(xd)
                 with torch.cuda.stream(dec):
                     dec.wait_event(ev)
+                    if wide_ok:
+                        self.set_context(i % depth)
                     out = self._decode_all(f)           # asynchronous: one persistent kernel + scan + bond head
-                x = next(it, None)
-                item = encode_on(x, encoder_ctas) if x is not None else None   # overlaps the decode just launched
-                if host:
-                    # D2H into engine-owned pinned buffers (one set per batch of the call, reused by later
-                    # calls: pinned allocation costs tens of milliseconds)
-                    key = (int(f.shape[0]), len(outs))
-                    dst = self._host_pool.get(key)
-                    if dst is None:
-                        dst = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in out.items()}
-                        self._host_pool[key] = dst
-                    with torch.cuda.stream(dec):
+                    if host:
+                        # D2H into engine-owned pinned buffers (one set per batch of the call, reused by later
+                        # calls: pinned allocation costs tens of milliseconds)
+                        key = (int(f.shape[0]), i)
+                        dst = self._host_pool.get(key)
+                        if dst is None:
+                            dst = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in out.items()}
+                            self._host_pool[key] = dst
                         for k, v in out.items():
                             dst[k].copy_(v, non_blocking=True)
-                    keep.append(out)
-                    out = dict(dst)
+                        keep.append(out)
+                        out = dict(dst)
                 outs.append(out)
         finally:
             self.lib.mnx_set_encoder_cta_limit(self.h, 0)
-            cur.wait_stream(dec)
+            if wide_ok:
+                self.lib.mnx_set_context(self.h, 0)
+                self.set_decode_path(prev_path)
+            for d in decs:
+                cur.wait_stream(d)
             cur.wait_stream(enc)
         if host:
-            dec.synchronize()
+            for d in decs:
+                d.synchronize()
         for o in outs:
             for v in o.values():
                 if v.is_cuda:
                     v.record_stream(cur)
         return outs
+
+    # ------------------------------------------------------------------ decode path / contexts
+    DECODE_PATHS = {"auto": 0, "graph": 1, "cluster": 2, "cluster16": 3, "wide": 6}
+
+    def set_decode_path(self, path) -> None:
+        """"auto" (lowest single-batch latency), "graph", "cluster", "cluster16" or "wide" (the throughput kernel:
+        8-CTA clusters of <= 16 rows).  Results are identical on every path."""
+        code = self.DECODE_PATHS[path] if isinstance(path, str) else int(path)
+        self._check(self.lib.mnx_set_decode_path(self.h, code), "mnx_set_decode_path")
+        self._decode_path = code
+
+    def reserve_contexts(self, n: int) -> None:
+        self._check(self.lib.mnx_reserve_contexts(self.h, n), "mnx_reserve_contexts")
+
+    def set_context(self, i: int) -> None:
+        self._check(self.lib.mnx_set_context(self.h, i), "mnx_set_context")
 
     # ------------------------------------------------------------------ introspection
     def launch_count(self) -> int:

@@ -27,7 +27,7 @@ def gather_predictions(local: Dict[str, torch.Tensor], n_total: int, group=None)
     if world == 1:
         return local
     sizes = [shard_bounds(n_total, world, r)[1] - shard_bounds(n_total, world, r)[0] for r in range(world)]
-    mx = max(sizes)
+    mx = max(max(sizes), 1)      # all_gather of zero-element tensors is backend-dependent: keep one padding row
     out = {}
     for k, t in local.items():
         pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
@@ -40,8 +40,18 @@ def gather_predictions(local: Dict[str, torch.Tensor], n_total: int, group=None)
 
 def predict_sharded(engine, images: torch.Tensor, group=None) -> Dict[str, torch.Tensor]:
     """Every rank passes the same global batch (host tensor); each runs its contiguous shard on its own
-    GPU and all ranks receive the full result."""
+    GPU and all ranks receive the full result.
+
+    Every rank enters every collective: a rank whose shard is empty (fewer images than ranks) skips the engine
+    and contributes zero-row tensors (`engine.empty_result()`), and a shard that would exceed the engine's
+    capacity is rejected on ALL ranks before any collective is issued (shard sizes are a function of
+    (n, world) only), so the job fails cleanly instead of hanging in all_gather until the NCCL timeout."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    lo, hi = shard_bounds(images.shape[0], world, rank)
-    local = engine.predict(images[lo:hi].to(engine.device))
-    return gather_predictions(local, images.shape[0], group)
+    n = int(images.shape[0])
+    largest = shard_bounds(n, world, 0)[1] - shard_bounds(n, world, 0)[0]
+    if largest > engine.max_batch:
+        raise ValueError(f"{n} images over {world} ranks gives shards of {largest} rows, above the engine's max_batch "
+                         f"{engine.max_batch}; the caller must chunk (chunk size is part of the semantics: SURVEY.md F3)")
+    lo, hi = shard_bounds(n, world, rank)
+    local = engine.predict(images[lo:hi].to(engine.device)) if hi > lo else engine.empty_result()
+    return gather_predictions(local, n, group)

@@ -14,7 +14,7 @@ from tests.helpers import load_golden, seeded_features
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["cluster16", "cluster", "graph"])
+@pytest.fixture(scope="module", params=["wide", "cluster16", "cluster", "graph"])
 def engines(request):
     """Both decode paths are exercised: the persistent cluster kernel (mega.cu) and the
     multi-kernel CUDA-graph path (decoder.cu) used for batches that do not fit in 16 clusters."""

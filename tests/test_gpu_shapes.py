@@ -13,7 +13,8 @@ from tests.helpers import seeded_features, seeded_images
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("B,path", [(37, "cluster"), (23, "cluster16"), (33, "cluster16"), (37, "graph")])
+@pytest.mark.parametrize("B,path", [(37, "cluster"), (23, "cluster16"), (33, "cluster16"), (37, "graph"),
+                                    (37, "wide"), (32, "wide"), (17, "wide")])
 def test_many_rows_match_oracle(B, path, monkeypatch):
     from molnextr_b200.engine import Engine
     from oracle import restate

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from molnextr_b200.parallel import gather_predictions, shard_bounds
+from molnextr_b200.parallel import gather_predictions, predict_sharded, shard_bounds
 
 
 def test_shard_bounds_cover_everything():
@@ -53,3 +53,60 @@ def test_gather_two_ranks_gloo():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+class _FakeEngine:
+    """Stand-in with the attributes predict_sharded uses; `predict` fails loudly on an empty shard like mnx_encode."""
+    device = torch.device("cpu")
+
+    def __init__(self, max_batch, lo):
+        self.max_batch, self.lo = max_batch, lo
+
+    def predict(self, x):
+        assert x.shape[0] > 0, "engine called with an empty shard"
+        return _fake_local(self.lo, self.lo + x.shape[0])
+
+    def empty_result(self):
+        return _fake_local(0, 0)
+
+
+def _worker_sharded(rank, world, port, n, max_batch, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, _ = shard_bounds(n, world, rank)
+    try:
+        out = predict_sharded(_FakeEngine(max_batch, lo), torch.zeros((n, 3, 4, 4)))
+        ref = _fake_local(0, n)
+        res = all(torch.equal(out[k], ref[k]) for k in ref)
+    except ValueError:
+        res = "rejected"
+    q.put((rank, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run_sharded(n, max_batch):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_sharded, args=(r, 2, port, n, max_batch, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    return res
+
+
+def test_sharded_fewer_images_than_ranks_gloo():
+    """n = 1 on 2 ranks: rank 1 has an empty shard, skips the engine and still enters the all-gather."""
+    assert _run_sharded(1, 8) == [(0, True), (1, True)]
+
+
+def test_sharded_over_capacity_is_rejected_on_every_rank_gloo():
+    """shards of 5 and 4 rows against max_batch = 4: BOTH ranks raise before any collective (no hang)."""
+    assert _run_sharded(9, 4) == [(0, "rejected"), (1, "rejected")]

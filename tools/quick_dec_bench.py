@@ -6,7 +6,7 @@ from tests.helpers import seeded_features
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 ck = {"decoder": synth.decoder_state(0, "fixed480"), "encoder": None}
 eng = Engine(ck, max_batch=B)
-print("max co-resident clusters: 8-CTA", eng.time_kernel(1000, 1), " 16-CTA", eng.time_kernel(1002, 1))
+print("max co-resident clusters: 8-CTA", eng.time_kernel(1000, 1), " 16-CTA", eng.time_kernel(1002, 1), " wide", eng.time_kernel(1004, 1))
 f = seeded_features(1, B, 144).cuda()
 for i in range(2): out = eng.decode_greedy(f)
 torch.cuda.synchronize()
