@@ -181,6 +181,9 @@ int mnx_predict_host(mnx_engine* e, const float* images_host, int32_t B, int32_t
  *                               3 = 16-CTA clusters, 6 = throughput kernel (8-CTA clusters of <= 16 rows: a
  *                               batch of 32 occupies 16 SMs, so ~4-8 batches decode side by side with the
  *                               encoder of the next ones).  Results are identical on every path.
+ *   mnx_set_wide_rows(e, r)     throughput kernel only: rows per 8-CTA cluster (0 = 16).  Fewer rows per cluster spread
+ *                               a batch over more SMs (bs 32: r = 16 -> 16 SMs, 8 -> 32 SMs, 4 -> 64 SMs) and shorten
+ *                               its decode: used for the last batches of a run, when SMs would otherwise idle.
  *   mnx_set_encoder_cta_limit(e, n)  cap the persistent grid of THIS handle's encoder GEMMs at n CTAs
  *                               (0 = one per SM) so that they fit on the SMs running decode kernels leave free
  *                               instead of queueing behind them.
@@ -188,6 +191,7 @@ int mnx_predict_host(mnx_engine* e, const float* images_host, int32_t B, int32_t
 int mnx_reserve_contexts(mnx_engine* e, int32_t n);
 int mnx_set_context(mnx_engine* e, int32_t i);
 int mnx_set_decode_path(mnx_engine* e, int32_t path);
+int mnx_set_wide_rows(mnx_engine* e, int32_t rows);
 int mnx_set_encoder_cta_limit(mnx_engine* e, int32_t n);
 
 /* introspection ------------------------------------------------------------------------ */

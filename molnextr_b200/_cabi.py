@@ -16,7 +16,7 @@ EXPORTS = [
     "mnx_create", "mnx_destroy", "mnx_last_error", "mnx_load_tensor", "mnx_finalize_weights",
     "mnx_preprocess", "mnx_encode", "mnx_decode_greedy", "mnx_decode_beam", "mnx_atom_indices", "mnx_edges", "mnx_predict",
     "mnx_predict_host", "mnx_set_encoder_cta_limit", "mnx_beam_trace", "mnx_launch_count", "mnx_last_decode_steps", "mnx_time_kernel",
-    "mnx_test_gemm_bf16", "mnx_reserve_contexts", "mnx_set_context", "mnx_set_decode_path",
+    "mnx_test_gemm_bf16", "mnx_reserve_contexts", "mnx_set_context", "mnx_set_decode_path", "mnx_set_wide_rows",
 ]
 
 
@@ -61,6 +61,7 @@ def load() -> C.CDLL:
     lib.mnx_reserve_contexts.argtypes = [vp, i32]
     lib.mnx_set_context.argtypes = [vp, i32]
     lib.mnx_set_decode_path.argtypes = [vp, i32]
+    lib.mnx_set_wide_rows.argtypes = [vp, i32]
     lib.mnx_beam_trace.argtypes = [vp, vp, i32]
     lib.mnx_launch_count.argtypes = [vp]
     lib.mnx_launch_count.restype = i64

@@ -100,6 +100,7 @@ struct mnx_engine {
     int max_clusters = 0;
     int decode_path = 0;   // 0 auto, 1 force multi-kernel graph path, 2 force 8-CTA cluster kernel, 3 force 16-CTA cluster kernel,
                            // 6 force the throughput kernel (wide.cu: 8-CTA clusters of <= 16 rows)
+    int wide_rows = 0;             // throughput kernel: rows per cluster (0 = MGW_GMAX_H); fewer rows = more SMs per batch, lower latency
     bool decode_profile = false;   // MNX_DECODE_PROFILE, read once at create
     // decode contexts: complete sets of per-call device buffers, so that several batches can be in flight on
     // different streams (Engine.predict_pipelined).  Context 0 is allocated at finalize; the flat pointer fields
@@ -618,6 +619,12 @@ extern "C" int mnx_set_context(mnx_engine* e, int32_t i) {
     return MNX_OK;
 }
 
+extern "C" int mnx_set_wide_rows(mnx_engine* e, int32_t rows) {
+    if (!e || rows < 0 || rows > MGW_GMAX_H) return fail(e, MNX_ERR_INVALID, "mnx_set_wide_rows: rows must be in [0,%d]", MGW_GMAX_H);
+    e->wide_rows = rows;
+    return MNX_OK;
+}
+
 extern "C" int mnx_set_decode_path(mnx_engine* e, int32_t path) {
     if (!e || (path != 0 && path != 1 && path != 2 && path != 3 && path != 6))
         return fail(e, MNX_ERR_INVALID, "mnx_set_decode_path: path must be 0 (auto), 1 (graph), 2 (cluster8), 3 (cluster16) or 6 (wide)");
@@ -703,7 +710,8 @@ static int decode_internal(mnx_engine* e, const float* features, int B, int S, c
     const bool fits8 = usable8 > 0 && B <= usable8 * MG_GMAX_H;
     if (e->decode_path == 3 && !fits16) return fail(e, MNX_ERR_CAPACITY, "16-CTA cluster path forced but %d rows do not fit %d clusters", B, usable16);
     if (e->decode_path == 2 && !fits8) return fail(e, MNX_ERR_CAPACITY, "8-CTA cluster path forced but %d rows do not fit %d clusters", B, usable8);
-    const int nclw = (B + MGW_GMAX_H - 1) / MGW_GMAX_H;
+    const int growsw = (e->wide_rows > 0 && e->wide_rows < MGW_GMAX_H) ? e->wide_rows : MGW_GMAX_H;
+    const int nclw = (B + growsw - 1) / growsw;
     const bool fitsw = nclw <= e->max_clusters_w && T <= MGW_MAX_KEYS_H + 1 && S <= MGW_MAX_KEYS_H;
     if (e->decode_path == 6 && !fitsw)
         return fail(e, MNX_ERR_CAPACITY, "throughput decode kernel forced but B=%d S=%d T=%d does not fit (%d clusters resident, <= %d keys)",
@@ -999,7 +1007,8 @@ extern "C" int mnx_time_kernel(mnx_engine* e, int32_t which, int32_t iters, floa
         if (e->last_path != 2 && e->last_path != 3 && e->last_path != 5 && e->last_path != 6) return fail(e, MNX_ERR_INVALID, "last decode did not use a cluster kernel");
         const bool use16 = e->last_path == 3, use16s = e->last_path == 5, usew = e->last_path == 6;
         const int B = e->last_B, S = e->last_S, T = e->cfg.max_len;
-        const int usable = usew ? (B + MGW_GMAX_H - 1) / MGW_GMAX_H : use16s ? (e->max_clusters16s < 8 ? e->max_clusters16s : 8)
+        const int growsw = (e->wide_rows > 0 && e->wide_rows < MGW_GMAX_H) ? e->wide_rows : MGW_GMAX_H;
+        const int usable = usew ? (B + growsw - 1) / growsw : use16s ? (e->max_clusters16s < 8 ? e->max_clusters16s : 8)
                                   : use16 ? (e->max_clusters16 < 8 ? e->max_clusters16 : 8) : (e->max_clusters < 16 ? e->max_clusters : 16);
         const int G = (B + usable - 1) / usable, clusters = (B + G - 1) / G;
         MegaArgs a{};

@@ -315,7 +315,7 @@ __device__ __forceinline__ void w_row_gemm_allreduce(WCtx& c, const ulonglong2* 
                 w_send4(c, WSmem::prtT + ((c.h * 8 + c.rg + 4 * rpi) * 16 + c.cg + 8 * cpi) * 16, (uint32_t)c.warp, w_out_unit(acc, cpi, rpi));
     }
     const int cp = c.tid & 15, rp = c.tid >> 4;
-    const float2 b = (c.tid < 128) ? reinterpret_cast<const float2*>(bias)[cp] : make_float2(0.f, 0.f);   // in flight during the wait
+    const float2 b = reinterpret_cast<const float2*>(bias)[cp];   // in flight during the wait
     w_exchange(c, 8u * 32u * W_G * 4u);
     if (c.tid < 128) {
         const float4* prt4 = reinterpret_cast<const float4*>(c.sm + WSmem::prtT) + c.tid;
@@ -402,21 +402,29 @@ __device__ __forceinline__ void w_attend(WCtx& c, int row, const WAtt& d, const 
     float* sc = reinterpret_cast<float*>(c.sm + WSmem::red) + c.warp * 512;
     const int nt = (n + W_TK - 1) / W_TK;
     float m = -INFINITY;
+    // lane j scores key j of a tile, reading its 128-byte row in a lane-rotated order (conflict free); the rotation
+    // does not depend on the tile, so the matching query chunks are loaded once per attention
+    float4 qr[8];
+#pragma unroll
+    for (int cc0 = 0; cc0 < 8; ++cc0) qr[cc0] = q4[(cc0 + c.lane) & 7];
 #pragma unroll 1
     for (int i = 0; i < nt; ++i) {
         const float* tile = w_kv_acquire(c);
         float s = -INFINITY;
         if (i * W_TK + c.lane < n) {
             const float4* kr = reinterpret_cast<const float4*>(tile + c.lane * 32);
-            float s0 = 0.f, s1 = 0.f;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-            for (int cc0 = 0; cc0 < 8; cc0 += 2) {
-                const int ca = (cc0 + c.lane) & 7, cb = (cc0 + 1 + c.lane) & 7;
-                const float4 ka = kr[ca], qa = q4[ca], kb = kr[cb], qb = q4[cb];
+            for (int cc0 = 0; cc0 < 8; cc0 += 4) {
+                const float4 ka = kr[(cc0 + c.lane) & 7], kb = kr[(cc0 + 1 + c.lane) & 7];
+                const float4 kc = kr[(cc0 + 2 + c.lane) & 7], kd = kr[(cc0 + 3 + c.lane) & 7];
+                const float4 qa = qr[cc0], qb = qr[cc0 + 1], qc = qr[cc0 + 2], qd = qr[cc0 + 3];
                 s0 = fmaf(qa.x, ka.x, s0); s0 = fmaf(qa.y, ka.y, s0); s0 = fmaf(qa.z, ka.z, s0); s0 = fmaf(qa.w, ka.w, s0);
                 s1 = fmaf(qb.x, kb.x, s1); s1 = fmaf(qb.y, kb.y, s1); s1 = fmaf(qb.z, kb.z, s1); s1 = fmaf(qb.w, kb.w, s1);
+                s2 = fmaf(qc.x, kc.x, s2); s2 = fmaf(qc.y, kc.y, s2); s2 = fmaf(qc.z, kc.z, s2); s2 = fmaf(qc.w, kc.w, s2);
+                s3 = fmaf(qd.x, kd.x, s3); s3 = fmaf(qd.y, kd.y, s3); s3 = fmaf(qd.z, kd.z, s3); s3 = fmaf(qd.w, kd.w, s3);
             }
-            s = s0 + s1;
+            s = (s0 + s1) + (s2 + s3);
         }
         sc[i * W_TK + c.lane] = s;
         m = fmaxf(m, s);
@@ -660,7 +668,7 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(W_THREADS, 1) decode
                     const float* bias0 = P + ((sub == 0) ? WP_BQ : (sub == 1) ? WP_BQC : WP_B1);
 #pragma unroll 1
                     for (int j = 0; j < ntile; ++j) {
-                        const float2 bias = (c.tid < 128) ? reinterpret_cast<const float2*>(bias0 + j * 32)[c.tid & 15] : make_float2(0.f, 0.f);
+                        const float2 bias = reinterpret_cast<const float2*>(bias0 + j * 32)[c.tid & 15];     // every thread: no branch on the load
                         w_col_tile(c, [&](int cp, int rp, float4 v) {
                             float o[4] = {v.x + bias.x, v.y + bias.y, v.z + bias.x, v.w + bias.y};   // (col, row): (0,0) (1,0) (0,1) (1,1)
                             if (sub == 2) {
@@ -716,7 +724,7 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(W_THREADS, 1) decode
             // ---------- final LayerNorm, vocabulary slice; the logits of row r go to CTA r / 2 ----------
             w_layer_norm(c, a.finalp, a.finalp + 256);
             {
-                const float2 bias = (c.tid < 128) ? reinterpret_cast<const float2*>(a.finalp + 512 + c.h * 32)[c.tid & 15] : make_float2(0.f, 0.f);
+                const float2 bias = reinterpret_cast<const float2*>(a.finalp + 512 + c.h * 32)[c.tid & 15];
                 w_col_tile(c, [&](int cp, int rp, float4 v) {
                     // rows 2rp and 2rp + 1 are both decided by CTA rp
                     const int col = c.h * 32 + 2 * cp;

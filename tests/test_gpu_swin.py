@@ -132,3 +132,22 @@ def test_pipelined_batches_equal_batch_by_batch():
             else:
                 assert torch.equal(r[k], g[k].cpu()) and torch.equal(r[k], h[k]), k
     eng.close()
+
+
+def test_pipelined_contexts_and_tail_spreading():
+    """Several decode contexts in flight (throughput kernel, two clusters per batch) and a partial last wave whose
+    batches are spread over more clusters of fewer rows: still exactly the batch-by-batch results."""
+    from molnextr_b200.engine import Engine
+    ck = synth.synthetic_checkpoint(0, "sensitised")
+    eng = Engine(ck, max_batch=20)
+    xs = [seeded_images(200 + i, 20 if i % 2 == 0 else 17, 384, 384) for i in range(5)]
+    ref = [{k: v.cpu() for k, v in eng.predict(x.cuda()).items()} for x in xs]
+    for depth in (2, 4):        # depth 4: the fifth batch is alone in its wave -> 4 rows per cluster
+        got = eng.predict_pipelined([x.cuda() for x in xs], depth=depth)
+        torch.cuda.synchronize()
+        for r, g in zip(ref, got):
+            assert torch.equal(r["lens"], g["lens"].cpu()) and torch.equal(r["ids"], g["ids"].cpu())
+            assert torch.equal(r["n_atoms"], g["n_atoms"].cpu())
+            for i, n in enumerate(r["n_atoms"].tolist()):
+                assert torch.equal(r["edges"][i][:n, :n], g["edges"][i][:n, :n].cpu())
+    eng.close()
