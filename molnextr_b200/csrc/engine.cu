@@ -12,6 +12,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "decoder.cuh"
@@ -100,6 +101,8 @@ struct mnx_engine {
     int max_clusters = 0;
     int decode_path = 0;   // 0 auto, 1 force multi-kernel graph path, 2 force 8-CTA cluster kernel, 3 force 16-CTA cluster kernel,
                            // 6 force the throughput kernel (wide.cu: 8-CTA clusters of <= 16 rows)
+    bool time_launches = false;    // bench instrumentation: CUDA events around every cluster decode launch (mnx_time_kernel 1005 / 1006)
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> launch_events;
     int wide_rows = 0;             // throughput kernel: rows per cluster (0 = MGW_GMAX_H); fewer rows = more SMs per batch, lower latency
     bool decode_profile = false;   // MNX_DECODE_PROFILE, read once at create
     // decode contexts: complete sets of per-call device buffers, so that several batches can be in flight on
@@ -738,7 +741,16 @@ static int decode_internal(mnx_engine* e, const float* features, int B, int S, c
         a.ids = e->ids; a.logp = e->logp; a.hidden = e->hidden; a.lens = e->lens;
         a.row_state = e->row_state; a.steps_run = e->steps_run_dev; a.g = e->g;
         a.prof = e->decode_profile ? e->prof_dev : nullptr;
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        if (e->time_launches) {
+            CUDA_TRY(e, cudaEventCreate(&ev0)); CUDA_TRY(e, cudaEventCreate(&ev1));
+            CUDA_TRY(e, cudaEventRecord(ev0, s));
+        }
         CUDA_TRY(e, usew ? wide_launch(a, clusters, s) : use16s ? mega16s_launch(a, clusters, s) : use16 ? mega16_launch(a, clusters, s) : mega_launch(a, clusters, s));
+        if (e->time_launches) {
+            CUDA_TRY(e, cudaEventRecord(ev1, s));
+            e->launch_events.emplace_back(ev0, ev1);
+        }
         e->launches += 1;
         e->last_path = usew ? 6 : use16s ? 5 : use16 ? 3 : 2;
         // no host synchronisation: the whole decode is one kernel, so the call is asynchronous like any other
@@ -989,6 +1001,23 @@ extern "C" int mnx_time_kernel(mnx_engine* e, int32_t which, int32_t iters, floa
     if (!e || !ms || iters < 1) return fail(e, MNX_ERR_INVALID, "mnx_time_kernel: bad argument");
     if (which == 1002) { *ms = (float)e->max_clusters16; return MNX_OK; }
     if (which == 1004) { *ms = (float)e->max_clusters_w; return MNX_OK; }
+    if (which == 1006) {   // start (iters = 1) / stop (iters = 2) recording CUDA events around every cluster decode launch
+        e->time_launches = (iters == 1);
+        *ms = 0.f;
+        return MNX_OK;
+    }
+    if (which == 1005) {   // mean device time of the cluster decode launches recorded since the last call (waits for them)
+        double total = 0.0;
+        int n = 0;
+        for (auto& p : e->launch_events) {
+            float t = 0.f;
+            if (cudaEventSynchronize(p.second) == cudaSuccess && cudaEventElapsedTime(&t, p.first, p.second) == cudaSuccess) { total += t; ++n; }
+            cudaEventDestroy(p.first); cudaEventDestroy(p.second);
+        }
+        e->launch_events.clear();
+        *ms = n ? (float)(total / n) : 0.f;
+        return MNX_OK;
+    }
     if (which == 1003) { *ms = (float)e->last_path; return MNX_OK; }
     if (which == 1000) { *ms = (float)e->max_clusters; return MNX_OK; }   // introspection: co-resident 8-CTA clusters
     if (which == 1001) {   // dump the cycle stamps recorded by the last profiled cluster decode (MNX_DECODE_PROFILE=1)

@@ -66,6 +66,7 @@ class Engine:
         self.max_beam = max_beam
         self._host_out: Dict[int, Dict[str, torch.Tensor]] = {}
         self._pipe_streams = None
+        self.last_pipeline: Dict[str, int] = {}
         self._host_pool: Dict[tuple, Dict[str, torch.Tensor]] = {}
         self._decode_path = self.DECODE_PATHS.get(os.environ.get("MNX_DECODE_PATH", "auto"), 0)   # mirrors mnx_create
         enc_sd = checkpoint.get("encoder")
@@ -339,6 +340,8 @@ class Engine:
             old = self._pipe_streams[1] if self._pipe_streams else []
             self._pipe_streams = (self._pipe_streams[0] if self._pipe_streams else torch.cuda.Stream(self.device, priority=0),
                                   old + [torch.cuda.Stream(self.device, priority=-1) for _ in range(depth - len(old))])
+        self.last_pipeline = {"depth": depth, "throughput_kernel": bool(wide_ok), "encoder_ctas": encoder_ctas,
+                              "clusters_per_batch": n_clusters}
         enc, decs = self._pipe_streams[0], self._pipe_streams[1][:depth]
         enc.wait_stream(cur)
         for d in decs:

@@ -1,7 +1,8 @@
-"""Import the reference's OWN modules from /root/reference (read-only, build container only).
+"""Import the reference's OWN modules from /root/reference (read-only, build container) or, on the GPU box,
+from the git-ignored copy staged by oracle/stage_ref.py under baseline/_ref.
 
-Used by oracle/make_golden.py and tests/test_oracle_vs_reference.py to pin oracle/restate.py.
-The GPU box has no /root/reference: nothing that runs there may call into this file.
+Used by oracle/make_golden.py and tests/test_oracle_vs_reference.py to pin oracle/restate.py, and by
+`bench.py --impl reference` (the reference arm).  The GPU tests and smoke() never call into this file.
 
 Recipe: register a stub package object `MolNexTR` whose __path__ is the
 reference package directory (skipping its __init__, which needs pystow/cv2/rdkit), put the
@@ -15,7 +16,10 @@ import sys
 import types
 import warnings
 
-REFERENCE_ROOT = os.environ.get("MOLNEXTR_REFERENCE_ROOT", "/root/reference")
+# /root/reference in the build container; on the GPU box the copy staged by oracle/stage_ref.py (git-ignored)
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+REFERENCE_ROOT = os.environ.get("MOLNEXTR_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isdir("/root/reference/MolNexTR") else _STAGED)
 _SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_shims")
 
 
