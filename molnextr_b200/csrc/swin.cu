@@ -15,6 +15,8 @@
 
 #include "common.cuh"
 #include "encoder.cuh"
+
+#include <cstring>
 #include "gemm_tc.cuh"
 
 namespace mnx {
@@ -28,6 +30,8 @@ struct SwinBlockW {
     const __nv_bfloat16 *qkv_w, *proj_w, *fc1_w, *fc2_w;
     const float *qkv_b, *proj_b, *fc1_b, *fc2_b;
     const float* rpb_t;   // [nH][529] relative position bias table, head-major
+    const uint2* rpb_frag;   // [nH][9 warps][18 key tiles][32 lanes]: bias / scale of the two query rows x two keys a lane
+                            // owns in the QK^T accumulator, as packed bf16 pairs (window_attn_kernel)
 };
 struct SwinMergeW {
     const float *ln_w, *ln_b;
@@ -267,135 +271,149 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(288) window_attn_kernel(const __nv_bfloat16* __restrict__ qkv, int C, int nH,
-                                                          const float* __restrict__ rpb_t, int Hp, int Wp, int shift,
-                                                          __nv_bfloat16* __restrict__ out) {
-    __shared__ __align__(16) __nv_bfloat16 Ks[WIN][40];       // [key][dim], row stride 80 B
-    __shared__ __align__(16) __nv_bfloat16 Vt[32][WIN + 8];   // [dim][key]
-    __shared__ float tab[529];
-    __shared__ uint8_t region[WIN];
-    const int win = blockIdx.x, h = blockIdx.y;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const size_t row0 = (size_t)win * WIN;
-    const int ld = 3 * C;
-    // stage K, V^T, bias table, mask regions
-    for (int i = tid; i < WIN * 4; i += 288) {
-        const int key = i >> 2, c8 = i & 3;
-        const uint4 kv = *reinterpret_cast<const uint4*>(qkv + (row0 + key) * ld + C + h * 32 + c8 * 8);
-        *reinterpret_cast<uint4*>(&Ks[key][c8 * 8]) = kv;
-        const uint4 vv = *reinterpret_cast<const uint4*>(qkv + (row0 + key) * ld + 2 * C + h * 32 + c8 * 8);
-        const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vv);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) Vt[c8 * 8 + e][key] = ve[e];
-    }
-    for (int i = tid; i < 529; i += 288) tab[i] = rpb_t[h * 529 + i];
-    if (tid < WIN) {
-        int reg = 0;
-        if (shift > 0) {
-            const int nww = Wp / WS;
-            const int wi = win % ((Hp / WS) * nww);
-            const int hs = (wi / nww) * WS + tid / WS, wsx = (wi % nww) * WS + tid % WS;
-            const int hid = hs < Hp - WS ? 0 : (hs < Hp - shift ? 1 : 2);
-            const int wid = wsx < Wp - WS ? 0 : (wsx < Wp - shift ? 1 : 2);
-            reg = hid * 3 + wid;
-        }
-        region[tid] = (uint8_t)reg;
-    }
-    __syncthreads();
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(smem_u32(smem_row)));
+}
 
+#define WA_WPC 1            // windows per CTA
+#define WA_SCALE 0.17677669529663687f                       // 32 ** -0.5
+#define WA_SCALE_LOG2E (0.17677669529663687f * 1.4426950408889634f)
+
+// grid (ceil(windows / WA_WPC), heads); 9 warps x 16 query rows.  Per window: K and V rows of the head are staged
+// as they are ([key][32 dims], 80-byte row stride); QK^T accumulators START from the precomputed relative-position
+// bias (divided by the scale, so that softmax((qk + b/s) * s) = softmax(qk * s + b)); the shift mask (-100) is only
+// evaluated for windows that touch the rolled edge; exp2 with the scale folded into the exponent; V^T fragments
+// come from ldmatrix.trans instead of a transposing store.
+__global__ void __launch_bounds__(288, 2) window_attn_kernel(const __nv_bfloat16* __restrict__ qkv, int C, int nH, int n_win,
+                                                          const uint2* __restrict__ rpb_frag, int Hp, int Wp, int shift,
+                                                          __nv_bfloat16* __restrict__ out) {
+    __shared__ __align__(16) __nv_bfloat16 Ks[WIN][40];       // [key][dim], row stride 80 B (conflict-free fragments)
+    __shared__ __align__(16) __nv_bfloat16 Vs[WIN][40];
+    __shared__ uint8_t region[WIN];
+    const int h = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ld = 3 * C;
     const int qr = lane >> 2, qc = (lane & 3) * 2;
     const int i0 = warp * 16 + qr, i1 = i0 + 8;             // the two query rows this thread owns
-    // Q fragments (2 k-steps of 16 dims)
-    uint32_t qa[2][4];
-    {
-        const __nv_bfloat16* q0 = qkv + (row0 + i0) * ld + h * 32;
-        const __nv_bfloat16* q1 = qkv + (row0 + i1) * ld + h * 32;
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-            qa[ks][0] = *reinterpret_cast<const uint32_t*>(q0 + ks * 16 + qc);
-            qa[ks][1] = *reinterpret_cast<const uint32_t*>(q1 + ks * 16 + qc);
-            qa[ks][2] = *reinterpret_cast<const uint32_t*>(q0 + ks * 16 + qc + 8);
-            qa[ks][3] = *reinterpret_cast<const uint32_t*>(q1 + ks * 16 + qc + 8);
+    // bias fragments of this head (L2 resident, 256 contiguous bytes per warp and key tile):
+    // bsrc[nt * 32] = {b(i0, j), b(i0, j+1) | b(i1, j), b(i1, j+1)} / scale as bf16 pairs, j = nt * 8 + qc
+    const uint2* bsrc = rpb_frag + ((size_t)(h * 9 + warp) * 18) * 32 + lane;
+    const int nww = Wp / WS, nwh = Hp / WS;
+#pragma unroll 1
+    for (int wi_ = 0; wi_ < WA_WPC; ++wi_) {
+        const int win = blockIdx.x * WA_WPC + wi_;
+        if (win >= n_win) break;
+        const size_t row0 = (size_t)win * WIN;
+        if (wi_ > 0) __syncthreads();                       // everybody is done with the previous window's K / V
+        for (int i = tid; i < WIN * 4; i += 288) {
+            const int key = i >> 2, c8 = i & 3;
+            *reinterpret_cast<uint4*>(&Ks[key][c8 * 8]) = *reinterpret_cast<const uint4*>(qkv + (row0 + key) * ld + C + h * 32 + c8 * 8);
+            *reinterpret_cast<uint4*>(&Vs[key][c8 * 8]) = *reinterpret_cast<const uint4*>(qkv + (row0 + key) * ld + 2 * C + h * 32 + c8 * 8);
         }
-    }
-    float s[18][4];
-#pragma unroll
-    for (int nt = 0; nt < 18; ++nt) {
-        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Ks[nt * 8 + qr][ks * 16 + qc]);
-            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Ks[nt * 8 + qr][ks * 16 + qc + 8]);
-            mma_bf16_16816(s[nt], qa[ks], b0, b1);
+        // only windows in the last row / column of the rolled map mix regions (transformers.py:220-243)
+        const int wimg = win % (nwh * nww);
+        const bool edge = shift > 0 && (wimg / nww == nwh - 1 || wimg % nww == nww - 1);
+        if (edge && tid < WIN) {
+            const int hs = (wimg / nww) * WS + tid / WS, wsx = (wimg % nww) * WS + tid % WS;
+            const int hid = hs < Hp - WS ? 0 : (hs < Hp - shift ? 1 : 2);
+            const int wid = wsx < Wp - WS ? 0 : (wsx < Wp - shift ? 1 : 2);
+            region[tid] = (uint8_t)(hid * 3 + wid);
         }
-    }
-    // scale, relative position bias, shift mask, softmax (fp32)
-    const float scale = 0.17677669529663687f;   // 32 ** -0.5
-    const int yi0 = i0 / WS, xi0 = i0 % WS, yi1 = i1 / WS, xi1 = i1 % WS;
-    const int r0 = region[i0], r1 = region[i1];
-    float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-    for (int nt = 0; nt < 18; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int j = nt * 8 + qc + e;
-            const int yj = j / WS, xj = j % WS;
-            const int rj = region[j];
-            float v0 = s[nt][e] * scale + tab[(yi0 - yj + WS - 1) * (2 * WS - 1) + (xi0 - xj + WS - 1)];
-            float v1 = s[nt][2 + e] * scale + tab[(yi1 - yj + WS - 1) * (2 * WS - 1) + (xi1 - xj + WS - 1)];
-            if (rj != r0) v0 += -100.0f;
-            if (rj != r1) v1 += -100.0f;
-            s[nt][e] = v0;
-            s[nt][2 + e] = v1;
-            m0 = fmaxf(m0, v0);
-            m1 = fmaxf(m1, v1);
-        }
-    }
-    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-    float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-    for (int nt = 0; nt < 18; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const float p0 = expf(s[nt][e] - m0), p1 = expf(s[nt][2 + e] - m1);
-            s[nt][e] = p0; s[nt][2 + e] = p1;
-            l0 += p0; l1 += p1;
-        }
-    }
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
-    // O = P V : 9 k-steps of 16 keys, 4 n-tiles of 8 dims
-    float o[4][4];
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
-#pragma unroll
-    for (int kk = 0; kk < 9; ++kk) {
-        uint32_t pa[4];
+        // Q fragments (2 k-steps of 16 dims), straight from global memory
+        uint32_t qa[2][4];
         {
-            __nv_bfloat162 t0 = __floats2bfloat162_rn(s[2 * kk][0] * inv0, s[2 * kk][1] * inv0);
-            __nv_bfloat162 t1 = __floats2bfloat162_rn(s[2 * kk][2] * inv1, s[2 * kk][3] * inv1);
-            __nv_bfloat162 t2 = __floats2bfloat162_rn(s[2 * kk + 1][0] * inv0, s[2 * kk + 1][1] * inv0);
-            __nv_bfloat162 t3 = __floats2bfloat162_rn(s[2 * kk + 1][2] * inv1, s[2 * kk + 1][3] * inv1);
-            pa[0] = *reinterpret_cast<uint32_t*>(&t0); pa[1] = *reinterpret_cast<uint32_t*>(&t1);
-            pa[2] = *reinterpret_cast<uint32_t*>(&t2); pa[3] = *reinterpret_cast<uint32_t*>(&t3);
+            const __nv_bfloat16* q0 = qkv + (row0 + i0) * ld + h * 32;
+            const __nv_bfloat16* q1 = qkv + (row0 + i1) * ld + h * 32;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                qa[ks][0] = *reinterpret_cast<const uint32_t*>(q0 + ks * 16 + qc);
+                qa[ks][1] = *reinterpret_cast<const uint32_t*>(q1 + ks * 16 + qc);
+                qa[ks][2] = *reinterpret_cast<const uint32_t*>(q0 + ks * 16 + qc + 8);
+                qa[ks][3] = *reinterpret_cast<const uint32_t*>(q1 + ks * 16 + qc + 8);
+            }
         }
+        __syncthreads();
+        float s[18][4];
+#pragma unroll
+        for (int nt = 0; nt < 18; ++nt) {
+            const uint2 bf = __ldg(bsrc + nt * 32);
+            s[nt][0] = __uint_as_float(bf.x << 16); s[nt][1] = __uint_as_float(bf.x & 0xffff0000u);
+            s[nt][2] = __uint_as_float(bf.y << 16); s[nt][3] = __uint_as_float(bf.y & 0xffff0000u);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Ks[nt * 8 + qr][ks * 16 + qc]);
+                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Ks[nt * 8 + qr][ks * 16 + qc + 8]);
+                mma_bf16_16816(s[nt], qa[ks], b0, b1);
+            }
+        }
+        if (edge) {                                          // CTA-uniform
+            const int r0 = region[i0], r1 = region[i1];
+            const float neg = -100.0f / WA_SCALE;
+#pragma unroll
+            for (int nt = 0; nt < 18; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int rj = region[nt * 8 + qc + e];
+                    if (rj != r0) s[nt][e] += neg;
+                    if (rj != r1) s[nt][2 + e] += neg;
+                }
+            }
+        }
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 18; ++nt) {
+            m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+            m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+        }
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+        const float mb0 = m0 * WA_SCALE_LOG2E, mb1 = m1 * WA_SCALE_LOG2E;
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 18; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const float p0 = exp2f(fmaf(s[nt][e], WA_SCALE_LOG2E, -mb0)), p1 = exp2f(fmaf(s[nt][2 + e], WA_SCALE_LOG2E, -mb1));
+                s[nt][e] = p0; s[nt][2 + e] = p1;
+                l0 += p0; l1 += p1;
+            }
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+        // O = P V : 9 k-steps of 16 keys, 4 n-tiles of 8 dims; V^T fragments via ldmatrix.trans:
+        // lane L supplies the row address of key (L & 15) at dims 8 * (L >> 4) (+16 for the second instruction)
+        float o[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 9; ++kk) {
+            uint32_t pa[4];
+            {
+                __nv_bfloat162 t0 = __floats2bfloat162_rn(s[2 * kk][0] * inv0, s[2 * kk][1] * inv0);
+                __nv_bfloat162 t1 = __floats2bfloat162_rn(s[2 * kk][2] * inv1, s[2 * kk][3] * inv1);
+                __nv_bfloat162 t2 = __floats2bfloat162_rn(s[2 * kk + 1][0] * inv0, s[2 * kk + 1][1] * inv0);
+                __nv_bfloat162 t3 = __floats2bfloat162_rn(s[2 * kk + 1][2] * inv1, s[2 * kk + 1][3] * inv1);
+                pa[0] = *reinterpret_cast<uint32_t*>(&t0); pa[1] = *reinterpret_cast<uint32_t*>(&t1);
+                pa[2] = *reinterpret_cast<uint32_t*>(&t2); pa[3] = *reinterpret_cast<uint32_t*>(&t3);
+            }
+            uint32_t vb[2][4];      // vb[p] = {b0, b1 of dims 16p..16p+7, b0, b1 of dims 16p+8..16p+15}
+#pragma unroll
+            for (int p2 = 0; p2 < 2; ++p2) ldmatrix_x4_trans(vb[p2], &Vs[kk * 16 + (lane & 15)][16 * p2 + 8 * (lane >> 4)]);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(o[nt], pa, vb[nt >> 1][(nt & 1) * 2], vb[nt >> 1][(nt & 1) * 2 + 1]);
+        }
+        __nv_bfloat16* o0 = out + (row0 + i0) * C + h * 32;
+        __nv_bfloat16* o1 = out + (row0 + i1) * C + h * 32;
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
-            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Vt[nt * 8 + qr][kk * 16 + qc]);
-            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Vt[nt * 8 + qr][kk * 16 + qc + 8]);
-            mma_bf16_16816(o[nt], pa, b0, b1);
+            __nv_bfloat162 a2 = __floats2bfloat162_rn(o[nt][0], o[nt][1]);
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(o[nt][2], o[nt][3]);
+            *reinterpret_cast<__nv_bfloat162*>(o0 + nt * 8 + qc) = a2;
+            *reinterpret_cast<__nv_bfloat162*>(o1 + nt * 8 + qc) = b2;
         }
-    }
-    __nv_bfloat16* o0 = out + (row0 + i0) * C + h * 32;
-    __nv_bfloat16* o1 = out + (row0 + i1) * C + h * 32;
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-        __nv_bfloat162 a = __floats2bfloat162_rn(o[nt][0], o[nt][1]);
-        __nv_bfloat162 b = __floats2bfloat162_rn(o[nt][2], o[nt][3]);
-        *reinterpret_cast<__nv_bfloat162*>(o0 + nt * 8 + qc) = a;
-        *reinterpret_cast<__nv_bfloat162*>(o1 + nt * 8 + qc) = b;
     }
 }
 
@@ -473,6 +491,24 @@ int swin_finalize(mnx_engine* e, SwinState** out, const mnx_config& cfg) {
             for (int i = 0; i < 529; ++i)
                 for (int hh = 0; hh < nH; ++hh) tt[(size_t)hh * 529 + i] = (*tab)[(size_t)i * nH + hh];
             SW_CUDA(e, mnx_upload(e, tt, &w.rpb_t));
+            {   // accumulator-fragment order of window_attn_kernel, bias / scale, packed bf16 pairs
+                std::vector<uint32_t> fr((size_t)nH * 9 * 18 * 32 * 2);
+                auto bf16_bits = [](float v) { __nv_bfloat16 b = __float2bfloat16_rn(v); uint16_t u; memcpy(&u, &b, 2); return (uint32_t)u; };
+                const float inv_scale = 1.0f / 0.17677669529663687f;
+                for (int hh = 0; hh < nH; ++hh)
+                    for (int wp = 0; wp < 9; ++wp)
+                        for (int nt = 0; nt < 18; ++nt)
+                            for (int ln = 0; ln < 32; ++ln) {
+                                const int qi0 = wp * 16 + (ln >> 2), qi1 = qi0 + 8, jj = nt * 8 + (ln & 3) * 2;
+                                auto bias = [&](int i, int j) { return tt[(size_t)hh * 529 + ref_idx[i * WIN + j]] * inv_scale; };
+                                const size_t o = ((((size_t)hh * 9 + wp) * 18 + nt) * 32 + ln) * 2;
+                                fr[o] = bf16_bits(bias(qi0, jj)) | (bf16_bits(bias(qi0, jj + 1)) << 16);
+                                fr[o + 1] = bf16_bits(bias(qi1, jj)) | (bf16_bits(bias(qi1, jj + 1)) << 16);
+                            }
+                void* dptr = nullptr;
+                SW_CUDA(e, mnx_upload_raw(e, fr.data(), fr.size() * 4, &dptr));
+                w.rpb_frag = reinterpret_cast<const uint2*>(dptr);
+            }
             const std::vector<int64_t>* idx = mnx_need_i64(e, B + "attn.relative_position_index", {WIN, WIN});
             if (!idx) return MNX_ERR_WEIGHTS;
             if (*idx != ref_idx) {
@@ -551,7 +587,8 @@ int swin_forward(mnx_engine* e, SwinState* st, const float* images, int B, int H
             ln_rows_kernel<true><<<(unsigned)((Mw + 7) / 8), 256, 0, s>>>(x, map0, Mw, C, w.ln1_w, w.ln1_b, 1e-5f, st->abuf);
             SW_CUDA(e, cudaGetLastError()); ++nl;
             SW_CUDA(e, gemm(st->abuf, w.qkv_w, Mw, 3 * C, C, GEMM_EPI_BF16, w.qkv_b, nullptr, st->qkv, s, st->cta_limit)); ++nl;
-            window_attn_kernel<<<dim3((unsigned)(Mw / WIN), nH), 288, 0, s>>>(st->qkv, C, nH, w.rpb_t, Hp, Wp, shift, st->attn);
+            window_attn_kernel<<<dim3((unsigned)((Mw / WIN + WA_WPC - 1) / WA_WPC), nH), 288, 0, s>>>(st->qkv, C, nH, (int)(Mw / WIN), w.rpb_frag, Hp,
+                                                                                                        Wp, shift, st->attn);
             SW_CUDA(e, cudaGetLastError()); ++nl;
             // proj + window_reverse + un-roll + crop + residual
             SW_CUDA(e, gemm(st->attn, w.proj_w, Mw, C, C, GEMM_EPI_RESADD_F32, w.proj_b, map0, x, s, st->cta_limit)); ++nl;

@@ -68,6 +68,10 @@ class molnextr:
     def predict_images(self, input_images: List, return_atoms_bonds=False, return_confidence=False, batch_size=16):
         predictions = []
         self.decoder.compute_confidence = return_confidence
+        if batch_size > self.engine.max_batch:
+            # not re-chunked silently: the chunk size is part of the semantics (row-rank positional encoding)
+            raise ValueError(f"batch_size {batch_size} exceeds this model's engine capacity (max_batch={self.engine.max_batch}); "
+                             f"construct molnextr(..., max_batch={batch_size})")
         # the reference's chunking is part of its semantics: the positional encoding of a row depends on
         # its rank inside its mini-batch, so chunks of `batch_size` are kept as is
         for idx in range(0, len(input_images), batch_size):

@@ -138,6 +138,33 @@ def make_decoder_only(name, seed, b, s):
     print(name, "lens", out["lens"].tolist(), "atoms", out["natoms"].tolist())
 
 
+def make_confidence(name, seed, b, s):
+    """Decoder.decode with compute_confidence=True (components.py:456-469,485-491): per-atom geometric-mean token
+    score, symmetrised edge scores, overall score = average token score * sqrt(prod(edge scores))."""
+    ck = synth.synthetic_checkpoint(seed, "sensitised")
+    _, dec, tok = ref_loader.build_reference(ck, compute_confidence=True)
+    feats = seeded_features(3000 + seed, b, s)
+    with torch.no_grad():
+        preds = dec.decode(feats, None)
+    kmax = max([len(p["edges"]) for p in preds] + [1])
+    natoms = np.array([len(p["edges"]) for p in preds], np.int32)
+    atom_scores = np.zeros((b, kmax), np.float64)
+    edge_scores = np.zeros((b, kmax, kmax), np.float64)
+    overall = np.zeros((b,), np.float64)
+    for i, p in enumerate(preds):
+        k = natoms[i]
+        assert "average_token_score" not in p["chartok_coords"]
+        atom_scores[i, :k] = p["chartok_coords"]["atom_scores"]
+        if k:
+            edge_scores[i, :k, :k] = np.asarray(p["edge_scores"], np.float64)
+        overall[i] = p["overall_score"]
+    smiles = [p["chartok_coords"]["smiles"] for p in preds]
+    np.savez_compressed(os.path.join(GOLDEN, name), natoms=natoms, atom_scores=atom_scores, edge_scores=edge_scores,
+                        overall_score=overall, meta=np.array(json.dumps(dict(smiles=smiles))),
+                        cfg=np.array(json.dumps(dict(ckpt_seed=seed, variant="sensitised", feat_seed=3000 + seed, b=b, s=s))))
+    print(name, "atoms", natoms.tolist(), "overall", overall.tolist())
+
+
 def make_tokenizer_and_edges(name):
     ck = synth.synthetic_checkpoint(0, "sensitised")
     _, dec, tok = ref_loader.build_reference(ck)
@@ -174,6 +201,7 @@ def main():
     make_decoder_only("decoder_b3_s64.npz", seed=1, b=3, s=64)
     make_swin_e2e("swin_b4_384.npz", seed=0, b=4, h=384, w=384)
     make_swin_e2e("swin_b1_408x424.npz", seed=2, b=1, h=408, w=424)
+    make_confidence("confidence_b5_s144.npz", seed=0, b=5, s=144)
 
 
 if __name__ == "__main__":

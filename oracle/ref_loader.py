@@ -54,14 +54,15 @@ def reference_args(encoder: str = "swin_base", **over):
     return ns
 
 
-def build_reference(ckpt: dict):
+def build_reference(ckpt: dict, **over):
     """(encoder, decoder, tokenizer) built by the reference's constructors and loaded the way
-    molnextr._get_model does (MolNexTR/model.py:83-95), but with strict=True."""
+    molnextr._get_model does (MolNexTR/model.py:83-95), but with strict=True.  `over` overrides
+    fields of the argument namespace (e.g. compute_confidence=True)."""
     _install()
     warnings.filterwarnings("ignore")
     from MolNexTR.components import Encoder, Decoder  # noqa
     from MolNexTR.tokenization import get_tokenizer  # noqa
-    args = reference_args()
+    args = reference_args(**over)
     for k, v in ckpt["args"].items():
         setattr(args, k, v)
     tokenizer = get_tokenizer(args)

@@ -539,13 +539,11 @@ def edge_probabilities(dec_sd: SD, hidden: torch.Tensor, indices: Sequence[int])
     return F.softmax(y, dim=2)
 
 
-def get_edge_prediction(prob: np.ndarray):
-    """get_edge_prediction (components.py:383-400) in double precision, as the reference runs
-    it on Python floats obtained from `.tolist()`.  The 5/6 rule reads edge_prob[i][j][5]
+def symmetrised_edge_probabilities(prob: np.ndarray) -> np.ndarray:
+    """The in-place symmetrisation of get_edge_prediction (components.py:389-397) in double precision, as the
+    reference runs it on Python floats obtained from `.tolist()`.  The 5/6 rule reads edge_prob[i][j][5]
     AFTER it was overwritten, exactly as the reference does."""
     n = prob.shape[0]
-    if n == 0:
-        return [], []
     p = prob.astype(np.float64).copy()
     for i in range(n):
         for j in range(i + 1, n):
@@ -556,6 +554,14 @@ def get_edge_prediction(prob: np.ndarray):
             p[i, j, 6] = (p[i, j, 6] + p[j, i, 5]) / 2
             p[j, i, 5] = p[i, j, 6]
             p[j, i, 6] = p[i, j, 5]
+    return p
+
+
+def get_edge_prediction(prob: np.ndarray):
+    """get_edge_prediction (components.py:383-400): symmetrise, then argmax / max per atom pair."""
+    if prob.shape[0] == 0:
+        return [], []
+    p = symmetrised_edge_probabilities(prob)
     return np.argmax(p, axis=2).tolist(), np.max(p, axis=2).tolist()
 
 

@@ -29,6 +29,31 @@ def test_decoder_decode_reproduces_reference_prediction_dicts():
     eng.close()
 
 
+def test_confidence_values_match_reference_fixture():
+    """compute_confidence=True (components.py:456-469,485-491): per-atom geometric-mean token scores, symmetrised edge
+    scores and the overall score against values the reference itself produced (oracle/make_golden.make_confidence)."""
+    from molnextr_b200.components import Decoder
+    from molnextr_b200.engine import Engine
+    g = load_golden("confidence_b5_s144.npz")
+    cfg = g["cfg"]
+    eng = Engine({"decoder": synth.decoder_state(cfg["ckpt_seed"], cfg["variant"]), "encoder": None}, max_batch=cfg["b"])
+    feats = seeded_features(cfg["feat_seed"], cfg["b"], cfg["s"]).cuda()
+    preds = Decoder(eng, compute_confidence=True).decode(feats, None)
+    assert [p["chartok_coords"]["smiles"] for p in preds] == g["meta"]["smiles"]
+    for i, p in enumerate(preds):
+        k = int(g["natoms"][i])
+        assert len(p["edges"]) == k and "average_token_score" not in p["chartok_coords"]
+        np.testing.assert_allclose(p["chartok_coords"]["atom_scores"], g["atom_scores"][i, :k], rtol=2e-4, atol=1e-7)
+        np.testing.assert_allclose(np.asarray(p["edge_scores"]), g["edge_scores"][i, :k, :k], rtol=0, atol=2e-5)
+        want = float(g["overall_score"][i])
+        # a product of k*k edge scores (up to 25 000 factors, often underflowing): compare in the log domain
+        if want == 0.0:
+            assert p["overall_score"] < 1e-250
+        else:
+            assert abs(np.log(p["overall_score"]) - np.log(want)) <= 1e-6 * k * k + 1e-3
+    eng.close()
+
+
 def test_molnextr_predict_images_schema():
     from molnextr_b200.model import molnextr
     ck = synth.synthetic_checkpoint(0, "sensitised")

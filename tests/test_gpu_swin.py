@@ -17,6 +17,7 @@ from tests.helpers import load_golden, seeded_images
 
 pytestmark = pytest.mark.gpu
 FEAT_MAX_TOL, FEAT_MEAN_TOL, LOGP_TOL = 0.12, 0.012, 0.15
+EDGE_GAP_TOL = 0.08   # symmetrised bond-class probability margin below which bf16 feature noise may flip a class
 
 
 @pytest.fixture(scope="module")
@@ -100,8 +101,19 @@ def test_predict_end_to_end_vs_reference_fixture(engine_cache):
             k = int(g["natoms"][i])
             assert int(out["n_atoms"][i]) == k
             assert out["atom_idx"][i, :k].cpu().tolist() == g["atom_idx"][i, :k].tolist()
-            frac = float((out["edges"][i, :k, :k].cpu().numpy().astype(np.int8) == g["edges"][i, :k, :k]).mean()) if k else 1.0
-            print(f"row {i}: ids exact, {frac:.4f} of bond classes match"); assert frac >= 0.90, f"row {i}: only {frac:.3f} of bond classes match"
+            # the bond head reads decoder hidden states computed from bf16-GEMM encoder features: a bond class may flip
+            # only where the reference's own symmetrised probabilities are a near-tie (top-2 gap <= EDGE_GAP_TOL)
+            got_e = out["edges"][i, :k, :k].cpu().numpy().astype(np.int8)
+            mism = np.argwhere(got_e != g["edges"][i, :k, :k])
+            frac = 1.0 - len(mism) / max(1, k * k)
+            if len(mism):
+                hid = raw[i]["hidden"]
+                prob = restate.edge_probabilities(ck["decoder"], hid, g["atom_idx"][i, :k].tolist()).numpy()
+                top2 = np.sort(restate.symmetrised_edge_probabilities(prob), axis=2)[:, :, -2:]
+                gaps = np.array([top2[a, b, 1] - top2[a, b, 0] for a, b in mism])
+                print(f"row {i}: ids exact, {len(mism)} of {k * k} bond classes differ, reference top-2 gaps max {gaps.max():.4f}")
+                assert gaps.max() <= EDGE_GAP_TOL, f"row {i}: a bond class differs where the reference margin is {gaps.max():.3f}"
+            assert frac >= 0.97, f"row {i}: only {frac:.3f} of bond classes match"
         else:
             m = np.nonzero(ids[i, :L] != g["ids"][i, :L])[0]
             t = int(m[0]) if len(m) else min(L, int(lens[i]))
