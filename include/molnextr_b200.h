@@ -22,6 +22,9 @@
  *                             ConvNeXt-B: timm forward_features, components.py:121-126)
  *   mnx_decode_greedy     <- TransformerDecoderAR.decode + GreedySearch
  *                            MolNexTR/components.py:253-334, MolNexTR/decoding/greedy_search.py:33-128
+ *   mnx_decode_greedy_labels <- TransformerDecoderAR.decode(..., labels=...) "partial prediction"
+ *                            MolNexTR/components.py:286-289,305,317-318,326-332,
+ *                            MolNexTR/decoding/greedy_search.py:83-85
  *   mnx_decode_beam       <- TransformerDecoderAR.decode + BeamSearch (repaired; see below)
  *                            MolNexTR/components.py:253-334, MolNexTR/decoding/beam_search.py:84-190
  *   mnx_atom_indices      <- CharTokenizer.sequence_to_smiles (the `indices` output only)
@@ -122,6 +125,23 @@ int mnx_encode(mnx_engine* e, const float* images, int32_t B, int32_t H, int32_t
 int mnx_decode_greedy(mnx_engine* e, const float* features, int32_t B, int32_t S,
                       int32_t* ids, int32_t* lens, float* token_logp, float* hidden,
                       void* cuda_stream);
+
+/* Greedy decode with part of every sequence GIVEN ("partial prediction", components.py:256-257).
+ * labels int32 (B, n_labels), device memory: column 0 is <sos>; a position holding MASK_ID (4,
+ * tokenization.py:13) is left to the model, any other value is teacher-forced as the INPUT of
+ * that step (components.py:286-289) and keys the grammar mask (:301-303); a row finishes when
+ * its NEXT label is <eos> (greedy_search.py:83-85; the model's own <eos> ends it only beyond the
+ * labels) or at max_len.  Rows leave the batch as in mnx_decode_greedy (row-rank PE rule); labels
+ * are addressed by original row, which is what labels.index_select (:317-318) keeps true in the
+ * reference.  On return ids/lens hold the merged result of :326-332:
+ *   lens[i] = min(len(pred_i), n_labels - 1), ids[i][j] = labels[i][1+j] unless that is MASK_ID;
+ * token_logp / hidden keep the model's own picks over the full decoded length, as in the reference.
+ * MNX_ERR_INVALID if the decode runs more steps than labels has columns (the reference raises
+ * IndexError at components.py:287).  Runs on the multi-kernel path, context 0. */
+int mnx_decode_greedy_labels(mnx_engine* e, const float* features, int32_t B, int32_t S,
+                             const int32_t* labels, int32_t n_labels,
+                             int32_t* ids, int32_t* lens, float* token_logp, float* hidden,
+                             void* cuda_stream);
 
 /* Beam-search decode of B images with `beam` hypotheses each (n_best <= beam returned, best first).
  * Replaces TransformerDecoderAR.decode with BeamSearch (MolNexTR/components.py:253-334,

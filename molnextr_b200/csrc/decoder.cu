@@ -24,6 +24,17 @@ namespace mnx {
 // embed + compaction  (GreedySearch.update_finished compaction, greedy_search.py:119-127;
 // Embeddings / PositionalEncoding with the row-rank rule, models/embedding.py:42-61)
 // =====================================================================================
+// input token of step t for an original row: the previous pick, unless a label is given for this position
+// (tgt = tgt * mask + label * (1 - mask), components.py:286-289)
+__device__ __forceinline__ int input_token(const DecBuffers& b, const Grammar& g, int lab_len, int row, int t) {
+    int tok = (t == 0) ? g.sos : b.cur_tok[row];
+    if (t < lab_len) {
+        const int lab = b.labels[(size_t)row * (b.T + 1) + t];
+        if (lab != MNX_MASK_ID) tok = lab;
+    }
+    return tok;
+}
+
 __global__ void __launch_bounds__(1024) embed_compact_kernel(DecBuffers b, DecWeights w, Grammar g) {
     __shared__ int warp_cnt[32];
     __shared__ int warp_excl[32];
@@ -71,11 +82,12 @@ __global__ void __launch_bounds__(1024) embed_compact_kernel(DecBuffers b, DecWe
         if (n == 0) st->done = 1; else st->steps_run = t + 1;
     }
     __syncthreads();   // cur[] complete before it is read below
+    const int lab_len = st->lab_len;
     // x[rank] = emb[tok] * sqrt(256) + pe[rank]      (row-rank rule)
     for (int idx = tid; idx < n * MNX_DEC_D; idx += 1024) {
         const int rank = idx >> 8, d = idx & 255;
         const int row = cur[rank];
-        const int tok = (t == 0) ? g.sos : b.cur_tok[row];
+        const int tok = input_token(b, g, lab_len, row, t);
         b.xa[idx] = w.emb[tok * MNX_DEC_D + d] * 16.0f + w.pe[rank * MNX_DEC_D + d];
     }
 }
@@ -637,7 +649,8 @@ __global__ void __launch_bounds__(1024) pick_kernel(DecBuffers b, DecWeights w, 
     for (int i = 0; i < 8; ++i) se += redf[i];
     float lp = (logit - m) - logf(se);
     // grammar mask keyed on the INPUT token of this step (tokenization.py:383-392)
-    const int tok_in = (t == 0) ? g.sos : b.cur_tok[row];
+    const int lab_len = BEAM ? 0 : b.st->lab_len;
+    const int tok_in = input_token(b, g, lab_len, row, t);
     const bool in_x = tok_in >= g.offset && tok_in < g.offset + g.maxx;
     const bool in_y = tok_in >= g.offset + g.maxx;
     if (in_x && tid < g.offset + g.maxx) lp = -10000.0f;
@@ -670,7 +683,10 @@ __global__ void __launch_bounds__(1024) pick_kernel(DecBuffers b, DecWeights w, 
         b.ids[(size_t)row * b.T + t] = ix;
         b.logp[(size_t)row * b.T + t] = v;
         b.cur_tok[row] = ix;
-        const int fin = (ix == g.eos) || (t == g.max_len - 1);
+        // with labels the NEXT given token decides (greedy_search.py:83-85: is_finished = label.eq(eos)); the stored id
+        // stays the model's pick (alive_seq, :86) until label_merge_kernel
+        const int ends = (t + 1 < lab_len) ? b.labels[(size_t)row * (b.T + 1) + t + 1] : ix;
+        const int fin = (ends == g.eos) || (t == g.max_len - 1);
         b.finished[row] = fin;
         if (fin) b.lens[row] = t + 1;
     }
@@ -1077,6 +1093,39 @@ static cudaError_t configure_skinny() {
 }
 
 // opt in to >48 KB dynamic shared memory on the current device (call once per device)
+// =====================================================================================
+// partial-label decoding: arm the labels, and the final merge of components.py:326-332
+//   label = orig_labels[i][1:len(pred)+1]; pred = pred[:len(label)]; pred = pred*mask + label*(1-mask)
+// =====================================================================================
+__global__ void set_label_len_kernel(DecState* st, int lab_len) { st->lab_len = lab_len; }
+
+__global__ void __launch_bounds__(256) label_merge_kernel(DecBuffers b, int lab_len) {
+    const int row = blockIdx.x;
+    const int n = b.lens[row];
+    const int keep = min(n, lab_len - 1);
+    for (int j = threadIdx.x; j < b.T; j += 256) {
+        int v = b.ids[(size_t)row * b.T + j];
+        if (j < keep) {
+            const int lab = b.labels[(size_t)row * (b.T + 1) + 1 + j];
+            if (lab != MNX_MASK_ID) v = lab;
+        } else {
+            v = 0;
+        }
+        b.ids[(size_t)row * b.T + j] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) b.lens[row] = keep;
+}
+
+cudaError_t dec_set_label_len(const DecBuffers& b, int lab_len, cudaStream_t s) {
+    set_label_len_kernel<<<1, 1, 0, s>>>(b.st, lab_len);
+    return cudaGetLastError();
+}
+cudaError_t dec_label_merge(const DecBuffers& b, int lab_len, cudaStream_t s) {
+    label_merge_kernel<<<b.B, 256, 0, s>>>(b, lab_len);
+    return cudaGetLastError();
+}
+
 cudaError_t dec_configure() {
     cudaError_t e;
     if ((e = configure_skinny<256, PRO_LN, EPI_QKV>()) != cudaSuccess) return e;

@@ -36,6 +36,7 @@ struct DecState {
     int done;        // 1 once every row has finished
     int steps_run;   // number of steps that had at least one alive row
     int n_img;       // beam search: images alive in the step being executed (n_alive = n_img * beam)
+    int lab_len;     // partial-label decoding (components.py:286-289): columns of DecBuffers::labels in use, 0 = none
 };
 
 struct DecBuffers {
@@ -60,7 +61,12 @@ struct DecBuffers {
     int* lens;         // [B]
     float* logp;       // [B][T]
     float* hidden;     // [B][T][256]
+    // partial-label decoding (TransformerDecoderAR.decode(labels=...), components.py:286-289,305,326-332): given
+    // tokens by ORIGINAL row (so the reference's labels.index_select on compaction, :317-318, is implicit);
+    // MNX_MASK_ID = position left to the model.  Read only while st->lab_len > 0.
+    const int* labels; // [B][T+1]
 };
+#define MNX_MASK_ID 4   // tokenization.py:13
 
 // Beam-search state (decoding/beam_search.py, repaired as described in oracle/restate.py
 // beam_decode).  A *slot* is a physical decoder row: slot = image * beam + k.  Hypotheses move

@@ -22,6 +22,8 @@
 namespace mnx {
 // decoder.cu
 cudaError_t dec_configure();
+cudaError_t dec_set_label_len(const DecBuffers& b, int lab_len, cudaStream_t s);
+cudaError_t dec_label_merge(const DecBuffers& b, int lab_len, cudaStream_t s);
 int dec_launch_step(const DecBuffers& b, const DecWeights& w, const Grammar& g, const BeamBuffers* bm, cudaStream_t s,
                     cudaError_t* err);
 cudaError_t dec_beam_init(const DecBuffers& b, const BeamBuffers& bm, cudaStream_t s);
@@ -85,6 +87,7 @@ struct mnx_engine {
     // decoder workspaces (sized for max_batch / S_max / max_len)
     DecState* st = nullptr;
     int *alive = nullptr, *cur_tok = nullptr, *finished = nullptr;
+    int* labels = nullptr;   // [max_batch][max_len + 1] given tokens of a partial-label decode (context 0, graph path)
     float *xa = nullptr, *xb = nullptr, *q = nullptr, *part = nullptr, *part2 = nullptr, *hbuf = nullptr;
     float *selfK = nullptr, *selfV = nullptr, *crossK = nullptr, *crossV = nullptr, *membank = nullptr;
     int *ids = nullptr, *lens = nullptr;
@@ -155,6 +158,21 @@ static int fail(mnx_engine* e, int code, const char* fmt, ...) {
         if (_c != cudaSuccess)                                                                 \
             return fail(e, MNX_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(_c), __FILE__, __LINE__); \
     } while (0)
+
+// Entry points run on the engine's device and put the caller's current device back on return (a process that drives
+// several engines, or torch on another GPU, keeps its own current device).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err;
+    explicit DeviceGuard(int dev) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev); else if (err == cudaSuccess) prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ON_ENGINE_DEVICE(e)                 \
+    DeviceGuard _dev_guard((e)->cfg.device); \
+    CUDA_TRY(e, _dev_guard.err)
 
 template <typename T>
 static cudaError_t dev_alloc(mnx_engine* e, T** p, size_t count) {
@@ -229,7 +247,8 @@ extern "C" int mnx_create(const mnx_config* cfg, mnx_engine** out) {
         return fail(nullptr, MNX_ERR_INVALID, "image bound gives %d memory positions; supported range is [1,%d]", hs * ws,
                     ATTN_MAXKEYS_HOST);
     }
-    cudaError_t c = cudaSetDevice(cfg->device);
+    DeviceGuard guard(cfg->device);
+    cudaError_t c = guard.err;
     if (c == cudaSuccess) c = dec_configure();
     if (c == cudaSuccess) c = mega_configure(&e->max_clusters);
     if (c == cudaSuccess) c = mega16_configure(&e->max_clusters16);
@@ -256,7 +275,7 @@ extern "C" int mnx_create(const mnx_config* cfg, mnx_engine** out) {
 
 extern "C" int mnx_destroy(mnx_engine* e) {
     if (!e) return MNX_OK;
-    cudaSetDevice(e->cfg.device);
+    DeviceGuard guard(e->cfg.device);
     cudaDeviceSynchronize();
     if (e->graph) cudaGraphExecDestroy(e->graph);
     if (e->graph_beam) cudaGraphExecDestroy(e->graph_beam);
@@ -570,6 +589,7 @@ static int alloc_workspaces(mnx_engine* e) {
     e->ctxs.assign(1, capture_context(e));
     e->cur_ctx = 0;
     e->edge_hidden = e->hidden;
+    CUDA_TRY(e, dev_alloc(e, &e->labels, B * (T + 1)));
     if (e->cfg.max_beam > 1) {
         BeamBuffers& m = e->bm;
         CUDA_TRY(e, dev_alloc(e, &m.alive_img, 2 * B));
@@ -604,7 +624,7 @@ static int alloc_workspaces(mnx_engine* e) {
 extern "C" int mnx_reserve_contexts(mnx_engine* e, int32_t n) {
     if (!e || n < 1 || n > 64) return fail(e, MNX_ERR_INVALID, "mnx_reserve_contexts: n must be in [1,64]");
     if (!e->finalized) return fail(e, MNX_ERR_INVALID, "weights not finalized");
-    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    ON_ENGINE_DEVICE(e);
     const CtxPtrs cur = capture_context(e);
     while ((int)e->ctxs.size() < n) {
         int rc = alloc_context(e, e->cfg.max_batch);
@@ -638,7 +658,7 @@ extern "C" int mnx_set_decode_path(mnx_engine* e, int32_t path) {
 extern "C" int mnx_finalize_weights(mnx_engine* e) {
     if (!e) return MNX_ERR_INVALID;
     if (e->finalized) return fail(e, MNX_ERR_INVALID, "weights already finalized");
-    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    ON_ENGINE_DEVICE(e);
     int rc = finalize_decoder(e);
     if (rc != MNX_OK) return rc;
     if (e->cfg.encoder_kind != MNX_ENCODER_NONE) {
@@ -662,6 +682,7 @@ static DecBuffers make_buffers(mnx_engine* e, int B, int S) {
     b.selfK = e->selfK; b.selfV = e->selfV; b.crossK = e->crossK; b.crossV = e->crossV; b.membank = e->membank;
     b.B = B; b.S = S; b.T = e->cfg.max_len;
     b.ids = e->ids; b.lens = e->lens; b.logp = e->logp; b.hidden = e->hidden;
+    b.labels = e->labels;
     return b;
 }
 
@@ -687,11 +708,12 @@ static int ensure_graph(mnx_engine* e, const DecBuffers& b) {
     return MNX_OK;
 }
 
-static int decode_internal(mnx_engine* e, const float* features, int B, int S, cudaStream_t s) {
+static int decode_internal(mnx_engine* e, const float* features, int B, int S, cudaStream_t s, const int32_t* labels = nullptr,
+                           int n_labels = 0) {
     if (!e->finalized) return fail(e, MNX_ERR_INVALID, "weights not finalized");
     if (B < 1 || B > e->cfg.max_batch) return fail(e, MNX_ERR_CAPACITY, "batch %d exceeds max_batch %d", B, e->cfg.max_batch);
     if (S < 1 || S > e->S_max) return fail(e, MNX_ERR_CAPACITY, "memory length %d exceeds capacity %d", S, e->S_max);
-    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    ON_ENGINE_DEVICE(e);
     DecBuffers b = make_buffers(e, B, S);
     const int T = e->cfg.max_len;
     e->edge_hidden = e->hidden;
@@ -719,9 +741,10 @@ static int decode_internal(mnx_engine* e, const float* features, int B, int S, c
     if (e->decode_path == 6 && !fitsw)
         return fail(e, MNX_ERR_CAPACITY, "throughput decode kernel forced but B=%d S=%d T=%d does not fit (%d clusters resident, <= %d keys)",
                     B, S, T, e->max_clusters_w, MGW_MAX_KEYS_H);
-    const bool usew = e->decode_path == 6;
-    const bool use16 = !usew && ((e->decode_path == 3) || (e->decode_path == 0 && fits16));
-    const bool use8 = !usew && !use16 && ((e->decode_path == 2) || (e->decode_path == 0 && fits8));
+    // partial-label decoding lives on the multi-kernel graph path only
+    const bool usew = !labels && e->decode_path == 6;
+    const bool use16 = !labels && !usew && ((e->decode_path == 3) || (e->decode_path == 0 && fits16));
+    const bool use8 = !labels && !usew && !use16 && ((e->decode_path == 2) || (e->decode_path == 0 && fits8));
     const bool use16s = use16 && fits16s;
     if (e->cur_ctx != 0 && !(usew || use16 || use8))
         return fail(e, MNX_ERR_INVALID, "the multi-kernel graph path runs in context 0 only");
@@ -763,6 +786,14 @@ static int decode_internal(mnx_engine* e, const float* features, int B, int S, c
     e->last_path = 1;
     int rc = ensure_graph(e, b);
     if (rc != MNX_OK) return rc;
+    const int lab_len = labels ? (n_labels < T + 1 ? n_labels : T + 1) : 0;
+    if (labels) {
+        // the columns a decode of <= T steps can read (t and t + 1), by original row
+        CUDA_TRY(e, cudaMemcpy2DAsync(e->labels, sizeof(int) * (size_t)(T + 1), labels, sizeof(int) * (size_t)n_labels, sizeof(int) * (size_t)lab_len,
+                                      (size_t)B, cudaMemcpyDeviceToDevice, s));
+        CUDA_TRY(e, dec_set_label_len(b, lab_len, s));
+        e->launches += 1;
+    }
     for (int chunk = 0; chunk < T / STEPS_PER_GRAPH; ++chunk) {
         CUDA_TRY(e, cudaGraphLaunch(e->graph, s));
         e->launches += e->graph_nodes;
@@ -776,6 +807,31 @@ static int decode_internal(mnx_engine* e, const float* features, int B, int S, c
     e->last_steps = hs.steps_run;
     e->steps_pending = false;
     e->last_B = B; e->last_S = S;
+    if (labels) {
+        // the reference indexes labels[:, step] at every step it runs (components.py:287): a decode that outlives the
+        // labels is its IndexError
+        if (hs.steps_run > n_labels)
+            return fail(e, MNX_ERR_INVALID, "labels have %d columns but the decode ran %d steps (IndexError at components.py:287 in the reference)",
+                        n_labels, hs.steps_run);
+        CUDA_TRY(e, dec_label_merge(b, lab_len, s));
+        e->launches += 1;
+    }
+    return MNX_OK;
+}
+
+extern "C" int mnx_decode_greedy_labels(mnx_engine* e, const float* features, int32_t B, int32_t S, const int32_t* labels, int32_t n_labels,
+                                        int32_t* ids, int32_t* lens, float* token_logp, float* hidden, void* cuda_stream) {
+    if (!e || !features || !labels) return fail(e, MNX_ERR_INVALID, "mnx_decode_greedy_labels: null argument");
+    if (n_labels < 1) return fail(e, MNX_ERR_INVALID, "mnx_decode_greedy_labels: labels need at least one column, got %d", n_labels);
+    if (e->cur_ctx != 0) return fail(e, MNX_ERR_INVALID, "partial-label decoding runs in context 0 only");
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    int rc = decode_internal(e, features, B, S, s, labels, n_labels);
+    if (rc != MNX_OK) return rc;
+    const size_t T = e->cfg.max_len;
+    if (ids) CUDA_TRY(e, cudaMemcpyAsync(ids, e->ids, sizeof(int) * B * T, cudaMemcpyDeviceToDevice, s));
+    if (lens) CUDA_TRY(e, cudaMemcpyAsync(lens, e->lens, sizeof(int) * B, cudaMemcpyDeviceToDevice, s));
+    if (token_logp) CUDA_TRY(e, cudaMemcpyAsync(token_logp, e->logp, sizeof(float) * B * T, cudaMemcpyDeviceToDevice, s));
+    if (hidden) CUDA_TRY(e, cudaMemcpyAsync(hidden, e->hidden, sizeof(float) * B * T * 256, cudaMemcpyDeviceToDevice, s));
     return MNX_OK;
 }
 
@@ -829,7 +885,7 @@ extern "C" int mnx_decode_beam(mnx_engine* e, const float* features, int32_t B, 
     if (B < 1 || B > e->cfg.max_batch) return fail(e, MNX_ERR_CAPACITY, "batch %d exceeds max_batch %d", B, e->cfg.max_batch);
     if (S < 1 || S > e->S_max) return fail(e, MNX_ERR_CAPACITY, "memory length %d exceeds capacity %d", S, e->S_max);
     cudaStream_t s = (cudaStream_t)cuda_stream;
-    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    ON_ENGINE_DEVICE(e);
     const int T = e->cfg.max_len, R = B * beam;
     DecBuffers bi = make_buffers(e, B, S);     // image-shaped view for the once-per-call projections
     DecBuffers b = make_buffers(e, R, S);      // row-shaped view for the step kernels
@@ -871,7 +927,7 @@ extern "C" int mnx_atom_indices(mnx_engine* e, const int32_t* ids, const int32_t
     if (!ids) { ids = e->ids; lens = e->lens; }
     if (!e->finalized) return fail(e, MNX_ERR_INVALID, "weights not finalized");
     if (B < 1 || B > e->cfg.max_batch) return fail(e, MNX_ERR_CAPACITY, "batch %d exceeds max_batch %d", B, e->cfg.max_batch);
-    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    ON_ENGINE_DEVICE(e);
     CUDA_TRY(e, dec_atom_scan(ids, lens, B, e->cfg.max_len, e->d_cls, e->g, e->cfg.max_atoms, atom_idx, n_atoms,
                               (cudaStream_t)cuda_stream));
     e->launches += 1;
@@ -883,7 +939,7 @@ extern "C" int mnx_edges(mnx_engine* e, const float* hidden, const int32_t* atom
     if (!e || !atom_idx || !n_atoms || !edges) return fail(e, MNX_ERR_INVALID, "mnx_edges: null argument");
     if (!e->finalized) return fail(e, MNX_ERR_INVALID, "weights not finalized");
     if (B < 1 || B > e->cfg.max_batch) return fail(e, MNX_ERR_CAPACITY, "batch %d exceeds max_batch %d", B, e->cfg.max_batch);
-    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    ON_ENGINE_DEVICE(e);
     int nl = 0;
     CUDA_TRY(e, dec_edges(hidden ? hidden : e->edge_hidden, atom_idx, n_atoms, B, e->cfg.max_len, e->cfg.max_atoms, e->dw,
                           e->hg, e->AB, e->prob, edges, edge_score, (cudaStream_t)cuda_stream, &nl));
@@ -899,7 +955,7 @@ extern "C" int mnx_encode(mnx_engine* e, const float* images, int32_t B, int32_t
     if (B < 1 || B > e->cfg.max_batch) return fail(e, MNX_ERR_CAPACITY, "batch %d exceeds max_batch %d", B, e->cfg.max_batch);
     if (H < 32 || W < 32 || H > e->cfg.max_height || W > e->cfg.max_width)
         return fail(e, MNX_ERR_CAPACITY, "image %dx%d outside [32, %dx%d]", H, W, e->cfg.max_height, e->cfg.max_width);
-    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    ON_ENGINE_DEVICE(e);
     int nl = 0;
     int rc = encoder_forward(e, e->enc, images, B, H, W, features, (cudaStream_t)cuda_stream, &nl);
     e->launches += nl;
@@ -919,7 +975,7 @@ extern "C" int mnx_preprocess(mnx_engine* e, const uint8_t* rgb, const int64_t* 
         if (heights[i] < 1 || widths[i] < 1 || offsets[i] < 0) return fail(e, MNX_ERR_INVALID, "image %d has a bad size or offset", i);
         off[i] = (unsigned long long)offsets[i];
     }
-    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    ON_ENGINE_DEVICE(e);
     int nl = 0;
     CUDA_TRY(e, pp_run(rgb, off.data(), heights, widths, B, pad, out_size, mean255, inv_std255, e->pp_bbox, images,
                        (cudaStream_t)cuda_stream, &nl));
@@ -959,7 +1015,7 @@ extern "C" int mnx_predict_host(mnx_engine* e, const float* images_host, int32_t
     if (e->cfg.encoder_kind == MNX_ENCODER_NONE) return fail(e, MNX_ERR_INVALID, "this handle was created without an encoder");
     if (B < 1 || B > e->cfg.max_batch || H > e->cfg.max_height || W > e->cfg.max_width)
         return fail(e, MNX_ERR_CAPACITY, "request (%d,%d,%d) exceeds the sizes given at create", B, H, W);
-    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    ON_ENGINE_DEVICE(e);
     cudaStream_t s = e->cap_stream;   // engine-owned non-blocking stream (never the legacy default stream)
     CUDA_TRY(e, cudaMemcpyAsync(e->images, images_host, sizeof(float) * (size_t)B * 3 * H * W, cudaMemcpyHostToDevice, s));
     int rc = mnx_predict(e, e->images, B, H, W, ids_host, lens_host, token_logp_host, atom_idx_host, n_atoms_host,
@@ -973,7 +1029,7 @@ extern "C" int mnx_beam_trace(mnx_engine* e, int32_t* trace_host, int32_t B) {
     if (!e || !trace_host) return fail(e, MNX_ERR_INVALID, "mnx_beam_trace: null argument");
     if (e->cfg.max_beam < 2 || e->last_beam_B == 0 || B != e->last_beam_B)
         return fail(e, MNX_ERR_INVALID, "mnx_beam_trace: B must equal the batch of the last mnx_decode_beam (%d)", e->last_beam_B);
-    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    ON_ENGINE_DEVICE(e);
     CUDA_TRY(e, cudaMemcpy(trace_host, e->bm.trace, sizeof(int) * (size_t)e->cfg.max_len * B * MNX_MAX_BEAM, cudaMemcpyDeviceToHost));
     return MNX_OK;
 }
@@ -984,7 +1040,7 @@ extern "C" int32_t mnx_last_decode_steps(const mnx_engine* ce) {
     if (!e) return 0;
     if (e->steps_pending) {      // cluster paths: wait for the decode kernel and fetch its step count
         int steps = 0;
-        cudaSetDevice(e->cfg.device);
+        DeviceGuard guard(e->cfg.device);
         if (cudaMemcpy(&steps, e->steps_run_dev, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess) e->last_steps = steps;
         e->steps_pending = false;
     }
@@ -1028,7 +1084,7 @@ extern "C" int mnx_time_kernel(mnx_engine* e, int32_t which, int32_t iters, floa
         return MNX_OK;
     }
     if (!e->finalized) return fail(e, MNX_ERR_INVALID, "weights not finalized");
-    CUDA_TRY(e, cudaSetDevice(e->cfg.device));
+    ON_ENGINE_DEVICE(e);
     cudaStream_t s = (cudaStream_t)cuda_stream;
     if (which >= 100) return encoder_time_kernel(e, e->enc, which, iters, ms, s);
     if (e->last_B == 0) return fail(e, MNX_ERR_INVALID, "run a decode first: timing uses its shapes and caches");

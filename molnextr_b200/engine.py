@@ -177,8 +177,10 @@ class Engine:
         self._check(self.lib.mnx_encode(self.h, self._p(images), B, H, W, self._p(feats), self._stream()), "mnx_encode")
         return feats
 
-    def decode_greedy(self, features: torch.Tensor, return_hidden: bool = False):
-        """TransformerDecoderAR.decode with GreedySearch (components.py:253-334)."""
+    def decode_greedy(self, features: torch.Tensor, return_hidden: bool = False, labels: Optional[torch.Tensor] = None):
+        """TransformerDecoderAR.decode with GreedySearch (components.py:253-334).  `labels` (B, n) integer tensor =
+        partial prediction (components.py:286-289,326-332): column 0 is <sos>, MASK_ID (4) marks the positions the
+        model fills in, every other position is given; ids / lens come back merged with the labels."""
         assert features.is_cuda and features.dtype == torch.float32
         self._same_device(features)
         features = features.contiguous().view(features.size(0), -1, features.size(-1))
@@ -188,8 +190,15 @@ class Engine:
         lens = torch.empty((B,), device=dev, dtype=torch.int32)
         logp = torch.empty((B, MAX_LEN), device=dev, dtype=torch.float32)
         hidden = torch.empty((B, MAX_LEN, 256), device=dev, dtype=torch.float32) if return_hidden else None
-        self._check(self.lib.mnx_decode_greedy(self.h, self._p(features), B, S, self._p(ids), self._p(lens),
-                                               self._p(logp), self._p(hidden), self._stream()), "mnx_decode_greedy")
+        if labels is not None:
+            assert labels.dim() == 2 and labels.size(0) == B, "labels must be (B, n)"
+            lab = labels.to(device=dev, dtype=torch.int32).contiguous()
+            self._check(self.lib.mnx_decode_greedy_labels(self.h, self._p(features), B, S, self._p(lab), lab.size(1), self._p(ids),
+                                                          self._p(lens), self._p(logp), self._p(hidden), self._stream()),
+                        "mnx_decode_greedy_labels")
+        else:
+            self._check(self.lib.mnx_decode_greedy(self.h, self._p(features), B, S, self._p(ids), self._p(lens),
+                                                   self._p(logp), self._p(hidden), self._stream()), "mnx_decode_greedy")
         out = {"ids": ids, "lens": lens, "logp": logp}
         if return_hidden:
             out["hidden"] = hidden

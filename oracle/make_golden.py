@@ -165,6 +165,79 @@ def make_confidence(name, seed, b, s):
     print(name, "atoms", natoms.tolist(), "overall", overall.tolist())
 
 
+def partial_labels(free_ids, max_len=480, offset=101):
+    """Label rows for a partial-label decode from the rows' FREE greedy ids; recipes 2, 0, 1, 3 are dealt in that order
+    over the rows sorted by free length (shortest first, so the rows that stop by themselves get recipes 2 and 0):
+      0  the reference's own use (tokenization.py:448-449): symbols given, both coordinate tokens <mask>, <eos> given
+      1  everything <mask>, <eos> label half way through the free sequence (the label ends the row early)
+      2  seven given tokens borrowed from the next row, then <mask>, <eos> label five positions AFTER the free
+         sequence's end (the model's own <eos> must not end the row)
+      3  everything <mask>, no <eos> label at all (runs to max_len)
+    Width max_len + 1 so that labels[:, step] and labels[:, step + 1] exist for every step (components.py:287,305)."""
+    PAD, SOS, EOS, MASK = 0, 1, 2, 4
+    B = len(free_ids)
+    lab = np.full((B, max_len + 1), PAD, np.int64)
+    lab[:, 0] = SOS
+    order = sorted(range(B), key=lambda r: (len(free_ids[r]), r))
+    kinds = {r: (2, 0, 1, 3)[n % 4] for n, r in enumerate(order)}
+    for i, ids in enumerate(free_ids):
+        ids = [int(v) for v in ids]
+        L = len(ids)
+        kind = kinds[i]
+        if kind == 0:
+            body = [MASK if v >= offset else v for v in ids]
+            if body[-1] != EOS and L < max_len:
+                body.append(EOS)
+            lab[i, 1:1 + len(body)] = body
+        elif kind == 1:
+            p = max(2, L // 2)
+            lab[i, 1:p] = MASK
+            lab[i, p] = EOS
+        elif kind == 2:
+            other = [int(v) for v in free_ids[(i + 1) % B]][:7]
+            end = min(max_len, L + 5)
+            lab[i, 1:end] = MASK
+            lab[i, 1:1 + len(other)] = [v if v != EOS else MASK for v in other]
+            lab[i, end] = EOS
+        else:
+            lab[i, 1:] = MASK
+    return lab
+
+
+def make_partial(name, seed, b, s):
+    """TransformerDecoderAR.decode(labels=...) run by the reference itself (components.py:286-289,305,317-318,326-332)."""
+    ck = synth.synthetic_checkpoint(seed, "sensitised")
+    _, dec, tok = ref_loader.build_reference(ck)
+    feats = seeded_features(4000 + seed, b, s)
+    ar = dec.decoder["chartok_coords"]
+    with torch.no_grad():
+        free, *_ = ar.decode(feats, 1, 1, max_length=480)
+        labels = torch.from_numpy(partial_labels([o[0].numpy() for o in free]))
+        outputs, scores, token_scores, hiddens = ar.decode(feats, 1, 1, max_length=480, labels=labels)
+    ids = np.zeros((b, 480), np.int32)
+    lens = np.zeros((b,), np.int32)
+    dec_len = np.zeros((b,), np.int32)         # steps the row was alive (token_scores / hidden keep this length)
+    logp = np.zeros((b, 480), np.float64)
+    hidden_sub = np.zeros((b, 480, 16), np.float32)
+    hidden_sum = np.zeros((b, 480), np.float32)
+    for i in range(b):
+        o = outputs[i][0].numpy()
+        lens[i] = len(o)
+        ids[i, :len(o)] = o
+        ts = np.asarray(token_scores[i][0], np.float64)
+        dec_len[i] = len(ts)
+        logp[i, :len(ts)] = ts
+        h = hiddens[i][0].numpy()
+        hidden_sub[i, :len(ts)] = h[:, ::16]
+        hidden_sum[i, :len(ts)] = h.sum(1)
+    np.savez_compressed(os.path.join(GOLDEN, name), labels=labels.numpy().astype(np.int32), ids=ids, lens=lens, dec_len=dec_len,
+                        token_scores=logp, hidden_sub=hidden_sub, hidden_sum=hidden_sum,
+                        free_lens=np.array([len(o[0]) for o in free], np.int32),
+                        seq_score=np.array([sc[0] for sc in scores], np.float32),
+                        cfg=np.array(json.dumps(dict(ckpt_seed=seed, variant="sensitised", feat_seed=4000 + seed, b=b, s=s))))
+    print(name, "free lens", [len(o[0]) for o in free], "lens", lens.tolist(), "alive steps", dec_len.tolist())
+
+
 def make_tokenizer_and_edges(name):
     ck = synth.synthetic_checkpoint(0, "sensitised")
     _, dec, tok = ref_loader.build_reference(ck)
@@ -202,6 +275,7 @@ def main():
     make_swin_e2e("swin_b4_384.npz", seed=0, b=4, h=384, w=384)
     make_swin_e2e("swin_b1_408x424.npz", seed=2, b=1, h=408, w=424)
     make_confidence("confidence_b5_s144.npz", seed=0, b=5, s=144)
+    make_partial("partial_b8_s64.npz", seed=0, b=8, s=64)
 
 
 if __name__ == "__main__":

@@ -313,7 +313,8 @@ def grammar_mask(tokens: torch.Tensor, offset: int, maxx: int, maxy: int) -> tor
 
 def greedy_decode(dec_sd: SD, features: torch.Tensor, max_len: int = 480,
                   grammar=(101, 64, 64), record_logprobs: bool = False,
-                  forced_ids: Optional[torch.Tensor] = None, min_length: int = 1):
+                  forced_ids: Optional[torch.Tensor] = None, min_length: int = 1,
+                  labels: Optional[torch.Tensor] = None):
     """TransformerDecoderAR.decode with GreedySearch (components.py:253-334,
     decoding/greedy_search.py:33-128, decode_strategy.py:4-62).
 
@@ -321,9 +322,14 @@ def greedy_decode(dec_sd: SD, features: torch.Tensor, max_len: int = 480,
     logp fp32 (L,); hidden fp32 (L,256); score = exp(mean(logp)).  With `record_logprobs`
     each dict also has `logprobs` (L,V): the masked log-probabilities GreedySearch.advance saw.
     `forced_ids` (B,T) teacher-forces the chosen token (all rows must then share one length;
-    used only to compare per-step log-probs at tensor level)."""
+    used only to compare per-step log-probs at tensor level).
+    `labels` (B,n) long = partial prediction (components.py:256-257,286-289,305,317-318,326-332;
+    greedy_search.py:83-85): given tokens are fed as step inputs, MASK_ID positions are the model's;
+    `ids` come back merged with the labels (and cut to the labels' length), logp / hidden stay the
+    model's own over the full decoded length."""
     sd = _strip(dec_sd)
     B = features.size(0)
+    orig_labels = labels
     mem = memory_bank(sd, features)
     state = DecoderState()
     w_out, b_out = sd[_P + "output_layer.weight"], sd[_P + "output_layer.bias"]
@@ -337,6 +343,10 @@ def greedy_decode(dec_sd: SD, features: torch.Tensor, max_len: int = 480,
     with torch.no_grad():
         for step in range(max_len):
             tgt = alive_seq[:, -1]
+            if labels is not None:
+                label = labels[:, step]                   # IndexError past the last column, as in the reference
+                mask = label.eq(MASK_ID).long()
+                tgt = tgt * mask + label * (1 - mask)
             dec_out = decoder_step(sd, tgt, mem, state)
             logits = F.linear(dec_out, w_out, b_out)
             log_probs = F.log_softmax(logits, dim=-1)
@@ -348,6 +358,8 @@ def greedy_decode(dec_sd: SD, features: torch.Tensor, max_len: int = 480,
                 topk_ids = forced_ids[orig_idx, step].view(-1, 1)
                 topk_scores = log_probs.gather(1, topk_ids)
             is_finished = topk_ids.eq(EOS_ID).view(-1)
+            if labels is not None and step + 1 < labels.size(1):
+                is_finished = labels[:, step + 1].eq(EOS_ID)
             alive_seq = torch.cat([alive_seq, topk_ids], -1)
             alive_logp = torch.cat([alive_logp, topk_scores], -1)
             h = dec_out.unsqueeze(1)
@@ -374,7 +386,16 @@ def greedy_decode(dec_sd: SD, features: torch.Tensor, max_len: int = 480,
                 select = alive.nonzero().view(-1)
                 orig_idx = orig_idx[alive]
                 mem = mem.index_select(0, select)
+                if labels is not None:
+                    labels = labels.index_select(0, select)
                 state.index_select(select)
+    if orig_labels is not None:
+        for i in range(B):
+            pred = results[i]["ids"]
+            label = orig_labels[i][1:len(pred) + 1]
+            mask = label.eq(MASK_ID).long()
+            pred = pred[:len(label)]
+            results[i]["ids"] = pred * mask + label * (1 - mask)
     return results
 
 

@@ -130,3 +130,36 @@ def test_errors_are_loud(engines):
     extra["decoder.bogus.weight"] = torch.zeros(3)
     with pytest.raises(EngineError, match="unexpected tensor"):
         Engine({"decoder": extra, "encoder": None}, max_batch=2)
+
+
+def test_partial_label_decode_matches_reference_fixture():
+    """mnx_decode_greedy_labels against TransformerDecoderAR.decode(labels=...) run by the reference
+    (components.py:286-289,305,317-318,326-332): merged ids / lengths bit-exact, the model's own token scores and
+    hidden states over the full decoded length within the fp32 tolerance of the other decode tests."""
+    from molnextr_b200.engine import Engine
+    g = load_golden("partial_b8_s64.npz")
+    cfg = g["cfg"]
+    ck = {"decoder": synth.decoder_state(cfg["ckpt_seed"], cfg["variant"]), "encoder": None}
+    eng = Engine(ck, max_batch=8, max_height=256, max_width=256)
+    try:
+        feats = seeded_features(cfg["feat_seed"], cfg["b"], cfg["s"]).cuda()
+        labels = torch.from_numpy(g["labels"]).cuda()
+        out = eng.decode_greedy(feats, return_hidden=True, labels=labels)
+        torch.cuda.synchronize()
+        lens, ids = out["lens"].cpu().numpy(), out["ids"].cpu().numpy()
+        assert lens.tolist() == g["lens"].tolist()
+        for i in range(cfg["b"]):
+            L, D = int(g["lens"][i]), int(g["dec_len"][i])
+            assert ids[i, :L].tolist() == g["ids"][i, :L].tolist(), f"row {i}"
+            assert (ids[i, L:] == 0).all()
+            np.testing.assert_allclose(np.exp(out["logp"][i, :D].double().cpu().numpy()), g["token_scores"][i, :D], rtol=5e-4, atol=1e-7)
+            np.testing.assert_allclose(out["hidden"][i, :D, ::16].cpu().numpy(), g["hidden_sub"][i, :D], rtol=0, atol=5e-4)
+        assert eng.last_decode_steps() == int(g["dec_len"].max())
+        # labels narrower than the decode -> the reference's IndexError becomes an error status
+        with pytest.raises(RuntimeError, match="IndexError"):
+            eng.decode_greedy(feats[:2], labels=torch.full((2, 5), 4, dtype=torch.int32).cuda())
+        # and the handle still decodes without labels afterwards, on the path it would normally take
+        free = eng.decode_greedy(feats)
+        assert free["lens"].cpu().numpy().tolist() == g["free_lens"].tolist()
+    finally:
+        eng.close()

@@ -89,3 +89,24 @@ def test_synthetic_checkpoint_schema():
     n_dec = sum(v.numel() for k, v in dec.items() if not k.endswith("pe.pe"))
     assert n_dec == 6834156
     assert dec["decoder.chartok_coords.embeddings.make_embedding.emb_luts.0.weight"][0].abs().sum() == 0
+
+
+def test_oracle_partial_label_decode_matches_reference_fixture():
+    """TransformerDecoderAR.decode(labels=...) (components.py:286-289,305,317-318,326-332): fixture written by the reference."""
+    g = load_golden("partial_b8_s64.npz")
+    cfg = g["cfg"]
+    dec = synth.decoder_state(cfg["ckpt_seed"], cfg["variant"])
+    feats = seeded_features(cfg["feat_seed"], cfg["b"], cfg["s"])
+    labels = torch.from_numpy(g["labels"]).long()
+    raw = restate.greedy_decode(dec, feats, labels=labels)
+    for i, r in enumerate(raw):
+        L, D = int(g["lens"][i]), int(g["dec_len"][i])
+        assert r["ids"].tolist() == g["ids"][i, :L].tolist()
+        assert len(r["logp"]) == D
+        np.testing.assert_allclose(np.exp(r["logp"].double().numpy()), g["token_scores"][i, :D], rtol=2e-4, atol=1e-7)
+        np.testing.assert_allclose(r["hidden"][:, ::16].numpy(), g["hidden_sub"][i, :D], rtol=0, atol=2e-4)
+    # the recipes did what they were meant to: a row cut short by its label, one that outlives its own <eos>
+    assert (g["lens"] < g["free_lens"]).any() and (g["lens"] > g["free_lens"]).any()
+    # labels narrower than the decode: the reference's IndexError (components.py:287)
+    with pytest.raises(IndexError):
+        restate.greedy_decode(dec, feats[:2], labels=torch.full((2, 5), 4, dtype=torch.long))

@@ -32,3 +32,21 @@ def test_oracle_equals_reference_swin_decode():
         p_ref = dec.decode(f_ref, None)
     p_or = restate.decode(ck["decoder"], f_or, CharTokenizer(64))
     assert p_ref == p_or
+
+
+def test_oracle_equals_reference_partial_label_decode():
+    """Fresh seed, labels built by the fixture script's recipes, the reference's own TransformerDecoderAR.decode(labels=...)."""
+    from oracle.make_golden import partial_labels, seeded_features
+    ck = synth.synthetic_checkpoint(6, "sensitised")
+    _, dec, _ = ref_loader.build_reference(ck)
+    ar = dec.decoder["chartok_coords"]
+    feats = seeded_features(77, 4, 36)
+    with torch.no_grad():
+        free, *_ = ar.decode(feats, 1, 1, max_length=480)
+        labels = torch.from_numpy(partial_labels([o[0].numpy() for o in free]))
+        outputs, scores, token_scores, hiddens = ar.decode(feats, 1, 1, max_length=480, labels=labels)
+    raw = restate.greedy_decode(ck["decoder"], feats, labels=labels)
+    for i, r in enumerate(raw):
+        assert r["ids"].tolist() == outputs[i][0].tolist()
+        assert torch.allclose(torch.exp(r["logp"]).double(), torch.tensor(token_scores[i][0]).double(), rtol=1e-5, atol=1e-9)
+        assert torch.allclose(r["hidden"], hiddens[i][0], rtol=0, atol=1e-5)
