@@ -4,9 +4,9 @@
 //   stem conv4x4/4 + LayerNorm2d | per stage: [LayerNorm2d + conv2x2/2] then blocks of
 //   dwconv7x7 -> LayerNorm(C, eps 1e-6) -> Linear C->4C -> GELU -> Linear 4C->C -> *gamma -> +x.
 //
-// Kernels: dwconv_ln_kernel (7x7 depthwise conv fused with the channel LayerNorm, NHWC fp32 in,
-// bf16 GEMM operand out; input halo tiles arrive by 4-D TMA with out-of-bounds zero fill = the conv's
-// zero padding), downsample_ln_kernel (per-pixel LN + 2x2 patch gather -> bf16), and the shared
+// Kernels: dwconv_stats_kernel (7x7 depthwise conv, NHWC fp32 in, bf16 GEMM operand out + the statistics of
+// the channel LayerNorm, which the fc1 GEMM applies in its epilogue; input halo tiles arrive by 4-D TMA with
+// out-of-bounds zero fill = the conv's zero padding), downsample_ln_kernel (per-pixel LN + 2x2 patch gather -> bf16), and the shared
 // tcgen05 GEMM (gemm_tc.cu) for fc1 (+GELU), fc2 (+gamma, +residual, in place) and the 2x2 conv.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -27,9 +27,9 @@ static const int CN_DEPTH[4] = {3, 3, 27, 3};
 
 struct CnBlockW {
     const float *dw_w, *dw_b;        // [49][C] tap-major, [C]
-    const float *ln_w, *ln_b;
-    const __nv_bfloat16 *fc1_w, *fc2_w;
-    const float *fc1_b, *fc2_b, *gamma;
+    const __nv_bfloat16 *fc1_w, *fc2_w;   // fc1_w = mlp.fc1.weight * diag(norm.weight)  (LayerNorm folded, see gemm_tc.cuh)
+    const float *fc1_b, *fc2_b, *gamma;   // fc1_b = mlp.fc1.weight @ norm.bias + mlp.fc1.bias
+    const float* fc1_colsum;              // [4C] row sums of the bf16 fc1_w
 };
 struct CnDownW {
     const float *ln_w, *ln_b;        // LayerNorm2d over C_in
@@ -42,24 +42,29 @@ struct ConvNextState {
     CnDownW down[4];
     float *x0 = nullptr, *x1 = nullptr;
     __nv_bfloat16 *abuf = nullptr, *hbuf = nullptr;
+    float* stats = nullptr;          // [splits][tokens][2] LayerNorm statistics of the block in flight
+    int split[4] = {1, 1, 4, 8};     // channel split (gridDim.z) of dwconv_stats_kernel per stage; MNX_DW_SPLIT="a,b,c,d" overrides
     size_t max_tokens = 0;
     int last_B = 0, last_H = 0, last_W = 0;
     int cta_limit = 0;   // cap of the persistent GEMM grids for the forward in progress (EncoderState::cta_limit)
 };
 
 // ------------------------------------------------------------------------------------------
-// depthwise 7x7 (pad 3) + bias + LayerNorm over channels -> bf16
-// One CTA = 8 x 8 output pixels x ALL channels, 4 warps; warp w owns output rows 2w and 2w+1.  Channels are
-// processed 64 at a time (lane = a PAIR of channels, arithmetic on packed fp32x2 FFMA2): the 14 x 14 x 64
-// input halo tile and the 49 x 64 weight tile of a chunk are fetched by TMA (4-D / 2-D tensor maps;
-// out-of-bounds zero fill is the conv's zero padding).  The kernel is bounded by shared-memory bytes per FMA,
-// so every input row that is read (14 x 8 bytes per lane) feeds BOTH output rows of the warp (kernel rows ky
-// and ky-1; the previous weight row stays in registers): 21 shared loads per 112 FFMA2 instead of per 56.
-// Shared memory is a single 62.5 KB stage, so three CTAs share an SM and one CTA's TMA wait is hidden behind
-// the others' arithmetic.  Conv outputs go to `out` un-normalised as bf16 -- the GEMM operand precision --
-// while their fp32 sum / sum of squares accumulate in registers; once every channel of a pixel is known the
-// thread that wrote an element re-reads it (same thread: no fence needed, L2-resident), normalises it and
-// writes it back (the fc1 GEMM's A operand).
+// depthwise 7x7 (pad 3) + bias -> bf16, plus the per-pixel statistics of the channel LayerNorm that follows
+// (timm ConvNeXtBlock: conv_dw -> norm -> mlp.fc1).  The LayerNorm itself is applied inside the fc1 GEMM's epilogue
+// (GEMM_EPI_LNFOLD_GELU_BF16, gemm_tc.cuh):  fc1(LN(x)) = rstd * (W' x - mean * colsum(W')) + (W beta + b) with
+// W' = W diag(gamma) -- so this kernel never revisits its output.  (The previous version normalised in place once all
+// channels of a pixel were known: re-reading its own bf16 output from L2 was 45 % of its samples in the ncu capture
+// profiles/r1c_summary.md, a latency chain of 128 dependent load -> store pairs per lane.)
+// One CTA = 8 x 8 output pixels x (C / gridDim.z) channels, 4 warps; warp w owns output rows 2w and 2w+1.  Channels
+// are processed 64 at a time (lane = a PAIR of channels, arithmetic on packed fp32x2 FFMA2): the 14 x 14 x 64 input
+// halo tile and the 49 x 64 weight tile of a chunk are fetched by TMA (4-D / 2-D tensor maps; out-of-bounds zero fill
+// is the conv's zero padding) into a single 62.5 KB stage, three CTAs per SM hide each other's TMA waits -- which is
+// why the channel range is split over gridDim.z when the map is small (stages 2 and 3 would otherwise leave SMs with
+// one or two resident CTAs that stall on every chunk).  Every input row that is read (14 x 8 bytes per lane) feeds
+// BOTH output rows of the warp (kernel rows ky and ky-1; the previous weight row stays in registers): 21 shared
+// loads per 112 FFMA2.  Statistics: fp32 sum / sum of squares of the UNROUNDED conv outputs per pixel over this
+// CTA's channels -> stats[blockIdx.z][pixel] (the GEMM epilogue adds the gridDim.z partials in a fixed order).
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     unsigned long long r;
@@ -77,13 +82,10 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 #define DW_SMEM ((DW_IN_FLOATS + DW_W_FLOATS) * 4 + 16 + 128)
 
 template <int C>
-__global__ void __launch_bounds__(128, 3) dwconv_ln_kernel(const __grid_constant__ CUtensorMap tmap_x,
-                                                           const __grid_constant__ CUtensorMap tmap_w, int H, int W,
-                                                           const float* __restrict__ dw_b,
-                                                           const float* __restrict__ ln_w,
-                                                           const float* __restrict__ ln_b, float eps,
-                                                           __nv_bfloat16* __restrict__ out) {
-    constexpr int NCHUNK = C / 64;
+__global__ void __launch_bounds__(128, 3) dwconv_stats_kernel(const __grid_constant__ CUtensorMap tmap_x,
+                                                              const __grid_constant__ CUtensorMap tmap_w, int H, int W,
+                                                              const float* __restrict__ dw_b,
+                                                              __nv_bfloat16* __restrict__ out, float* __restrict__ stats) {
     extern __shared__ __align__(128) uint8_t smem_raw[];           // (no integer round trip: keeps LDS, not generic LD)
     float* in_buf = reinterpret_cast<float*>(smem_raw);            // [14][14][64]
     float* w_buf = in_buf + DW_IN_FLOATS;                          // [49][64]
@@ -94,6 +96,8 @@ __global__ void __launch_bounds__(128, 3) dwconv_ln_kernel(const __grid_constant
     const int ty = blockIdx.x / tiles_x, tx = blockIdx.x % tiles_x;
     const int y0 = ty * DW_TILE, x0 = tx * DW_TILE;
     const int yA = y0 + 2 * warp;                                  // this warp's first output row
+    const int nchunk = (C / 64) / (int)gridDim.z;                  // chunks of this CTA
+    const int chunk0 = (int)blockIdx.z * nchunk;
 
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
@@ -115,21 +119,20 @@ __global__ void __launch_bounds__(128, 3) dwconv_ln_kernel(const __grid_constant
             "l"(reinterpret_cast<uint64_t>(&tmap_w)), "r"(smem_u32(bar)), "r"(chunk * 64), "r"(0)
             : "memory");
     };
-    if (threadIdx.x == 0) issue(0);
+    if (threadIdx.x == 0) issue(chunk0);
 
-    float psum[2][DW_TILE], psq[2][DW_TILE];   // this lane's share of each pixel's channel sum / sum of squares
+    // this lane's share of each pixel's channel sum / sum of squares: st[(r * 8 + ox) * 2 + {0: sum, 1: squares}]
+    float st[32];
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
-#pragma unroll
-        for (int ox = 0; ox < DW_TILE; ++ox) psum[r][ox] = psq[r][ox] = 0.f;
+    for (int i = 0; i < 32; ++i) st[i] = 0.f;
 
     const float2* tin = reinterpret_cast<const float2*>(in_buf);
     const float2* tw = reinterpret_cast<const float2*>(w_buf);
 #pragma unroll 1
-    for (int chunk = 0; chunk < NCHUNK; ++chunk) {
-        const int c = chunk * 64 + 2 * lane;
+    for (int ci = 0; ci < nchunk; ++ci) {
+        const int c = (chunk0 + ci) * 64 + 2 * lane;
         const float2 bias = *reinterpret_cast<const float2*>(dw_b + c);
-        mbar_wait(bar, (uint32_t)chunk & 1u);
+        mbar_wait(bar, (uint32_t)ci & 1u);
         float2 acc0[DW_TILE], acc1[DW_TILE];
 #pragma unroll
         for (int ox = 0; ox < DW_TILE; ++ox) acc0[ox] = acc1[ox] = bias;
@@ -161,13 +164,13 @@ __global__ void __launch_bounds__(128, 3) dwconv_ln_kernel(const __grid_constant
             }
         }
         __syncthreads();   // everyone is done with the stage: refill it while the results are written out
-        if (threadIdx.x == 0 && chunk + 1 < NCHUNK) issue(chunk + 1);
+        if (threadIdx.x == 0 && ci + 1 < nchunk) issue(chunk0 + ci + 1);
 #pragma unroll
         for (int ox = 0; ox < DW_TILE; ++ox) {
-            psum[0][ox] += acc0[ox].x + acc0[ox].y;
-            psq[0][ox] = fmaf(acc0[ox].x, acc0[ox].x, fmaf(acc0[ox].y, acc0[ox].y, psq[0][ox]));
-            psum[1][ox] += acc1[ox].x + acc1[ox].y;
-            psq[1][ox] = fmaf(acc1[ox].x, acc1[ox].x, fmaf(acc1[ox].y, acc1[ox].y, psq[1][ox]));
+            st[ox * 2] += acc0[ox].x + acc0[ox].y;
+            st[ox * 2 + 1] = fmaf(acc0[ox].x, acc0[ox].x, fmaf(acc0[ox].y, acc0[ox].y, st[ox * 2 + 1]));
+            st[16 + ox * 2] += acc1[ox].x + acc1[ox].y;
+            st[16 + ox * 2 + 1] = fmaf(acc1[ox].x, acc1[ox].x, fmaf(acc1[ox].y, acc1[ox].y, st[16 + ox * 2 + 1]));
             const int x = x0 + ox;
             if (x < W) {
                 if (yA < H)
@@ -177,26 +180,23 @@ __global__ void __launch_bounds__(128, 3) dwconv_ln_kernel(const __grid_constant
             }
         }
     }
-    // LayerNorm over C for the warp's 16 pixels (statistics from the unrounded fp32 conv outputs); every thread
-    // re-reads exactly the elements it wrote
+    // transposing warp reduction: 32 values per lane -> lane L holds the warp total of value L (31 shuffles)
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool hi = (lane & off) != 0;
 #pragma unroll
-        for (int ox = 0; ox < DW_TILE; ++ox) {
-            const float mean = warp_sum(psum[r][ox]) * (1.0f / (float)C);
-            const float var = fmaxf(warp_sum(psq[r][ox]) * (1.0f / (float)C) - mean * mean, 0.f);
-            const float rstd = 1.0f / sqrtf(var + eps);
-            const int y = yA + r, x = x0 + ox;
-            if (y >= H || x >= W) continue;
-            __nv_bfloat16* o = out + (((size_t)b * H + y) * W + x) * C;
-#pragma unroll
-            for (int i = lane * 2; i < C; i += 64) {
-                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(o + i));
-                const float2 g = *reinterpret_cast<const float2*>(ln_w + i);
-                const float2 be = *reinterpret_cast<const float2*>(ln_b + i);
-                *reinterpret_cast<__nv_bfloat162*>(o + i) =
-                    __floats2bfloat162_rn((f.x - mean) * rstd * g.x + be.x, (f.y - mean) * rstd * g.y + be.y);
-            }
+        for (int i = 0; i < off; ++i) {
+            const float keep = hi ? st[i + off] : st[i];
+            const float send = hi ? st[i] : st[i + off];
+            st[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    {
+        const int pix = lane >> 1, r = pix >> 3, ox = pix & 7;      // value L = (r * 8 + ox) * 2 + k
+        const int y = yA + r, x = x0 + ox;
+        if (y < H && x < W) {
+            const size_t M = (size_t)gridDim.y * H * W;
+            stats[((size_t)blockIdx.z * M + ((size_t)b * H + y) * W + x) * 2 + (lane & 1)] = st[0];
         }
     }
 }
@@ -291,10 +291,10 @@ int convnext_finalize(mnx_engine* e, ConvNextState** out, const mnx_config& cfg)
         if (qres != cudaDriverEntryPointSuccess || !fn) { mnx_set_error(e, "cuTensorMapEncodeTiled unavailable"); return MNX_ERR_CUDA; }
         g_cn_encode = reinterpret_cast<PFN_encodeTiled>(fn);
     }
-    CN_CUDA(e, cudaFuncSetAttribute(dwconv_ln_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM));
-    CN_CUDA(e, cudaFuncSetAttribute(dwconv_ln_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM));
-    CN_CUDA(e, cudaFuncSetAttribute(dwconv_ln_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM));
-    CN_CUDA(e, cudaFuncSetAttribute(dwconv_ln_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM));
+    CN_CUDA(e, cudaFuncSetAttribute(dwconv_stats_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM));
+    CN_CUDA(e, cudaFuncSetAttribute(dwconv_stats_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM));
+    CN_CUDA(e, cudaFuncSetAttribute(dwconv_stats_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM));
+    CN_CUDA(e, cudaFuncSetAttribute(dwconv_stats_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM));
     if (cfg.max_height % 32 != 0 || cfg.max_width % 32 != 0) {
         mnx_set_error(e, "ConvNeXt-B needs image bounds that are multiples of 32");
         return MNX_ERR_INVALID;
@@ -335,10 +335,29 @@ int convnext_finalize(mnx_engine* e, ConvNextState** out, const mnx_config& cfg)
                 for (int i = 0; i < 49; ++i) t[(size_t)i * C + c] = (*dw)[(size_t)c * 49 + i];
             CN_CUDA(e, mnx_upload(e, t, &w.dw_w));
             CN_TRY(cn_f32(e, B + "conv_dw.bias", {C}, &w.dw_b));
-            CN_TRY(cn_f32(e, B + "norm.weight", {C}, &w.ln_w));
-            CN_TRY(cn_f32(e, B + "norm.bias", {C}, &w.ln_b));
-            CN_TRY(cn_bf16(e, B + "mlp.fc1.weight", {4 * C, C}, &w.fc1_w));
-            CN_TRY(cn_f32(e, B + "mlp.fc1.bias", {4 * C}, &w.fc1_b));
+            {   // fold the LayerNorm's affine part into fc1: W' = W diag(g), b' = W beta + b, colsum = W' 1 (of the bf16 W')
+                const std::vector<float>* lw = mnx_need(e, B + "norm.weight", {C});
+                const std::vector<float>* lb = mnx_need(e, B + "norm.bias", {C});
+                const std::vector<float>* fw = mnx_need(e, B + "mlp.fc1.weight", {4 * C, C});
+                const std::vector<float>* fb = mnx_need(e, B + "mlp.fc1.bias", {4 * C});
+                if (!lw || !lb || !fw || !fb) return MNX_ERR_WEIGHTS;
+                std::vector<float> wf((size_t)4 * C * C), bf((size_t)4 * C), cs((size_t)4 * C);
+                for (int64_t n = 0; n < 4 * C; ++n) {
+                    double bacc = (*fb)[n], sacc = 0.0;
+                    for (int64_t k = 0; k < C; ++k) {
+                        const float wv = (*fw)[(size_t)n * C + k];
+                        const float wg = wv * (*lw)[k];
+                        wf[(size_t)n * C + k] = wg;
+                        sacc += (double)__bfloat162float(__float2bfloat16_rn(wg));
+                        bacc += (double)wv * (double)(*lb)[k];
+                    }
+                    bf[n] = (float)bacc;
+                    cs[n] = (float)sacc;
+                }
+                CN_TRY(cn_bf16_vec(e, wf, &w.fc1_w));
+                CN_CUDA(e, mnx_upload(e, bf, &w.fc1_b));
+                CN_CUDA(e, mnx_upload(e, cs, &w.fc1_colsum));
+            }
             CN_TRY(cn_bf16(e, B + "mlp.fc2.weight", {C, 4 * C}, &w.fc2_w));
             CN_TRY(cn_f32(e, B + "mlp.fc2.bias", {C}, &w.fc2_b));
             CN_TRY(cn_f32(e, B + "gamma", {C}, &w.gamma));
@@ -351,22 +370,36 @@ int convnext_finalize(mnx_engine* e, ConvNextState** out, const mnx_config& cfg)
     CN_CUDA(e, mnx_dev_alloc_bytes(e, &p, tok * 128 * sizeof(float) / 2 + 1024)); st->x1 = (float*)p;
     CN_CUDA(e, mnx_dev_alloc_bytes(e, &p, tok * 128 * 2)); st->abuf = (__nv_bfloat16*)p;
     CN_CUDA(e, mnx_dev_alloc_bytes(e, &p, tok * 512 * 2)); st->hbuf = (__nv_bfloat16*)p;
+    if (const char* env = getenv("MNX_DW_SPLIT")) {     // kernel tuning only (A/B timing on the GPU box)
+        int v[4];
+        if (sscanf(env, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]) == 4)
+            for (int i = 0; i < 4; ++i)
+                if (v[i] >= 1 && v[i] <= (2 << i) && ((2 << i) % v[i]) == 0) st->split[i] = v[i];
+    }
+    size_t stat_floats = 0;
+    for (int i = 0; i < 4; ++i) {
+        const size_t need = (size_t)st->split[i] * (tok >> (2 * i)) * 2;
+        if (need > stat_floats) stat_floats = need;
+    }
+    CN_CUDA(e, mnx_dev_alloc_bytes(e, &p, stat_floats * sizeof(float))); st->stats = (float*)p;
     return MNX_OK;
 }
 
 void convnext_destroy(ConvNextState* st) { delete st; }
 
 static cudaError_t cn_gemm(const __nv_bfloat16* A, const __nv_bfloat16* W, long long M, int N, int K, int epi,
-                           const float* bias, const float* gamma, void* out, cudaStream_t s, int cta_limit) {
+                           const float* bias, const float* gamma, void* out, cudaStream_t s, int cta_limit,
+                           const float* colsum = nullptr, const float* ln_stats = nullptr, int ln_splits = 0) {
     GemmParams p{};
     p.cta_limit = cta_limit;
     p.A = A; p.W = W; p.M = (int)M; p.N = N; p.K = K; p.epilogue = epi; p.bias = bias; p.gamma = gamma; p.out = out;
+    p.colsum = colsum; p.ln_stats = ln_stats; p.ln_splits = ln_splits; p.ln_eps = 1e-6f;
     return gemm_tc_launch(p, s);
 }
 
 template <int C>
 static int launch_dwconv_t(mnx_engine* e, const float* x, int B, int H, int W, const CnBlockW& w, __nv_bfloat16* out,
-                           cudaStream_t s) {
+                           float* stats, int split, cudaStream_t s) {
     CUtensorMap map, wmap;
     {
         const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -389,17 +422,17 @@ static int launch_dwconv_t(mnx_engine* e, const float* x, int B, int H, int W, c
         if (r != CUDA_SUCCESS) { mnx_set_error(e, "cuTensorMapEncodeTiled failed for the dwconv weights"); return MNX_ERR_CUDA; }
     }
     const int tiles = ((H + DW_TILE - 1) / DW_TILE) * ((W + DW_TILE - 1) / DW_TILE);
-    dwconv_ln_kernel<C><<<dim3(tiles, B), 128, DW_SMEM, s>>>(map, wmap, H, W, w.dw_b, w.ln_w, w.ln_b, 1e-6f, out);
+    dwconv_stats_kernel<C><<<dim3(tiles, B, split), 128, DW_SMEM, s>>>(map, wmap, H, W, w.dw_b, out, stats);
     CN_CUDA(e, cudaGetLastError());
     return MNX_OK;
 }
 static int launch_dwconv(mnx_engine* e, const float* x, int B, int H, int W, int C, const CnBlockW& w, __nv_bfloat16* out,
-                         cudaStream_t s) {
+                         float* stats, int split, cudaStream_t s) {
     switch (C) {
-        case 128: return launch_dwconv_t<128>(e, x, B, H, W, w, out, s);
-        case 256: return launch_dwconv_t<256>(e, x, B, H, W, w, out, s);
-        case 512: return launch_dwconv_t<512>(e, x, B, H, W, w, out, s);
-        default: return launch_dwconv_t<1024>(e, x, B, H, W, w, out, s);
+        case 128: return launch_dwconv_t<128>(e, x, B, H, W, w, out, stats, split, s);
+        case 256: return launch_dwconv_t<256>(e, x, B, H, W, w, out, stats, split, s);
+        case 512: return launch_dwconv_t<512>(e, x, B, H, W, w, out, stats, split, s);
+        default: return launch_dwconv_t<1024>(e, x, B, H, W, w, out, stats, split, s);
     }
 }
 
@@ -433,9 +466,10 @@ int convnext_forward(mnx_engine* e, ConvNextState* st, const float* images, int 
         const long long M = (long long)B * Hc * Wc;
         for (int j = 0; j < CN_DEPTH[stage]; ++j) {
             const CnBlockW& w = st->blocks[stage][j];
-            CN_TRY(launch_dwconv(e, x, B, Hc, Wc, C, w, st->abuf, s));
+            CN_TRY(launch_dwconv(e, x, B, Hc, Wc, C, w, st->abuf, st->stats, st->split[stage], s));
             ++nl;
-            CN_CUDA(e, cn_gemm(st->abuf, w.fc1_w, M, 4 * C, C, GEMM_EPI_GELU_BF16, w.fc1_b, nullptr, st->hbuf, s, st->cta_limit)); ++nl;
+            CN_CUDA(e, cn_gemm(st->abuf, w.fc1_w, M, 4 * C, C, GEMM_EPI_LNFOLD_GELU_BF16, w.fc1_b, nullptr, st->hbuf, s, st->cta_limit,
+                               w.fc1_colsum, st->stats, st->split[stage])); ++nl;
             CN_CUDA(e, cn_gemm(st->hbuf, w.fc2_w, M, C, 4 * C, GEMM_EPI_RESADD_F32, w.fc2_b, w.gamma, x, s, st->cta_limit)); ++nl;
         }
     }
@@ -444,7 +478,7 @@ int convnext_forward(mnx_engine* e, ConvNextState* st, const float* images, int 
     return MNX_OK;
 }
 
-// isolated timing of the fused dwconv+LN kernel at the shapes of stage (which - 101) of the last call
+// isolated timing of the dwconv (+ LayerNorm statistics) kernel at the shapes of stage (which - 101) of the last call
 int convnext_time_kernel(mnx_engine* e, ConvNextState* st, int which, int iters, float* ms, cudaStream_t s) {
     const int stage = which - 101;
     if (stage < 0 || stage > 3 || st->last_B == 0) { mnx_set_error(e, "convnext timing: ids 101..104 after an encode"); return MNX_ERR_INVALID; }
@@ -457,7 +491,7 @@ int convnext_time_kernel(mnx_engine* e, ConvNextState* st, int which, int iters,
     int rc = MNX_OK;
     for (int i = 0; i < 3 + iters && rc == MNX_OK; ++i) {
         if (i == 3) cudaEventRecord(e0, s);
-        rc = launch_dwconv(e, x, B, Hc, Wc, C, w, st->abuf, s);
+        rc = launch_dwconv(e, x, B, Hc, Wc, C, w, st->abuf, st->stats, st->split[stage], s);
     }
     cudaEventRecord(e1, s);
     cudaStreamSynchronize(s);

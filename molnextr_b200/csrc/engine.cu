@@ -132,6 +132,9 @@ struct mnx_engine {
     cudaGraphExec_t graph_beam = nullptr;
     int gb_B = -1, gb_S = -1, gb_K = -1, gb_NB = -1, gb_nodes = 0;
     int last_beam_B = 0;
+    cudaEvent_t ev_last = nullptr;       // recorded behind the work of every entry point on the caller's stream: mnx_predict_host
+                                         // (which runs on cap_stream) orders itself after it, so that calls on one handle from
+                                         // different streams never overlap on the shared workspaces
     cudaStream_t cap_stream = nullptr;   // engine-owned non-blocking stream: graph capture and mnx_predict_host
     int* h_done = nullptr;   // pinned
     int64_t launches = 0;
@@ -169,6 +172,15 @@ struct DeviceGuard {
         if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev); else if (err == cudaSuccess) prev = -1;
     }
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+static void mark_work(mnx_engine* e, cudaStream_t s) {
+    if (e->ev_last) cudaEventRecord(e->ev_last, s);
+}
+struct WorkMark {
+    mnx_engine* e;
+    cudaStream_t s;
+    WorkMark(mnx_engine* e_, cudaStream_t s_) : e(e_), s(s_) {}
+    ~WorkMark() { mark_work(e, s); }
 };
 #define ON_ENGINE_DEVICE(e)                 \
     DeviceGuard _dev_guard((e)->cfg.device); \
@@ -264,6 +276,7 @@ extern "C" int mnx_create(const mnx_config* cfg, mnx_engine** out) {
     }
     if (c == cudaSuccess) c = cudaMallocHost(&e->h_done, sizeof(int));
     if (c == cudaSuccess) c = cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking);
+    if (c == cudaSuccess) c = cudaEventCreateWithFlags(&e->ev_last, cudaEventDisableTiming);
     if (c != cudaSuccess) {
         std::string m = cudaGetErrorString(c);
         delete e;
@@ -283,6 +296,7 @@ extern "C" int mnx_destroy(mnx_engine* e) {
     for (void* p : e->allocs) cudaFree(p);
     if (e->h_done) cudaFreeHost(e->h_done);
     if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+    if (e->ev_last) cudaEventDestroy(e->ev_last);
     delete e;
     return MNX_OK;
 }
@@ -714,6 +728,7 @@ static int decode_internal(mnx_engine* e, const float* features, int B, int S, c
     if (B < 1 || B > e->cfg.max_batch) return fail(e, MNX_ERR_CAPACITY, "batch %d exceeds max_batch %d", B, e->cfg.max_batch);
     if (S < 1 || S > e->S_max) return fail(e, MNX_ERR_CAPACITY, "memory length %d exceeds capacity %d", S, e->S_max);
     ON_ENGINE_DEVICE(e);
+    WorkMark work_mark(e, s);
     DecBuffers b = make_buffers(e, B, S);
     const int T = e->cfg.max_len;
     e->edge_hidden = e->hidden;
@@ -825,6 +840,8 @@ extern "C" int mnx_decode_greedy_labels(mnx_engine* e, const float* features, in
     if (n_labels < 1) return fail(e, MNX_ERR_INVALID, "mnx_decode_greedy_labels: labels need at least one column, got %d", n_labels);
     if (e->cur_ctx != 0) return fail(e, MNX_ERR_INVALID, "partial-label decoding runs in context 0 only");
     cudaStream_t s = (cudaStream_t)cuda_stream;
+    ON_ENGINE_DEVICE(e);
+    WorkMark work_mark(e, s);
     int rc = decode_internal(e, features, B, S, s, labels, n_labels);
     if (rc != MNX_OK) return rc;
     const size_t T = e->cfg.max_len;
@@ -839,6 +856,8 @@ extern "C" int mnx_decode_greedy(mnx_engine* e, const float* features, int32_t B
                                  int32_t* lens, float* token_logp, float* hidden, void* cuda_stream) {
     if (!e || !features) return fail(e, MNX_ERR_INVALID, "mnx_decode_greedy: null argument");
     cudaStream_t s = (cudaStream_t)cuda_stream;
+    ON_ENGINE_DEVICE(e);
+    WorkMark work_mark(e, s);
     int rc = decode_internal(e, features, B, S, s);
     if (rc != MNX_OK) return rc;
     const size_t T = e->cfg.max_len;
@@ -886,6 +905,7 @@ extern "C" int mnx_decode_beam(mnx_engine* e, const float* features, int32_t B, 
     if (S < 1 || S > e->S_max) return fail(e, MNX_ERR_CAPACITY, "memory length %d exceeds capacity %d", S, e->S_max);
     cudaStream_t s = (cudaStream_t)cuda_stream;
     ON_ENGINE_DEVICE(e);
+    WorkMark work_mark(e, (cudaStream_t)cuda_stream);
     const int T = e->cfg.max_len, R = B * beam;
     DecBuffers bi = make_buffers(e, B, S);     // image-shaped view for the once-per-call projections
     DecBuffers b = make_buffers(e, R, S);      // row-shaped view for the step kernels
@@ -928,6 +948,7 @@ extern "C" int mnx_atom_indices(mnx_engine* e, const int32_t* ids, const int32_t
     if (!e->finalized) return fail(e, MNX_ERR_INVALID, "weights not finalized");
     if (B < 1 || B > e->cfg.max_batch) return fail(e, MNX_ERR_CAPACITY, "batch %d exceeds max_batch %d", B, e->cfg.max_batch);
     ON_ENGINE_DEVICE(e);
+    WorkMark work_mark(e, (cudaStream_t)cuda_stream);
     CUDA_TRY(e, dec_atom_scan(ids, lens, B, e->cfg.max_len, e->d_cls, e->g, e->cfg.max_atoms, atom_idx, n_atoms,
                               (cudaStream_t)cuda_stream));
     e->launches += 1;
@@ -940,6 +961,7 @@ extern "C" int mnx_edges(mnx_engine* e, const float* hidden, const int32_t* atom
     if (!e->finalized) return fail(e, MNX_ERR_INVALID, "weights not finalized");
     if (B < 1 || B > e->cfg.max_batch) return fail(e, MNX_ERR_CAPACITY, "batch %d exceeds max_batch %d", B, e->cfg.max_batch);
     ON_ENGINE_DEVICE(e);
+    WorkMark work_mark(e, (cudaStream_t)cuda_stream);
     int nl = 0;
     CUDA_TRY(e, dec_edges(hidden ? hidden : e->edge_hidden, atom_idx, n_atoms, B, e->cfg.max_len, e->cfg.max_atoms, e->dw,
                           e->hg, e->AB, e->prob, edges, edge_score, (cudaStream_t)cuda_stream, &nl));
@@ -956,6 +978,7 @@ extern "C" int mnx_encode(mnx_engine* e, const float* images, int32_t B, int32_t
     if (H < 32 || W < 32 || H > e->cfg.max_height || W > e->cfg.max_width)
         return fail(e, MNX_ERR_CAPACITY, "image %dx%d outside [32, %dx%d]", H, W, e->cfg.max_height, e->cfg.max_width);
     ON_ENGINE_DEVICE(e);
+    WorkMark work_mark(e, (cudaStream_t)cuda_stream);
     int nl = 0;
     int rc = encoder_forward(e, e->enc, images, B, H, W, features, (cudaStream_t)cuda_stream, &nl);
     e->launches += nl;
@@ -976,6 +999,7 @@ extern "C" int mnx_preprocess(mnx_engine* e, const uint8_t* rgb, const int64_t* 
         off[i] = (unsigned long long)offsets[i];
     }
     ON_ENGINE_DEVICE(e);
+    WorkMark work_mark(e, (cudaStream_t)cuda_stream);
     int nl = 0;
     CUDA_TRY(e, pp_run(rgb, off.data(), heights, widths, B, pad, out_size, mean255, inv_std255, e->pp_bbox, images,
                        (cudaStream_t)cuda_stream, &nl));
@@ -988,6 +1012,8 @@ extern "C" int mnx_predict(mnx_engine* e, const float* images, int32_t B, int32_
                            void* cuda_stream) {
     if (!e) return MNX_ERR_INVALID;
     cudaStream_t s = (cudaStream_t)cuda_stream;
+    ON_ENGINE_DEVICE(e);
+    WorkMark work_mark(e, s);   // recorded behind the result copies below
     int rc = mnx_encode(e, images, B, H, W, e->features, s);
     if (rc != MNX_OK) return rc;
     const int S = encoder_seq_len(e->cfg.encoder_kind, H, W);
@@ -1017,6 +1043,7 @@ extern "C" int mnx_predict_host(mnx_engine* e, const float* images_host, int32_t
         return fail(e, MNX_ERR_CAPACITY, "request (%d,%d,%d) exceeds the sizes given at create", B, H, W);
     ON_ENGINE_DEVICE(e);
     cudaStream_t s = e->cap_stream;   // engine-owned non-blocking stream (never the legacy default stream)
+    CUDA_TRY(e, cudaStreamWaitEvent(s, e->ev_last, 0));   // earlier calls on this handle, whatever stream they used
     CUDA_TRY(e, cudaMemcpyAsync(e->images, images_host, sizeof(float) * (size_t)B * 3 * H * W, cudaMemcpyHostToDevice, s));
     int rc = mnx_predict(e, e->images, B, H, W, ids_host, lens_host, token_logp_host, atom_idx_host, n_atoms_host,
                          edges_host, s);

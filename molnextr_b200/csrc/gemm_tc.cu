@@ -103,6 +103,10 @@ struct GemmKernelArgs {
     const float* gamma;
     const int* row_map;
     void* out;
+    const float* colsum;
+    const float* ln_stats;
+    int ln_splits;
+    float ln_eps;
 };
 
 // GELU(erf) for the bf16-output epilogue, two elements per instruction on packed fp32 pairs and WITHOUT the special
@@ -245,6 +249,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             int dst_row = m;
             if (g.row_map != nullptr && m < g.M) dst_row = g.row_map[m];
             const bool live = (m < g.M) && (dst_row >= 0);
+            float ln_rstd = 1.f, ln_nmr = 0.f;          // rstd and -mean * rstd of this row (LN-fold epilogue)
+            if (g.epilogue == GEMM_EPI_LNFOLD_GELU_BF16 && m < g.M) {
+                float S = 0.f, Q = 0.f;
+                for (int z = 0; z < g.ln_splits; ++z) {
+                    const float2 p2 = *reinterpret_cast<const float2*>(g.ln_stats + ((size_t)z * g.M + m) * 2);
+                    S += p2.x; Q += p2.y;
+                }
+                const float inv_k = 1.0f / (float)g.K;
+                const float mean = S * inv_k;
+                const float var = fmaxf(Q * inv_k - mean * mean, 0.f);
+                ln_rstd = 1.0f / sqrtf(var + g.ln_eps);
+                ln_nmr = -mean * ln_rstd;
+            }
             mbar_wait(&acc_full[acc], (j >> 1) & 1u);
             tc_fence_after();
 #pragma unroll 1
@@ -256,15 +273,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 float v[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                if (g.bias != nullptr) {
+                if (g.epilogue == GEMM_EPI_LNFOLD_GELU_BF16) {
+                    // v = rstd * (acc - mean * colsum[n]) + bias[n]
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 s4 = *reinterpret_cast<const float4*>(g.colsum + n0 + i);
+                        const float4 b4 = *reinterpret_cast<const float4*>(g.bias + n0 + i);
+                        v[i] = fmaf(v[i], ln_rstd, fmaf(ln_nmr, s4.x, b4.x));
+                        v[i + 1] = fmaf(v[i + 1], ln_rstd, fmaf(ln_nmr, s4.y, b4.y));
+                        v[i + 2] = fmaf(v[i + 2], ln_rstd, fmaf(ln_nmr, s4.z, b4.z));
+                        v[i + 3] = fmaf(v[i + 3], ln_rstd, fmaf(ln_nmr, s4.w, b4.w));
+                    }
+                } else if (g.bias != nullptr) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
                         const float4 b4 = *reinterpret_cast<const float4*>(g.bias + n0 + i);
                         v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
                     }
                 }
-                if (g.epilogue == GEMM_EPI_BF16 || g.epilogue == GEMM_EPI_GELU_BF16) {
-                    if (g.epilogue == GEMM_EPI_GELU_BF16) {
+                if (g.epilogue == GEMM_EPI_BF16 || g.epilogue == GEMM_EPI_GELU_BF16 || g.epilogue == GEMM_EPI_LNFOLD_GELU_BF16) {
+                    if (g.epilogue != GEMM_EPI_BF16) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 2) gelu_erf_pair(v[i], v[i + 1]);
                     }
@@ -349,11 +377,12 @@ cudaError_t gemm_tc_launch(const GemmParams& p, cudaStream_t s) {
     if (g_encode == nullptr) return cudaErrorNotReady;
     if (p.M < 1 || p.N % 128 != 0 || p.K % BK != 0 || p.K < BK) return cudaErrorInvalidValue;
     const int BN = (p.N % 256 == 0) ? 256 : 128;
+    if (p.epilogue == GEMM_EPI_LNFOLD_GELU_BF16 && (!p.colsum || !p.ln_stats || !p.bias || p.ln_splits < 1)) return cudaErrorInvalidValue;
     if ((reinterpret_cast<uintptr_t>(p.A) & 15) || (reinterpret_cast<uintptr_t>(p.W) & 15)) return cudaErrorInvalidValue;
     CUtensorMap ma, mw;
     if (!make_map(&ma, p.A, (uint64_t)p.M, (uint64_t)p.K, BM)) return cudaErrorInvalidValue;
     if (!make_map(&mw, p.W, (uint64_t)p.N, (uint64_t)p.K, BN)) return cudaErrorInvalidValue;
-    GemmKernelArgs g{p.M, p.N, p.K, p.epilogue, p.bias, p.gamma, p.row_map, p.out};
+    GemmKernelArgs g{p.M, p.N, p.K, p.epilogue, p.bias, p.gamma, p.row_map, p.out, p.colsum, p.ln_stats, p.ln_splits, p.ln_eps};
     const int total_tiles = (p.N / BN) * ((p.M + BM - 1) / BM);
     int dev = 0, num_sms = 148;
     cudaGetDevice(&dev);

@@ -13,6 +13,10 @@ enum GemmEpilogue {
     GEMM_EPI_GELU_BF16 = 1,   // out_bf16[m][n] = gelu_erf(acc + bias[n])
     GEMM_EPI_RESADD_F32 = 2,  // resid[row_map ? row_map[m] : m][n] += (gamma ? gamma[n] : 1) * (acc + bias[n])
     GEMM_EPI_F32 = 3,         // out_f32[m][n] = acc + (bias ? bias[n] : 0)
+    GEMM_EPI_LNFOLD_GELU_BF16 = 4,  // A holds UN-normalised rows x; the LayerNorm over K that precedes this Linear is applied
+                              // here:  out_bf16[m][n] = gelu_erf(rstd[m] * (acc - mean[m] * colsum[n]) + bias[n]),  with
+                              // W = weight * diag(ln_weight) (bf16), colsum[n] = sum_k W[n][k], bias = weight @ ln_bias + b,
+                              // mean / rstd from ln_stats (per-row sum and sum of squares of x, `ln_splits` partials)
 };
 
 struct GemmParams {
@@ -24,6 +28,10 @@ struct GemmParams {
     const float* gamma;       // [N] or nullptr
     const int* row_map;       // [M] destination row (or -1 = drop) or nullptr
     void* out;                // bf16 [M][N] / fp32 [M][N] / fp32 residual stream [*][N]
+    const float* colsum;      // [N]               (GEMM_EPI_LNFOLD_GELU_BF16)
+    const float* ln_stats;    // [ln_splits][M][2] {sum, sum of squares} over a K / ln_splits channel range each
+    int ln_splits;
+    float ln_eps;
     int cta_limit;            // > 0: cap the persistent grid at this many CTAs (0 = one per SM): lets the encoder of the
                               // next batch run on the SMs that concurrently running persistent decode kernels leave free
 };

@@ -17,6 +17,7 @@
 #include "encoder.cuh"
 
 #include <cstring>
+#include <cuda_fp16.h>
 #include "gemm_tc.cuh"
 
 namespace mnx {
@@ -31,7 +32,7 @@ struct SwinBlockW {
     const float *qkv_b, *proj_b, *fc1_b, *fc2_b;
     const float* rpb_t;   // [nH][529] relative position bias table, head-major
     const uint2* rpb_frag;   // [nH][9 warps][18 key tiles][32 lanes]: bias / scale of the two query rows x two keys a lane
-                            // owns in the QK^T accumulator, as packed bf16 pairs (window_attn_kernel)
+                            // owns in the QK^T accumulator, as packed fp16 pairs (window_attn_kernel)
 };
 struct SwinMergeW {
     const float *ln_w, *ln_b;
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(288, 2) window_attn_kernel(const __nv_bfloat16
     const int qr = lane >> 2, qc = (lane & 3) * 2;
     const int i0 = warp * 16 + qr, i1 = i0 + 8;             // the two query rows this thread owns
     // bias fragments of this head (L2 resident, 256 contiguous bytes per warp and key tile):
-    // bsrc[nt * 32] = {b(i0, j), b(i0, j+1) | b(i1, j), b(i1, j+1)} / scale as bf16 pairs, j = nt * 8 + qc
+    // bsrc[nt * 32] = {b(i0, j), b(i0, j+1) | b(i1, j), b(i1, j+1)} / scale as fp16 pairs, j = nt * 8 + qc
     const uint2* bsrc = rpb_frag + ((size_t)(h * 9 + warp) * 18) * 32 + lane;
     const int nww = Wp / WS, nwh = Hp / WS;
 #pragma unroll 1
@@ -339,8 +340,9 @@ __global__ void __launch_bounds__(288, 2) window_attn_kernel(const __nv_bfloat16
 #pragma unroll
         for (int nt = 0; nt < 18; ++nt) {
             const uint2 bf = __ldg(bsrc + nt * 32);
-            s[nt][0] = __uint_as_float(bf.x << 16); s[nt][1] = __uint_as_float(bf.x & 0xffff0000u);
-            s[nt][2] = __uint_as_float(bf.y << 16); s[nt][3] = __uint_as_float(bf.y & 0xffff0000u);
+            const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&bf.x));
+            const float2 b1 = __half22float2(*reinterpret_cast<const __half2*>(&bf.y));
+            s[nt][0] = b0.x; s[nt][1] = b0.y; s[nt][2] = b1.x; s[nt][3] = b1.y;
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
                 const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Ks[nt * 8 + qr][ks * 16 + qc]);
@@ -493,7 +495,9 @@ int swin_finalize(mnx_engine* e, SwinState** out, const mnx_config& cfg) {
             SW_CUDA(e, mnx_upload(e, tt, &w.rpb_t));
             {   // accumulator-fragment order of window_attn_kernel, bias / scale, packed bf16 pairs
                 std::vector<uint32_t> fr((size_t)nH * 9 * 18 * 32 * 2);
-                auto bf16_bits = [](float v) { __nv_bfloat16 b = __float2bfloat16_rn(v); uint16_t u; memcpy(&u, &b, 2); return (uint32_t)u; };
+                // fp16, not bf16: |bias / scale| stays far below 65504 and keeps 11 significant bits (the bias is added to an
+                // fp32 QK^T accumulator; bf16 here cost as much accuracy as the bf16 q / k operands themselves)
+                auto bf16_bits = [](float v) { __half b = __float2half_rn(v); uint16_t u; memcpy(&u, &b, 2); return (uint32_t)u; };
                 const float inv_scale = 1.0f / 0.17677669529663687f;
                 for (int hh = 0; hh < nH; ++hh)
                     for (int wp = 0; wp < 9; ++wp)
