@@ -43,7 +43,8 @@ struct ConvNextState {
     float *x0 = nullptr, *x1 = nullptr;
     __nv_bfloat16 *abuf = nullptr, *hbuf = nullptr;
     float* stats = nullptr;          // [splits][tokens][2] LayerNorm statistics of the block in flight
-    int split[4] = {1, 1, 4, 8};     // channel split (gridDim.z) of dwconv_stats_kernel per stage; MNX_DW_SPLIT="a,b,c,d" overrides
+    int tile[4] = {8, 8, 8, 12};     // tile side of dwconv_stats_kernel per stage (MNX_DW_TILE="a,b,c,d", values 8 or 12)
+    int split[4] = {1, 1, 1, 8};     // channel split (gridDim.z) of dwconv_stats_kernel per stage; MNX_DW_SPLIT="a,b,c,d" overrides
     size_t max_tokens = 0;
     int last_B = 0, last_H = 0, last_W = 0;
     int cta_limit = 0;   // cap of the persistent GEMM grids for the forward in progress (EncoderState::cta_limit)
@@ -56,15 +57,19 @@ struct ConvNextState {
 // W' = W diag(gamma) -- so this kernel never revisits its output.  (The previous version normalised in place once all
 // channels of a pixel were known: re-reading its own bf16 output from L2 was 45 % of its samples in the ncu capture
 // profiles/r1c_summary.md, a latency chain of 128 dependent load -> store pairs per lane.)
-// One CTA = 8 x 8 output pixels x (C / gridDim.z) channels, 4 warps; warp w owns output rows 2w and 2w+1.  Channels
-// are processed 64 at a time (lane = a PAIR of channels, arithmetic on packed fp32x2 FFMA2): the 14 x 14 x 64 input
+// One CTA = 12 x 12 output pixels x (C / gridDim.z) channels, 6 warps; warp w owns output rows 2w and 2w+1.  Channels
+// are processed 64 at a time (lane = a PAIR of channels, arithmetic on packed fp32x2 FFMA2): the 18 x 18 x 64 input
 // halo tile and the 49 x 64 weight tile of a chunk are fetched by TMA (4-D / 2-D tensor maps; out-of-bounds zero fill
-// is the conv's zero padding) into a single 62.5 KB stage, three CTAs per SM hide each other's TMA waits -- which is
-// why the channel range is split over gridDim.z when the map is small (stages 2 and 3 would otherwise leave SMs with
-// one or two resident CTAs that stall on every chunk).  Every input row that is read (14 x 8 bytes per lane) feeds
-// BOTH output rows of the warp (kernel rows ky and ky-1; the previous weight row stays in registers): 21 shared
-// loads per 112 FFMA2.  Statistics: fp32 sum / sum of squares of the UNROUNDED conv outputs per pixel over this
-// CTA's channels -> stats[blockIdx.z][pixel] (the GEMM epilogue adds the gridDim.z partials in a fixed order).
+// is the conv's zero padding) into a single 93 KB stage, two CTAs per SM.  Tile size: the kernel's real bound is the
+// L2 -> shared-memory fill -- with 8 x 8 tiles ((14 x 14 x 256 + 12.5 K) bytes per 64 x 64 outputs = 15.3 B per output)
+// every stage of the network ran at the same ~6 TB/s of fill whatever the grid / occupancy / pipelining (measured: one
+// to three resident CTAs, 1-16 channel splits, a persistent two-stage ring), i.e. the FMA roofline of stage 2 would
+// have needed 11.6 TB/s of the chip's ~12.4 TB/s L2 cap; 12 x 12 tiles fetch 10.4 B per output and divide every map of
+// a 384 x 384 image exactly.  Every input row that is read (18 x 8 bytes per lane) feeds BOTH output rows of the warp
+// (kernel rows ky and ky-1; the previous weight row stays in registers): 25 shared loads per 168 FFMA2.  Statistics:
+// fp32 sum / sum of squares of the UNROUNDED conv outputs per pixel, reduced over the warp's lanes after every chunk
+// (47 shuffles: the 48 per-lane partials would not fit in registers next to the accumulators) and carried in two
+// registers -> stats[blockIdx.z][pixel] (the GEMM epilogue adds the gridDim.z partials in a fixed order).
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     unsigned long long r;
@@ -75,19 +80,22 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     return *reinterpret_cast<float2*>(&r);
 }
 
-#define DW_TILE 8
-#define DW_IN (DW_TILE + 6)
-#define DW_IN_FLOATS (DW_IN * DW_IN * 64)
+// tile side TS = 8 (4 warps, three CTAs per SM) or 12 (6 warps, two CTAs per SM; 10.4 instead of 15.3 fetched bytes per output)
+template <int TS> struct DwCfg {
+    static constexpr int WARPS = TS / 2, IN = TS + 6, IN_FLOATS = IN * IN * 64;
+    static constexpr int SMEM = (IN_FLOATS + 49 * 64) * 4 + 16 + 128;
+    static constexpr int CTAS = TS == 8 ? 3 : 2;
+};
 #define DW_W_FLOATS (49 * 64)
-#define DW_SMEM ((DW_IN_FLOATS + DW_W_FLOATS) * 4 + 16 + 128)
 
-template <int C>
-__global__ void __launch_bounds__(128, 3) dwconv_stats_kernel(const __grid_constant__ CUtensorMap tmap_x,
+template <int C, int TS>
+__global__ void __launch_bounds__(32 * DwCfg<TS>::WARPS, DwCfg<TS>::CTAS) dwconv_stats_kernel(const __grid_constant__ CUtensorMap tmap_x,
                                                               const __grid_constant__ CUtensorMap tmap_w, int H, int W,
                                                               const float* __restrict__ dw_b,
                                                               __nv_bfloat16* __restrict__ out, float* __restrict__ stats) {
+    constexpr int DW_TILE = TS, DW_IN = DwCfg<TS>::IN, DW_IN_FLOATS = DwCfg<TS>::IN_FLOATS;
     extern __shared__ __align__(128) uint8_t smem_raw[];           // (no integer round trip: keeps LDS, not generic LD)
-    float* in_buf = reinterpret_cast<float*>(smem_raw);            // [14][14][64]
+    float* in_buf = reinterpret_cast<float*>(smem_raw);            // [TS + 6][TS + 6][64]
     float* w_buf = in_buf + DW_IN_FLOATS;                          // [49][64]
     uint64_t* bar = reinterpret_cast<uint64_t*>(w_buf + DW_W_FLOATS);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -121,10 +129,12 @@ __global__ void __launch_bounds__(128, 3) dwconv_stats_kernel(const __grid_const
     };
     if (threadIdx.x == 0) issue(chunk0);
 
-    // this lane's share of each pixel's channel sum / sum of squares: st[(r * 8 + ox) * 2 + {0: sum, 1: squares}]
-    float st[32];
+    // running warp totals of the 48 statistics value v = (r * 12 + ox) * 2 + {0: sum, 1: squares}: lane L carries value L in
+    // tot_a and value 32 + (L >> 1) in tot_b
+    float tot_a = 0.f, tot_b = 0.f;
+    float st8[TS == 8 ? 32 : 1];       // TS == 8: per-lane partials of value (r * 8 + ox) * 2 + k, reduced once at the end
 #pragma unroll
-    for (int i = 0; i < 32; ++i) st[i] = 0.f;
+    for (int i = 0; i < (TS == 8 ? 32 : 1); ++i) st8[i] = 0.f;
 
     const float2* tin = reinterpret_cast<const float2*>(in_buf);
     const float2* tw = reinterpret_cast<const float2*>(w_buf);
@@ -165,12 +175,25 @@ __global__ void __launch_bounds__(128, 3) dwconv_stats_kernel(const __grid_const
         }
         __syncthreads();   // everyone is done with the stage: refill it while the results are written out
         if (threadIdx.x == 0 && ci + 1 < nchunk) issue(chunk0 + ci + 1);
+        if constexpr (TS == 8) {
+            // 32 per-lane partials fit in registers next to the 8-wide accumulators: one reduction per CTA (below)
+#pragma unroll
+            for (int ox = 0; ox < DW_TILE; ++ox) {
+                st8[ox * 2] += acc0[ox].x + acc0[ox].y;
+                st8[ox * 2 + 1] = fmaf(acc0[ox].x, acc0[ox].x, fmaf(acc0[ox].y, acc0[ox].y, st8[ox * 2 + 1]));
+                st8[16 + ox * 2] += acc1[ox].x + acc1[ox].y;
+                st8[16 + ox * 2 + 1] = fmaf(acc1[ox].x, acc1[ox].x, fmaf(acc1[ox].y, acc1[ox].y, st8[16 + ox * 2 + 1]));
+            }
+        }
+        float st[TS == 12 ? 48 : 1];
 #pragma unroll
         for (int ox = 0; ox < DW_TILE; ++ox) {
-            st[ox * 2] += acc0[ox].x + acc0[ox].y;
-            st[ox * 2 + 1] = fmaf(acc0[ox].x, acc0[ox].x, fmaf(acc0[ox].y, acc0[ox].y, st[ox * 2 + 1]));
-            st[16 + ox * 2] += acc1[ox].x + acc1[ox].y;
-            st[16 + ox * 2 + 1] = fmaf(acc1[ox].x, acc1[ox].x, fmaf(acc1[ox].y, acc1[ox].y, st[16 + ox * 2 + 1]));
+            if constexpr (TS == 12) {
+                st[ox * 2] = acc0[ox].x + acc0[ox].y;
+                st[ox * 2 + 1] = fmaf(acc0[ox].x, acc0[ox].x, acc0[ox].y * acc0[ox].y);
+                st[2 * DW_TILE + ox * 2] = acc1[ox].x + acc1[ox].y;
+                st[2 * DW_TILE + ox * 2 + 1] = fmaf(acc1[ox].x, acc1[ox].x, acc1[ox].y * acc1[ox].y);
+            }
             const int x = x0 + ox;
             if (x < W) {
                 if (yA < H)
@@ -179,24 +202,61 @@ __global__ void __launch_bounds__(128, 3) dwconv_stats_kernel(const __grid_const
                     *reinterpret_cast<__nv_bfloat162*>(out + (((size_t)b * H + yA + 1) * W + x) * C + c) = __floats2bfloat162_rn(acc1[ox].x, acc1[ox].y);
             }
         }
-    }
-    // transposing warp reduction: 32 values per lane -> lane L holds the warp total of value L (31 shuffles)
+        if constexpr (TS == 12) {
+            // transposing warp reductions after every chunk (the 48 per-lane partials would not fit in registers next to the
+            // 12-wide accumulators): values 0..31 -> lane L ends with the warp total of value L (31 shuffles); values 32..47 ->
+            // lanes 2i and 2i+1 end with the total of value 32 + i (16 shuffles)
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        const bool hi = (lane & off) != 0;
+            for (int off = 16; off >= 1; off >>= 1) {
+                const bool hi = (lane & off) != 0;
 #pragma unroll
-        for (int i = 0; i < off; ++i) {
-            const float keep = hi ? st[i + off] : st[i];
-            const float send = hi ? st[i] : st[i + off];
-            st[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                for (int i = 0; i < off; ++i) {
+                    const float keep = hi ? st[i + off] : st[i];
+                    const float send = hi ? st[i] : st[i + off];
+                    st[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+            tot_a += st[0];
+#pragma unroll
+            for (int off = 16, n = 8; off >= 2; off >>= 1, n >>= 1) {
+                const bool hi = (lane & off) != 0;
+#pragma unroll
+                for (int i = 0; i < n; ++i) {
+                    const float keep = hi ? st[32 + i + n] : st[32 + i];
+                    const float send = hi ? st[32 + i] : st[32 + i + n];
+                    st[32 + i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+            st[32] += __shfl_xor_sync(0xffffffffu, st[32], 1);
+            tot_b += st[32];
         }
     }
+    if constexpr (TS == 8) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const bool hi = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+                const float keep = hi ? st8[i + off] : st8[i];
+                const float send = hi ? st8[i] : st8[i + off];
+                st8[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+        }
+        tot_a = st8[0];
+    }
     {
-        const int pix = lane >> 1, r = pix >> 3, ox = pix & 7;      // value L = (r * 8 + ox) * 2 + k
-        const int y = yA + r, x = x0 + ox;
-        if (y < H && x < W) {
-            const size_t M = (size_t)gridDim.y * H * W;
-            stats[((size_t)blockIdx.z * M + ((size_t)b * H + y) * W + x) * 2 + (lane & 1)] = st[0];
+        const size_t M = (size_t)gridDim.y * H * W;
+        float* dst = stats + (size_t)blockIdx.z * M * 2;
+        {   // value L = (r * 12 + ox) * 2 + k
+            const int pix = lane >> 1, r = pix / DW_TILE, ox = pix % DW_TILE;
+            const int y = yA + r, x = x0 + ox;
+            if (y < H && x < W) dst[(((size_t)b * H + y) * W + x) * 2 + (lane & 1)] = tot_a;
+        }
+        if (TS == 12 && (lane & 1) == 0) {   // value 32 + (L >> 1): after the four halving steps lane L holds index 8 b16 + 4 b8 + 2 b4 + b2
+            const int v = 32 + (lane >> 1);
+            const int pix = v >> 1, r = pix / DW_TILE, ox = pix % DW_TILE;
+            const int y = yA + r, x = x0 + ox;
+            if (y < H && x < W) dst[(((size_t)b * H + y) * W + x) * 2 + (v & 1)] = tot_b;
         }
     }
 }
@@ -291,10 +351,14 @@ int convnext_finalize(mnx_engine* e, ConvNextState** out, const mnx_config& cfg)
         if (qres != cudaDriverEntryPointSuccess || !fn) { mnx_set_error(e, "cuTensorMapEncodeTiled unavailable"); return MNX_ERR_CUDA; }
         g_cn_encode = reinterpret_cast<PFN_encodeTiled>(fn);
     }
-    CN_CUDA(e, cudaFuncSetAttribute(dwconv_stats_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM));
-    CN_CUDA(e, cudaFuncSetAttribute(dwconv_stats_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM));
-    CN_CUDA(e, cudaFuncSetAttribute(dwconv_stats_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM));
-    CN_CUDA(e, cudaFuncSetAttribute(dwconv_stats_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM));
+    CN_CUDA(e, (cudaFuncSetAttribute(dwconv_stats_kernel<128, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwCfg<8>::SMEM)));
+    CN_CUDA(e, (cudaFuncSetAttribute(dwconv_stats_kernel<256, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwCfg<8>::SMEM)));
+    CN_CUDA(e, (cudaFuncSetAttribute(dwconv_stats_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwCfg<8>::SMEM)));
+    CN_CUDA(e, (cudaFuncSetAttribute(dwconv_stats_kernel<1024, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwCfg<8>::SMEM)));
+    CN_CUDA(e, (cudaFuncSetAttribute(dwconv_stats_kernel<128, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwCfg<12>::SMEM)));
+    CN_CUDA(e, (cudaFuncSetAttribute(dwconv_stats_kernel<256, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwCfg<12>::SMEM)));
+    CN_CUDA(e, (cudaFuncSetAttribute(dwconv_stats_kernel<512, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwCfg<12>::SMEM)));
+    CN_CUDA(e, (cudaFuncSetAttribute(dwconv_stats_kernel<1024, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, DwCfg<12>::SMEM)));
     if (cfg.max_height % 32 != 0 || cfg.max_width % 32 != 0) {
         mnx_set_error(e, "ConvNeXt-B needs image bounds that are multiples of 32");
         return MNX_ERR_INVALID;
@@ -370,6 +434,12 @@ int convnext_finalize(mnx_engine* e, ConvNextState** out, const mnx_config& cfg)
     CN_CUDA(e, mnx_dev_alloc_bytes(e, &p, tok * 128 * sizeof(float) / 2 + 1024)); st->x1 = (float*)p;
     CN_CUDA(e, mnx_dev_alloc_bytes(e, &p, tok * 128 * 2)); st->abuf = (__nv_bfloat16*)p;
     CN_CUDA(e, mnx_dev_alloc_bytes(e, &p, tok * 512 * 2)); st->hbuf = (__nv_bfloat16*)p;
+    if (const char* env = getenv("MNX_DW_TILE")) {
+        int v[4];
+        if (sscanf(env, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]) == 4)
+            for (int i = 0; i < 4; ++i)
+                if (v[i] == 8 || v[i] == 12) st->tile[i] = v[i];
+    }
     if (const char* env = getenv("MNX_DW_SPLIT")) {     // kernel tuning only (A/B timing on the GPU box)
         int v[4];
         if (sscanf(env, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]) == 4)
@@ -397,9 +467,10 @@ static cudaError_t cn_gemm(const __nv_bfloat16* A, const __nv_bfloat16* W, long 
     return gemm_tc_launch(p, s);
 }
 
-template <int C>
+template <int C, int TS>
 static int launch_dwconv_t(mnx_engine* e, const float* x, int B, int H, int W, const CnBlockW& w, __nv_bfloat16* out,
                            float* stats, int split, cudaStream_t s) {
+    constexpr int DW_TILE = TS, DW_IN = DwCfg<TS>::IN;
     CUtensorMap map, wmap;
     {
         const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -422,17 +493,25 @@ static int launch_dwconv_t(mnx_engine* e, const float* x, int B, int H, int W, c
         if (r != CUDA_SUCCESS) { mnx_set_error(e, "cuTensorMapEncodeTiled failed for the dwconv weights"); return MNX_ERR_CUDA; }
     }
     const int tiles = ((H + DW_TILE - 1) / DW_TILE) * ((W + DW_TILE - 1) / DW_TILE);
-    dwconv_stats_kernel<C><<<dim3(tiles, B, split), 128, DW_SMEM, s>>>(map, wmap, H, W, w.dw_b, out, stats);
+    dwconv_stats_kernel<C, TS><<<dim3(tiles, B, split), 32 * DwCfg<TS>::WARPS, DwCfg<TS>::SMEM, s>>>(map, wmap, H, W, w.dw_b, out, stats);
     CN_CUDA(e, cudaGetLastError());
     return MNX_OK;
 }
 static int launch_dwconv(mnx_engine* e, const float* x, int B, int H, int W, int C, const CnBlockW& w, __nv_bfloat16* out,
-                         float* stats, int split, cudaStream_t s) {
+                         float* stats, int split, int tile, cudaStream_t s) {
+    if (tile == 12) {
+        switch (C) {
+            case 128: return launch_dwconv_t<128, 12>(e, x, B, H, W, w, out, stats, split, s);
+            case 256: return launch_dwconv_t<256, 12>(e, x, B, H, W, w, out, stats, split, s);
+            case 512: return launch_dwconv_t<512, 12>(e, x, B, H, W, w, out, stats, split, s);
+            default: return launch_dwconv_t<1024, 12>(e, x, B, H, W, w, out, stats, split, s);
+        }
+    }
     switch (C) {
-        case 128: return launch_dwconv_t<128>(e, x, B, H, W, w, out, stats, split, s);
-        case 256: return launch_dwconv_t<256>(e, x, B, H, W, w, out, stats, split, s);
-        case 512: return launch_dwconv_t<512>(e, x, B, H, W, w, out, stats, split, s);
-        default: return launch_dwconv_t<1024>(e, x, B, H, W, w, out, stats, split, s);
+        case 128: return launch_dwconv_t<128, 8>(e, x, B, H, W, w, out, stats, split, s);
+        case 256: return launch_dwconv_t<256, 8>(e, x, B, H, W, w, out, stats, split, s);
+        case 512: return launch_dwconv_t<512, 8>(e, x, B, H, W, w, out, stats, split, s);
+        default: return launch_dwconv_t<1024, 8>(e, x, B, H, W, w, out, stats, split, s);
     }
 }
 
@@ -466,7 +545,7 @@ int convnext_forward(mnx_engine* e, ConvNextState* st, const float* images, int 
         const long long M = (long long)B * Hc * Wc;
         for (int j = 0; j < CN_DEPTH[stage]; ++j) {
             const CnBlockW& w = st->blocks[stage][j];
-            CN_TRY(launch_dwconv(e, x, B, Hc, Wc, C, w, st->abuf, st->stats, st->split[stage], s));
+            CN_TRY(launch_dwconv(e, x, B, Hc, Wc, C, w, st->abuf, st->stats, st->split[stage], st->tile[stage], s));
             ++nl;
             CN_CUDA(e, cn_gemm(st->abuf, w.fc1_w, M, 4 * C, C, GEMM_EPI_LNFOLD_GELU_BF16, w.fc1_b, nullptr, st->hbuf, s, st->cta_limit,
                                w.fc1_colsum, st->stats, st->split[stage])); ++nl;
@@ -491,7 +570,7 @@ int convnext_time_kernel(mnx_engine* e, ConvNextState* st, int which, int iters,
     int rc = MNX_OK;
     for (int i = 0; i < 3 + iters && rc == MNX_OK; ++i) {
         if (i == 3) cudaEventRecord(e0, s);
-        rc = launch_dwconv(e, x, B, Hc, Wc, C, w, st->abuf, st->stats, st->split[stage], s);
+        rc = launch_dwconv(e, x, B, Hc, Wc, C, w, st->abuf, st->stats, st->split[stage], st->tile[stage], s);
     }
     cudaEventRecord(e1, s);
     cudaStreamSynchronize(s);

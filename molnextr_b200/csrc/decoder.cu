@@ -17,6 +17,7 @@
 #include "decoder.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace mnx {
 
@@ -330,6 +331,181 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(SkinnyArgs a) {
             a.out[(size_t)rank * a.N + n] = gelu_erf(v);
         } else {   // EPI_PART: k-slice partial of the W2 product; bias and residual are added by the consumer
             a.out[((size_t)rank * 8 + kslice) * MNX_DEC_D + n] = v;
+        }
+    }
+}
+
+// =====================================================================================
+// The same Linear for MANY rows (beam search: images x beams = up to 1280; greedy shards of > 288 rows): a register-
+// tiled fp32 GEMM with the skinny kernel's prologues and epilogues.  One CTA = 64 rows x 64 output columns, 256 threads
+// as 16 x 16, each thread 4 rows x 4 columns; activations of the 64 rows sit in shared memory ([64][K + 4], the
+// LayerNorm is applied there), weights stream through a double-buffered [32 k][64 cols] tile.  Per 4 k a thread issues
+// 4 + 4 LDS.128 for 64 FMA (the skinny kernel: one broadcast LDS.128 per 4 FMA per lane, which is what held it to
+// ~8 % of the FMA peak at 1280 rows).  Same arithmetic per output as skinny_gemm_kernel except the order of the k sum
+// (sequential here, 8 warp-partials there): results agree to fp32 rounding, ids are checked by the same tests.
+// =====================================================================================
+#define TG_ROWS 64
+#define TG_COLS 64
+#define TG_KC 32
+template <int K, int PRO, int EPI>
+__global__ void __launch_bounds__(256, 2) tile_gemm_kernel(SkinnyArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int LDX = K + 4;
+    float* Xs = smem;                          // [64][K + 4]
+    float* Ws = smem + TG_ROWS * LDX;          // [2][32][64]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int n_alive = a.st->n_alive;
+    const int rank0 = blockIdx.y * TG_ROWS;
+    if (rank0 >= n_alive) return;
+    const int nrows = min(TG_ROWS, n_alive - rank0);
+    const int n0 = blockIdx.x * TG_COLS;
+    const int kslice = blockIdx.z;
+    const float* wbase = a.wt + (size_t)kslice * K * a.N + n0;     // row k of this CTA's weight tile: wbase + k * N
+
+    // first weight tile in flight before the prologue
+    float4 wreg[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int idx = tid + 256 * j;                 // 512 float4 = 32 k x 16 column quads
+        wreg[j] = *reinterpret_cast<const float4*>(wbase + (size_t)(idx >> 4) * a.N + (idx & 15) * 4);
+    }
+
+    // ---------------- prologue: fill Xs (identical arithmetic to skinny_gemm_kernel) ----------------
+    if (PRO == PRO_PLAIN) {
+        for (int idx = tid; idx < TG_ROWS * (K / 4); idx += 256) {
+            const int r = idx / (K / 4), c4 = idx % (K / 4);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < nrows)
+                v = reinterpret_cast<const float4*>(a.x_in + (size_t)(rank0 + r) * a.x_stride + kslice * K)[c4];
+            *reinterpret_cast<float4*>(Xs + r * LDX + 4 * c4) = v;
+        }
+        __syncthreads();
+    } else {
+        for (int idx = tid; idx < TG_ROWS * 64; idx += 256) {
+            const int r = idx >> 6, c4 = idx & 63;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < nrows) {
+                v = reinterpret_cast<const float4*>(a.x_in + (size_t)(rank0 + r) * MNX_DEC_D)[c4];
+                if (PRO == PRO_SUM_LN) {
+                    const float4 bb = reinterpret_cast<const float4*>(a.bo)[c4];
+                    const float* pr = a.part + (size_t)(rank0 + r) * 8 * MNX_DEC_D;
+                    float4 p[8];
+#pragma unroll
+                    for (int h = 0; h < 8; ++h) p[h] = reinterpret_cast<const float4*>(pr + h * MNX_DEC_D)[c4];
+                    float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int h = 0; h < 8; ++h) { sacc.x += p[h].x; sacc.y += p[h].y; sacc.z += p[h].z; sacc.w += p[h].w; }
+                    v.x = (sacc.x + bb.x) + v.x; v.y = (sacc.y + bb.y) + v.y;
+                    v.z = (sacc.z + bb.z) + v.z; v.w = (sacc.w + bb.w) + v.w;
+                    if (blockIdx.x == 0)
+                        reinterpret_cast<float4*>(a.x_sum_out + (size_t)(rank0 + r) * MNX_DEC_D)[c4] = v;
+                }
+            }
+            *reinterpret_cast<float4*>(Xs + r * LDX + 4 * c4) = v;
+        }
+        __syncthreads();
+        const float4 g0 = reinterpret_cast<const float4*>(a.ln_w)[lane];
+        const float4 g1 = reinterpret_cast<const float4*>(a.ln_w)[lane + 32];
+        const float4 c0 = reinterpret_cast<const float4*>(a.ln_b)[lane];
+        const float4 c1 = reinterpret_cast<const float4*>(a.ln_b)[lane + 32];
+        for (int r = wid; r < nrows; r += 8) {
+            float4 v0 = *reinterpret_cast<float4*>(Xs + r * LDX + 4 * lane);
+            float4 v1 = *reinterpret_cast<float4*>(Xs + r * LDX + 4 * (lane + 32));
+            const float sum = ((v0.x + v0.y) + (v0.z + v0.w)) + ((v1.x + v1.y) + (v1.z + v1.w));
+            const float mean = warp_sum(sum) * (1.0f / MNX_DEC_D);
+            v0.x -= mean; v0.y -= mean; v0.z -= mean; v0.w -= mean;
+            v1.x -= mean; v1.y -= mean; v1.z -= mean; v1.w -= mean;
+            const float sq = ((v0.x * v0.x + v0.y * v0.y) + (v0.z * v0.z + v0.w * v0.w)) +
+                             ((v1.x * v1.x + v1.y * v1.y) + (v1.z * v1.z + v1.w * v1.w));
+            const float var = warp_sum(sq) * (1.0f / MNX_DEC_D);
+            const float rstd = 1.0f / sqrtf(var + 1e-6f);
+            v0.x = v0.x * rstd * g0.x + c0.x; v0.y = v0.y * rstd * g0.y + c0.y;
+            v0.z = v0.z * rstd * g0.z + c0.z; v0.w = v0.w * rstd * g0.w + c0.w;
+            v1.x = v1.x * rstd * g1.x + c1.x; v1.y = v1.y * rstd * g1.y + c1.y;
+            v1.z = v1.z * rstd * g1.z + c1.z; v1.w = v1.w * rstd * g1.w + c1.w;
+            *reinterpret_cast<float4*>(Xs + r * LDX + 4 * lane) = v0;
+            *reinterpret_cast<float4*>(Xs + r * LDX + 4 * (lane + 32)) = v1;
+        }
+        // (the barrier of the first k-chunk below orders these writes before the reads)
+    }
+
+    // ---------------- main loop ----------------
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    constexpr int NCH = K / TG_KC;
+#pragma unroll 1
+    for (int ch = 0; ch < NCH; ++ch) {
+        float* wt = Ws + (ch & 1) * (TG_KC * TG_COLS);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int idx = tid + 256 * j;
+            *reinterpret_cast<float4*>(wt + (idx >> 4) * TG_COLS + (idx & 15) * 4) = wreg[j];
+        }
+        __syncthreads();          // tile ch visible; every thread is done with tile ch-1 (the buffer the NEXT store overwrites)
+        if (ch + 1 < NCH) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int idx = tid + 256 * j;
+                wreg[j] = *reinterpret_cast<const float4*>(wbase + (size_t)((ch + 1) * TG_KC + (idx >> 4)) * a.N + (idx & 15) * 4);
+            }
+        }
+        const float* xs = Xs + (4 * ty) * LDX + ch * TG_KC;
+#pragma unroll
+        for (int kk = 0; kk < TG_KC; kk += 4) {
+            float4 xv[4], wv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(xs + i * LDX + kk);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) wv[q] = *reinterpret_cast<const float4*>(wt + (kk + q) * TG_COLS + 4 * tx);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                acc[i][0] = fmaf(xv[i].x, wv[0].x, acc[i][0]); acc[i][1] = fmaf(xv[i].x, wv[0].y, acc[i][1]);
+                acc[i][2] = fmaf(xv[i].x, wv[0].z, acc[i][2]); acc[i][3] = fmaf(xv[i].x, wv[0].w, acc[i][3]);
+                acc[i][0] = fmaf(xv[i].y, wv[1].x, acc[i][0]); acc[i][1] = fmaf(xv[i].y, wv[1].y, acc[i][1]);
+                acc[i][2] = fmaf(xv[i].y, wv[1].z, acc[i][2]); acc[i][3] = fmaf(xv[i].y, wv[1].w, acc[i][3]);
+                acc[i][0] = fmaf(xv[i].z, wv[2].x, acc[i][0]); acc[i][1] = fmaf(xv[i].z, wv[2].y, acc[i][1]);
+                acc[i][2] = fmaf(xv[i].z, wv[2].z, acc[i][2]); acc[i][3] = fmaf(xv[i].z, wv[2].w, acc[i][3]);
+                acc[i][0] = fmaf(xv[i].w, wv[3].x, acc[i][0]); acc[i][1] = fmaf(xv[i].w, wv[3].y, acc[i][1]);
+                acc[i][2] = fmaf(xv[i].w, wv[3].z, acc[i][2]); acc[i][3] = fmaf(xv[i].w, wv[3].w, acc[i][3]);
+            }
+        }
+    }
+
+    // ---------------- epilogue ----------------
+    const int n = n0 + 4 * tx;                                   // first of this thread's four columns
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (EPI != EPI_PART) bias = *reinterpret_cast<const float4*>(a.bias + n);
+    const int t = a.st->step;
+    const int* alive = a.alive + (t & 1) * a.B;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = 4 * ty + i;
+        if (r >= nrows) break;
+        const int rank = rank0 + r;
+        float4 v = make_float4(acc[i][0] + bias.x, acc[i][1] + bias.y, acc[i][2] + bias.z, acc[i][3] + bias.w);
+        if (EPI == EPI_QKV) {
+            const int sec = n >> 8, f = n & 255;
+            if (sec == 0) {
+                v.x = v.x / SKINNY_QSCALE; v.y = v.y / SKINNY_QSCALE; v.z = v.z / SKINNY_QSCALE; v.w = v.w / SKINNY_QSCALE;
+                *reinterpret_cast<float4*>(a.out + (size_t)rank * MNX_DEC_D + f) = v;
+            } else {
+                const int row = alive[rank];
+                const int h = f >> 5, d = f & 31;
+                float* dst = (sec == 1) ? a.kc : a.vc;
+                *reinterpret_cast<float4*>(dst + (((size_t)row * 8 + h) * a.T + t) * 32 + d) = v;
+            }
+        } else if (EPI == EPI_Q) {
+            v.x = v.x / SKINNY_QSCALE; v.y = v.y / SKINNY_QSCALE; v.z = v.z / SKINNY_QSCALE; v.w = v.w / SKINNY_QSCALE;
+            *reinterpret_cast<float4*>(a.out + (size_t)rank * MNX_DEC_D + n) = v;
+        } else if (EPI == EPI_GELU) {
+            v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+            *reinterpret_cast<float4*>(a.out + (size_t)rank * a.N + n) = v;
+        } else {
+            *reinterpret_cast<float4*>(a.out + ((size_t)rank * 8 + kslice) * MNX_DEC_D + n) = v;
         }
     }
 }
@@ -1078,8 +1254,18 @@ __global__ void edge_sym_kernel(const float* __restrict__ prob, const int* __res
 // =====================================================================================
 // host-side launchers
 // =====================================================================================
+#define TG_MIN_ROWS 128     // row capacity from which the register-tiled kernel replaces the skinny one
+static int g_tile_min_rows = TG_MIN_ROWS;   // MNX_TILE_GEMM_MIN_ROWS overrides it (tests run the small fixtures through the tiled kernel)
+template <int K>
+constexpr size_t tile_gemm_smem() { return (size_t)(TG_ROWS * (K + 4) + 2 * TG_KC * TG_COLS) * sizeof(float); }
+
 template <int K, int PRO, int EPI>
 static cudaError_t launch_skinny(const SkinnyArgs& a, int B, cudaStream_t s) {
+    if (B >= g_tile_min_rows) {
+        dim3 grid(a.N / TG_COLS, (B + TG_ROWS - 1) / TG_ROWS, EPI == EPI_PART ? 8 : 1);
+        tile_gemm_kernel<K, PRO, EPI><<<grid, 256, tile_gemm_smem<K>(), s>>>(a);
+        return cudaGetLastError();
+    }
     const size_t smem = (size_t)(32 * K + 8 * 32 * 32) * sizeof(float);
     dim3 grid(a.N / 32, (B + 31) / 32, EPI == EPI_PART ? 8 : 1);
     skinny_gemm_kernel<K, PRO, EPI><<<grid, 256, smem, s>>>(a);
@@ -1089,6 +1275,8 @@ static cudaError_t launch_skinny(const SkinnyArgs& a, int B, cudaStream_t s) {
 template <int K, int PRO, int EPI>
 static cudaError_t configure_skinny() {
     const size_t smem = (size_t)(32 * K + 8 * 32 * 32) * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(tile_gemm_kernel<K, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_gemm_smem<K>());
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(skinny_gemm_kernel<K, PRO, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
@@ -1128,6 +1316,8 @@ cudaError_t dec_label_merge(const DecBuffers& b, int lab_len, cudaStream_t s) {
 
 cudaError_t dec_configure() {
     cudaError_t e;
+    const char* env = getenv("MNX_TILE_GEMM_MIN_ROWS");
+    g_tile_min_rows = (env && atoi(env) > 0) ? atoi(env) : TG_MIN_ROWS;
     if ((e = configure_skinny<256, PRO_LN, EPI_QKV>()) != cudaSuccess) return e;
     if ((e = configure_skinny<256, PRO_SUM_LN, EPI_QKV>()) != cudaSuccess) return e;
     if ((e = configure_skinny<256, PRO_SUM_LN, EPI_Q>()) != cudaSuccess) return e;
@@ -1300,16 +1490,22 @@ cudaError_t dec_time_kernel(int which, int iters, const DecBuffers& b, const Dec
     const DecLayerW& L = w.layer[0];
     const size_t kv_layer = (size_t)b.B * 8 * b.T * 32;
     (void)kv_layer;
+    int call = 0;
     auto once = [&]() -> cudaError_t {
         SkinnyArgs a{};
         a.st = b.st; a.alive = b.alive; a.B = b.B;
         AttnArgs at{};
         at.st = b.st; at.alive = b.alive; at.B = b.B; at.q = b.q; at.part = b.part; at.kv_div = 1;
         switch (which) {
-            case 1:
-                at.Kc = b.crossK; at.Vc = b.crossV; at.cap = b.S; at.nkeys_cross = b.S; at.wo_t = L.wo_c_t;
+            case 1: {
+                // walk the six layers' memory-bank K/V like a decode step does (56 MB at bs = 32: L2-resident, as in the real
+                // loop; 453 MB at bs = 256: every launch streams from HBM)
+                const size_t cross_layer = (size_t)b.B * 8 * b.S * 32;
+                const int l = call++ % MNX_DEC_L;
+                at.Kc = b.crossK + l * cross_layer; at.Vc = b.crossV + l * cross_layer; at.cap = b.S; at.nkeys_cross = b.S; at.wo_t = L.wo_c_t;
                 attn_kernel<false><<<dim3(b.B, 8), 128, 0, s>>>(at);
                 return cudaGetLastError();
+            }
             case 2:
                 at.Kc = b.selfK; at.Vc = b.selfV; at.cap = b.T; at.wo_t = L.wo_s_t;
                 attn_kernel<true><<<dim3(b.B, 8), 128, 0, s>>>(at);

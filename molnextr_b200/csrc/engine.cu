@@ -757,6 +757,9 @@ static int decode_internal(mnx_engine* e, const float* features, int B, int S, c
         return fail(e, MNX_ERR_CAPACITY, "throughput decode kernel forced but B=%d S=%d T=%d does not fit (%d clusters resident, <= %d keys)",
                     B, S, T, e->max_clusters_w, MGW_MAX_KEYS_H);
     // partial-label decoding lives on the multi-kernel graph path only
+    // the throughput kernel is opt-in (predict_pipelined / mnx_set_decode_path): it wins when several batches decode side
+    // by side on 16 SMs each; ONE batch of 256 rows on 16 clusters measured 331 ms against 262 ms on the multi-kernel
+    // graph path (its per-warp 4 KB K/V copies do not keep enough HBM traffic in flight once the caches outgrow L2)
     const bool usew = !labels && e->decode_path == 6;
     const bool use16 = !labels && !usew && ((e->decode_path == 3) || (e->decode_path == 0 && fits16));
     const bool use8 = !labels && !usew && !use16 && ((e->decode_path == 2) || (e->decode_path == 0 && fits8));

@@ -12,6 +12,7 @@
 #include "gemm_tc.cuh"
 
 #include <cuda.h>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -26,7 +27,8 @@ template <int BN_> struct GemmCfg {
     static constexpr int BN = BN_;
     static constexpr int STAGES = (BN_ == 128) ? 5 : 4;
     static constexpr int B_STAGE_BYTES = BN_ * BK * 2;   // 16 / 32 KB
-    static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+    // operand ring | barriers (1 KB slot) | 8 x 4 KB epilogue staging tiles (TMA stores), all 1024-byte aligned
+    static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 1024 /*barriers*/ + 8 * 4096;
     static constexpr uint32_t TMEM_COLS = 2 * BN_;       // two accumulators
 };
 static constexpr int GEMM_THREADS = 320;   // producer warp + MMA warp + 8 epilogue warps
@@ -107,7 +109,25 @@ struct GemmKernelArgs {
     const float* ln_stats;
     int ln_splits;
     float ln_eps;
+    int tma_out;   // 1: results leave through shared memory and TMA (bf16 tile stores / fp32 reduce-add into the residual stream)
 };
+
+// ---- epilogue through TMA -------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // GELU(erf) for the bf16-output epilogue, two elements per instruction on packed fp32 pairs and WITHOUT the special
 // function unit: gelu(x) = 0.5 x + 0.5 |x| erf(|x| / sqrt 2), erf(z) = z P(2 z^2 / 9 - 1) on z <= 3 (degree-8 least-squares
@@ -155,7 +175,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, GemmKernelArgs g) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+               const __grid_constant__ CUtensorMap tmap_out, GemmKernelArgs g) {
     constexpr int STAGES = GemmCfg<BN>::STAGES, B_STAGE_BYTES = GemmCfg<BN>::B_STAGE_BYTES;
     constexpr uint32_t TMEM_COLS = GemmCfg<BN>::TMEM_COLS;
     extern __shared__ uint8_t smem_raw[];
@@ -168,6 +189,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint64_t* acc_full = empty_bar + STAGES;     // [2] accumulator ready for the epilogue
     uint64_t* acc_empty = acc_full + 2;          // [2] accumulator drained by the 4 epilogue warps
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint8_t* stage_out = smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024;     // [8 epilogue warps][32 rows][128 B], 128-B swizzle
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = g.K / BK;
@@ -178,6 +200,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_a)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w)) : "memory");
+        if (g.tma_out) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_out)) : "memory");
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -240,6 +263,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int q = warp & 3;                        // TMEM lane quarter this warp may access
         const int chalf = (warp - 2) >> 2;             // which half of the accumulator columns
         constexpr int CPW = BN / 64;                   // 32-column chunks per warp
+        // staging tile of this warp: row r = lane, 128 bytes, 16-byte chunk j stored at chunk (j ^ (r & 7))
+        uint8_t* stg_row = stage_out + (warp - 2) * 4096 + lane * 128;
+        const int sw = lane & 7;
+        const bool tma_bf16 = g.tma_out && g.epilogue != GEMM_EPI_RESADD_F32;
+        const bool tma_add = g.tma_out && g.epilogue == GEMM_EPI_RESADD_F32;
         uint32_t j = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
             const int n_tile = tile % n_tiles, m_tile = tile / n_tiles;
@@ -268,7 +296,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int c = chalf * CPW; c < chalf * CPW + CPW; ++c) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(c * 32), r);
-                if (!live) continue;
+                if (!live && !g.tma_out) continue;       // (TMA stores clip rows >= M themselves; every lane takes part)
                 const int n0 = n_tile * BN + c * 32;
                 float v[32];
 #pragma unroll
@@ -296,6 +324,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
                         for (int i = 0; i < 32; i += 2) gelu_erf_pair(v[i], v[i + 1]);
                     }
+                    if (tma_bf16) {
+                        // two 32-column chunks fill the warp's [32 rows][64 bf16] staging tile, then one TMA store
+                        const int half = (c - chalf * CPW) & 1;
+                        if (half == 0) {
+                            if (lane == 0) bulk_wait_read0();        // the previous store has read the tile
+                            __syncwarp();
+                        }
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            uint4 pk;
+                            pk.x = pack_bf16(v[i], v[i + 1]); pk.y = pack_bf16(v[i + 2], v[i + 3]);
+                            pk.z = pack_bf16(v[i + 4], v[i + 5]); pk.w = pack_bf16(v[i + 6], v[i + 7]);
+                            *reinterpret_cast<uint4*>(stg_row + (((half * 4 + (i >> 3)) ^ sw) << 4)) = pk;
+                        }
+                        if (half == 1) {
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0) {
+                                tma_store_2d(&tmap_out, stage_out + (warp - 2) * 4096, n0 - 32, m_tile * BM + q * 32);
+                                bulk_commit();
+                            }
+                        }
+                        continue;
+                    }
                     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(g.out) + (size_t)dst_row * g.N + n0;
 #pragma unroll
                     for (int i = 0; i < 32; i += 8) {
@@ -312,6 +364,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                             const float4 g4 = *reinterpret_cast<const float4*>(g.gamma + n0 + i);
                             v[i] *= g4.x; v[i + 1] *= g4.y; v[i + 2] *= g4.z; v[i + 3] *= g4.w;
                         }
+                    }
+                    if (tma_add) {
+                        // [32 rows][32 fp32] staging tile, added into the residual stream by the TMA unit (no read-modify-write
+                        // through the SM; every element is added exactly once per GEMM, so the result is deterministic)
+                        if (lane == 0) bulk_wait_read0();
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4)
+                            *reinterpret_cast<float4*>(stg_row + (((i >> 2) ^ sw) << 4)) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_reduce_add_2d(&tmap_out, stage_out + (warp - 2) * 4096, n0, m_tile * BM + q * 32);
+                            bulk_commit();
+                        }
+                        continue;
                     }
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
@@ -332,6 +400,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if (lane == 0) mbar_arrive(&acc_empty[acc]);
         }
     }
+    if (g.tma_out && warp >= 2 && lane == 0) bulk_wait_all();   // the staging tiles outlive the CTA otherwise
     // ---- teardown: every role is done with TMEM before it is released ----
     tc_fence_before();
     __syncthreads();
@@ -346,8 +415,10 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static PFN_encodeTiled g_encode = nullptr;
+static bool g_tma_epilogue = true;     // MNX_GEMM_TMA_EPILOGUE=0: per-lane stores (A/B timing on the GPU box)
 
 cudaError_t gemm_tc_configure() {
+    if (const char* env = getenv("MNX_GEMM_TMA_EPILOGUE")) g_tma_epilogue = env[0] != '0';
     if (g_encode == nullptr) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -373,6 +444,18 @@ static bool make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t
     return r == CUDA_SUCCESS;
 }
 
+// output map for the TMA epilogue: [rows][cols] row-major, box = [32 rows][128 bytes], 128-byte swizzle
+static bool make_out_map(CUtensorMap* map, void* base, uint64_t rows, uint64_t cols, bool f32) {
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * (f32 ? 4u : 2u)};
+    const cuuint32_t box[2] = {f32 ? 32u : 64u, 32u};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 cudaError_t gemm_tc_launch(const GemmParams& p, cudaStream_t s) {
     if (g_encode == nullptr) return cudaErrorNotReady;
     if (p.M < 1 || p.N % 128 != 0 || p.K % BK != 0 || p.K < BK) return cudaErrorInvalidValue;
@@ -382,15 +465,21 @@ cudaError_t gemm_tc_launch(const GemmParams& p, cudaStream_t s) {
     CUtensorMap ma, mw;
     if (!make_map(&ma, p.A, (uint64_t)p.M, (uint64_t)p.K, BM)) return cudaErrorInvalidValue;
     if (!make_map(&mw, p.W, (uint64_t)p.N, (uint64_t)p.K, BN)) return cudaErrorInvalidValue;
-    GemmKernelArgs g{p.M, p.N, p.K, p.epilogue, p.bias, p.gamma, p.row_map, p.out, p.colsum, p.ln_stats, p.ln_splits, p.ln_eps};
+    // TMA epilogue: bf16 outputs, and the residual add when rows are not scattered through a row map
+    const bool bf16_out = p.epilogue == GEMM_EPI_BF16 || p.epilogue == GEMM_EPI_GELU_BF16 || p.epilogue == GEMM_EPI_LNFOLD_GELU_BF16;
+    const bool add_out = p.epilogue == GEMM_EPI_RESADD_F32 && p.row_map == nullptr;
+    const int tma_out = (g_tma_epilogue && (bf16_out || add_out) && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) ? 1 : 0;
+    CUtensorMap mo = ma;
+    if (tma_out && !make_out_map(&mo, p.out, (uint64_t)p.M, (uint64_t)p.N, add_out)) return cudaErrorInvalidValue;
+    GemmKernelArgs g{p.M, p.N, p.K, p.epilogue, p.bias, p.gamma, p.row_map, p.out, p.colsum, p.ln_stats, p.ln_splits, p.ln_eps, tma_out};
     const int total_tiles = (p.N / BN) * ((p.M + BM - 1) / BM);
     int dev = 0, num_sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);     // cached by the runtime
     const int cap = (p.cta_limit > 0 && p.cta_limit < num_sms) ? p.cta_limit : num_sms;
     const int grid = total_tiles < cap ? total_tiles : cap;
-    if (BN == 256) gemm_tc_kernel<256><<<grid, GEMM_THREADS, GemmCfg<256>::SMEM_BYTES, s>>>(ma, mw, g);
-    else gemm_tc_kernel<128><<<grid, GEMM_THREADS, GemmCfg<128>::SMEM_BYTES, s>>>(ma, mw, g);
+    if (BN == 256) gemm_tc_kernel<256><<<grid, GEMM_THREADS, GemmCfg<256>::SMEM_BYTES, s>>>(ma, mw, mo, g);
+    else gemm_tc_kernel<128><<<grid, GEMM_THREADS, GemmCfg<128>::SMEM_BYTES, s>>>(ma, mw, mo, g);
     return cudaGetLastError();
 }
 

@@ -25,13 +25,19 @@ pytestmark = pytest.mark.gpu
 TOL = 2e-3     # cumulative-log-prob units (values are O(100): about 60 fp32 ulps)
 
 
-@pytest.fixture(scope="module")
-def engine():
+@pytest.fixture(scope="module", params=["skinny", "tiled"])
+def engine(request):
+    """Both GEMM kernels of the multi-kernel path: the skinny one (< 128 rows) and the register-tiled one that serves the
+    1280 rows of BASELINE configs[2] (forced here through MNX_TILE_GEMM_MIN_ROWS so that the oracle can follow it)."""
+    import os
     from molnextr_b200.engine import Engine
+    if request.param == "tiled":
+        os.environ["MNX_TILE_GEMM_MIN_ROWS"] = "1"
     ck = {"decoder": synth.decoder_state(0, "sensitised"), "encoder": None}
     eng = Engine(ck, max_batch=8, max_height=384, max_width=384, max_beam=5)
     yield eng
     eng.close()
+    os.environ.pop("MNX_TILE_GEMM_MIN_ROWS", None)
 
 
 def _check_against_following_oracle(eng, feats, K, NB):

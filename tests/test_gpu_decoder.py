@@ -14,14 +14,17 @@ from tests.helpers import load_golden, seeded_features
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["wide", "cluster16", "cluster", "graph"])
+@pytest.fixture(scope="module", params=["wide", "cluster16", "cluster", "graph", "graph-tiled"])
 def engines(request):
     """Both decode paths are exercised: the persistent cluster kernel (mega.cu) and the
     multi-kernel CUDA-graph path (decoder.cu) used for batches that do not fit in 16 clusters."""
     import os
     from molnextr_b200.engine import Engine
     cache = {}
-    os.environ["MNX_DECODE_PATH"] = request.param
+    # "graph-tiled": the multi-kernel path with the register-tiled GEMM that serves >= 128 rows (beam search, large shards)
+    os.environ["MNX_DECODE_PATH"] = request.param.split("-")[0]
+    if request.param == "graph-tiled":
+        os.environ["MNX_TILE_GEMM_MIN_ROWS"] = "1"
 
     def get(seed):
         if seed not in cache:
@@ -33,6 +36,7 @@ def engines(request):
     for e in cache.values():
         e.close()
     os.environ.pop("MNX_DECODE_PATH", None)
+    os.environ.pop("MNX_TILE_GEMM_MIN_ROWS", None)
 
 
 def _compare(out, atom_idx, n_atoms, edges, ref_ids, ref_lens, ref_tokp, ref_hsub, ref_natoms, ref_aidx, ref_edges):

@@ -57,7 +57,9 @@ def test_beam5_bs256_prefix_invariance_and_grammar():
     torch.cuda.synchronize()
     for k in ("ids", "lens"):
         assert torch.equal(big[k][:6], small[k]), k
-    np.testing.assert_allclose(big["scores"][:6].cpu().numpy(), small["scores"].cpu().numpy(), rtol=0, atol=0)
+    # 1280 rows run the register-tiled GEMM, 30 rows the skinny one: the k-sums are ordered differently, so scores agree to
+    # fp32 rounding (ids and lengths exactly)
+    np.testing.assert_allclose(big["scores"][:6].cpu().numpy(), small["scores"].cpu().numpy(), rtol=0, atol=2e-5)
     ids, lens, scores = big["ids"].cpu().numpy(), big["lens"].cpu().numpy(), big["scores"].cpu().numpy()
     assert np.isfinite(scores).all() and (scores[:, 0] >= scores[:, 1]).all()
     for i in range(B):
