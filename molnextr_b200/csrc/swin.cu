@@ -331,8 +331,18 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* 
 #define WA_SCALE_LOG2E (0.17677669529663687f * 1.4426950408889634f)
 #define WA_KV_ELEMS (WIN * 40)                              // one [key][32 dims] tile with an 80-byte row stride
 #define WA_BIAS_BYTES (9 * 18 * 32 * 8)
-#define WA_SMEM (WA_BIAS_BYTES + 4 * WA_KV_ELEMS * 2 + 2 * WIN)
+#define WA_SMEM (WA_BIAS_BYTES + 6 * WA_KV_ELEMS * 2 + 2 * WIN)
 
+__device__ __forceinline__ float ex2_approx(float x) {      // MUFU.EX2 alone (exp2f adds a denormal-range fix-up per element)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(smem_u32(smem_row)));
+}
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -353,8 +363,8 @@ __global__ void __launch_bounds__(288, 2) window_attn_kernel(const __nv_bfloat16
                                                           const int* __restrict__ row_map, __nv_bfloat16* __restrict__ out) {
     extern __shared__ __align__(16) uint8_t wa_smem[];
     uint2* bias_s = reinterpret_cast<uint2*>(wa_smem);                                   // [9][18][32]
-    __nv_bfloat16* kv_s = reinterpret_cast<__nv_bfloat16*>(wa_smem + WA_BIAS_BYTES);      // [2 buffers][K | V][WIN][40]
-    uint8_t* region_s = wa_smem + WA_BIAS_BYTES + 4 * WA_KV_ELEMS * 2;                    // [2][WIN]
+    __nv_bfloat16* kv_s = reinterpret_cast<__nv_bfloat16*>(wa_smem + WA_BIAS_BYTES);      // [2 buffers][Q | K | V][WIN][40]
+    uint8_t* region_s = wa_smem + WA_BIAS_BYTES + 6 * WA_KV_ELEMS * 2;                    // [2][WIN]
     const int h = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ld = 3 * C;
@@ -367,24 +377,14 @@ __global__ void __launch_bounds__(288, 2) window_attn_kernel(const __nv_bfloat16
 
     auto stage_kv = [&](int win, int buf) {
         const size_t row0 = (size_t)win * WIN;
-        __nv_bfloat16* Kd = kv_s + (size_t)buf * 2 * WA_KV_ELEMS;
+        __nv_bfloat16* Qd = kv_s + (size_t)buf * 3 * WA_KV_ELEMS;
+        __nv_bfloat16* Kd = Qd + WA_KV_ELEMS;
         __nv_bfloat16* Vd = Kd + WA_KV_ELEMS;
         for (int i = tid; i < WIN * 4; i += 288) {
             const int key = i >> 2, c8 = i & 3;
+            cp_async16(Qd + key * 40 + c8 * 8, qkv + (row0 + key) * ld + h * 32 + c8 * 8);
             cp_async16(Kd + key * 40 + c8 * 8, qkv + (row0 + key) * ld + C + h * 32 + c8 * 8);
             cp_async16(Vd + key * 40 + c8 * 8, qkv + (row0 + key) * ld + 2 * C + h * 32 + c8 * 8);
-        }
-    };
-    auto load_q = [&](int win, uint32_t (&q)[2][4]) {
-        const size_t row0 = (size_t)win * WIN;
-        const __nv_bfloat16* q0 = qkv + (row0 + i0) * ld + h * 32;
-        const __nv_bfloat16* q1 = qkv + (row0 + i1) * ld + h * 32;
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-            q[ks][0] = *reinterpret_cast<const uint32_t*>(q0 + ks * 16 + qc);
-            q[ks][1] = *reinterpret_cast<const uint32_t*>(q1 + ks * 16 + qc);
-            q[ks][2] = *reinterpret_cast<const uint32_t*>(q0 + ks * 16 + qc + 8);
-            q[ks][3] = *reinterpret_cast<const uint32_t*>(q1 + ks * 16 + qc + 8);
         }
     };
     // prologue: bias fragments of the head + K / V of the first window (one cp.async group)
@@ -395,8 +395,6 @@ __global__ void __launch_bounds__(288, 2) window_attn_kernel(const __nv_bfloat16
     }
     stage_kv(w_begin, 0);
     cp_async_commit();
-    uint32_t qa[2][4];
-    load_q(w_begin, qa);
     const uint2* bsrc = bias_s + (warp * 18) * 32 + lane;
 
 #pragma unroll 1
@@ -414,14 +412,17 @@ __global__ void __launch_bounds__(288, 2) window_attn_kernel(const __nv_bfloat16
         }
         cp_async_wait_all();
         __syncthreads();            // K / V (and region) of this window visible; everybody is done with the other buffer
-        uint32_t qn[2][4];
         if (win + 1 < w_end) {
             stage_kv(win + 1, buf ^ 1);
             cp_async_commit();
-            load_q(win + 1, qn);
         }
-        const __nv_bfloat16* Ks = kv_s + (size_t)buf * 2 * WA_KV_ELEMS;
+        const __nv_bfloat16* Qs = kv_s + (size_t)buf * 3 * WA_KV_ELEMS;
+        const __nv_bfloat16* Ks = Qs + WA_KV_ELEMS;
         const __nv_bfloat16* Vs = Ks + WA_KV_ELEMS;
+        // Q fragments (A operand, 2 k-steps of 16 dims): lane L supplies the address of row (L & 15) at dims 8 * (L >> 4)
+        uint32_t qa[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) ldmatrix_x4(qa[ks], Qs + (warp * 16 + (lane & 15)) * 40 + ks * 16 + 8 * (lane >> 4));
         float s[18][4];
 #pragma unroll
         for (int nt = 0; nt < 18; ++nt) {
@@ -462,8 +463,8 @@ __global__ void __launch_bounds__(288, 2) window_attn_kernel(const __nv_bfloat16
         uint32_t pk[18][2];                                  // un-normalised probabilities, bf16 pairs (rows i0 / i1)
 #pragma unroll
         for (int nt = 0; nt < 18; ++nt) {
-            const float p00 = exp2f(fmaf(s[nt][0], WA_SCALE_LOG2E, -mb0)), p01 = exp2f(fmaf(s[nt][1], WA_SCALE_LOG2E, -mb0));
-            const float p10 = exp2f(fmaf(s[nt][2], WA_SCALE_LOG2E, -mb1)), p11 = exp2f(fmaf(s[nt][3], WA_SCALE_LOG2E, -mb1));
+            const float p00 = ex2_approx(fmaf(s[nt][0], WA_SCALE_LOG2E, -mb0)), p01 = ex2_approx(fmaf(s[nt][1], WA_SCALE_LOG2E, -mb0));
+            const float p10 = ex2_approx(fmaf(s[nt][2], WA_SCALE_LOG2E, -mb1)), p11 = ex2_approx(fmaf(s[nt][3], WA_SCALE_LOG2E, -mb1));
             // the row sums run over the ROUNDED probabilities the PV product will see
             const __nv_bfloat162 t0 = __floats2bfloat162_rn(p00, p01), t1 = __floats2bfloat162_rn(p10, p11);
             const float2 r0 = __bfloat1622float2(t0), r1 = __bfloat1622float2(t1);
@@ -500,12 +501,6 @@ __global__ void __launch_bounds__(288, 2) window_attn_kernel(const __nv_bfloat16
             __nv_bfloat162 b2 = __floats2bfloat162_rn(o[nt][2] * inv1, o[nt][3] * inv1);
             if (d0 >= 0) *reinterpret_cast<__nv_bfloat162*>(o0 + nt * 8 + qc) = a2;
             if (d1 >= 0) *reinterpret_cast<__nv_bfloat162*>(o1 + nt * 8 + qc) = b2;
-        }
-        if (win + 1 < w_end) {
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) qa[ks][j] = qn[ks][j];
         }
     }
 }
