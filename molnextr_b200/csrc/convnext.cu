@@ -366,7 +366,14 @@ int convnext_finalize(mnx_engine* e, ConvNextState** out, const mnx_config& cfg)
     ConvNextState* st = new ConvNextState();
     *out = st;
     const std::string P = "encoder.cnn.";
-    CN_TRY(cn_f32(e, P + "stem.0.weight", {128, 3, 4, 4}, &st->stem_w));
+    {   // k-major [48][128] for launch_patch_embed (coalesced per-channel loads)
+        const std::vector<float>* pw = mnx_need(e, P + "stem.0.weight", {128, 3, 4, 4});
+        if (!pw) return MNX_ERR_WEIGHTS;
+        std::vector<float> t(48 * 128);
+        for (int c = 0; c < 128; ++c)
+            for (int k = 0; k < 48; ++k) t[k * 128 + c] = (*pw)[c * 48 + k];
+        CN_CUDA(e, mnx_upload(e, t, &st->stem_w));
+    }
     CN_TRY(cn_f32(e, P + "stem.0.bias", {128}, &st->stem_b));
     CN_TRY(cn_f32(e, P + "stem.1.weight", {128}, &st->stem_ln_w));
     CN_TRY(cn_f32(e, P + "stem.1.bias", {128}, &st->stem_ln_b));

@@ -40,14 +40,17 @@ struct SwinMergeW {
 };
 
 struct SwinState {
-    const float *pe_w, *pe_b, *pe_ln_w, *pe_ln_b;   // patch embed: [128][48], [128]
+    const float *pe_w, *pe_b, *pe_ln_w, *pe_ln_b;   // patch embed: [48][128] (k-major: coalesced per-channel loads), [128]
     std::vector<SwinBlockW> blocks[4];
     SwinMergeW merge[3];
     const float *norm_w, *norm_b;
     // workspaces
     float *x0 = nullptr, *x1 = nullptr;             // residual stream ping-pong (merging switches)
     __nv_bfloat16 *abuf = nullptr, *qkv = nullptr, *attn = nullptr, *hbuf = nullptr;
-    int* row_map = nullptr;                          // [2][max Mw]
+    int* row_map = nullptr;                          // per (stage, shift): window row -> token row, kept across calls of one shape
+    size_t map_off[4][2] = {};                       // offsets into row_map
+    int map_B = 0, map_H = 0, map_W = 0;             // the request the cached maps were built for ...
+    cudaStream_t map_stream = nullptr;               // ... and the stream that built them (another stream rebuilds)
     size_t max_tokens = 0;
     int last_B = 0, last_H = 0, last_W = 0;
     int cta_limit = 0;   // cap of the persistent GEMM grids for the forward in progress (EncoderState::cta_limit)
@@ -55,9 +58,9 @@ struct SwinState {
 };
 
 // ------------------------------------------------------------------------------------------
-// patch embed: conv 4x4 stride 4 (3 -> 128) + LayerNorm(128, eps 1e-5); 64 tokens per CTA
+// patch embed: conv 4x4 stride 4 (3 -> 128) + LayerNorm(128, eps 1e-5); 128 tokens per CTA; weights k-major [48][128]
 // ------------------------------------------------------------------------------------------
-#define PE_TOK_PER_CTA 64
+#define PE_TOK_PER_CTA 128
 #define PE_TB 16          // tokens per inner iteration
 __global__ void __launch_bounds__(128) patch_embed_kernel(const float* __restrict__ img, int B, int H, int W, int Hp,
                                                           int Wp, const float* __restrict__ w,
@@ -67,25 +70,25 @@ __global__ void __launch_bounds__(128) patch_embed_kernel(const float* __restric
     __shared__ __align__(16) float patch[PE_TB][48];
     __shared__ float red[PE_TB][4][2];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const long long ntok = (long long)B * Hp * Wp;
+    const unsigned ntok = (unsigned)B * Hp * Wp;        // < 2^31: checked by the launcher (32-bit index arithmetic below)
+    const unsigned hw = (unsigned)Hp * Wp;
     float wr[48];
 #pragma unroll
-    for (int k = 0; k < 48; ++k) wr[k] = w[tid * 48 + k];
+    for (int k = 0; k < 48; ++k) wr[k] = w[k * 128 + tid];      // w is [48][128]
     const float bi = bias[tid], g = ln_w[tid], be = ln_b[tid];
     // thread = output channel: its 48 weights stay in registers while the CTA walks over 64 tokens, 16 at a time; the patch
     // pixels are broadcast out of shared memory four at a time (one LDS.128 per 4 FMA: the scalar version was bound by
     // one shared-memory load per FMA and ran 10x off its HBM roofline)
     for (int it = 0; it < PE_TOK_PER_CTA / PE_TB; ++it) {
-        const long long tok0 = (long long)blockIdx.x * PE_TOK_PER_CTA + it * PE_TB;
+        const unsigned tok0 = blockIdx.x * PE_TOK_PER_CTA + it * PE_TB;
         if (tok0 >= ntok) break;
         for (int i = tid; i < PE_TB * 12; i += 128) {       // one (token, channel, row) = 4 contiguous pixels per thread
             const int t = i / 12, cr = i % 12, c = cr >> 2, dy = cr & 3;
-            const long long tok = tok0 + t;
+            const unsigned tok = tok0 + t;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (tok < ntok) {
-                const int b = (int)(tok / ((long long)Hp * Wp));
-                const int r = (int)(tok % ((long long)Hp * Wp));
-                const int py = r / Wp, px = r % Wp;
+                const unsigned b = tok / hw, r = tok - b * hw;
+                const int py = (int)(r / (unsigned)Wp), px = (int)(r - (unsigned)py * Wp);
                 const int yy = py * 4 + dy, xx = px * 4;
                 if (yy < H) {
                     const float* src = img + (((size_t)b * 3 + c) * H + yy) * W + xx;
@@ -146,6 +149,7 @@ cudaError_t launch_patch_embed(const float* img, int B, int H, int W, const floa
                                const float* ln_w, const float* ln_b, float eps, float* x, cudaStream_t s) {
     const int Hc = (H + 3) / 4, Wc = (W + 3) / 4;
     const long long ntok = (long long)B * Hc * Wc;
+    if (ntok >= (1ll << 31)) return cudaErrorInvalidValue;
     patch_embed_kernel<<<(unsigned)((ntok + PE_TOK_PER_CTA - 1) / PE_TOK_PER_CTA), 128, 0, s>>>(img, B, H, W, Hc, Wc, w, bias, ln_w, ln_b, eps, x);
     return cudaGetLastError();
 }
@@ -425,16 +429,22 @@ __global__ void __launch_bounds__(288, 2) window_attn_kernel(const __nv_bfloat16
         for (int ks = 0; ks < 2; ++ks) ldmatrix_x4(qa[ks], Qs + (warp * 16 + (lane & 15)) * 40 + ks * 16 + 8 * (lane >> 4));
         float s[18][4];
 #pragma unroll
-        for (int nt = 0; nt < 18; ++nt) {
-            const uint2 bf = bsrc[nt * 32];
-            const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&bf.x));
-            const float2 b1 = __half22float2(*reinterpret_cast<const __half2*>(&bf.y));
-            s[nt][0] = b0.x; s[nt][1] = b0.y; s[nt][2] = b1.x; s[nt][3] = b1.y;
+        for (int np = 0; np < 9; ++np) {
+            // K fragments of key tiles 2np and 2np+1 (B operand, [key][dim] rows = k-contiguous columns): lane L supplies the
+            // address of key 16 np + (L & 7) + 8 (L >> 4) at dims 8 ((L >> 3) & 1) (+16 for the second k-step)
+            uint32_t kb[2][4];      // kb[ks] = {b0, b1 of tile 2np, b0, b1 of tile 2np+1}
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                const uint32_t kb0 = *reinterpret_cast<const uint32_t*>(Ks + (nt * 8 + qr) * 40 + ks * 16 + qc);
-                const uint32_t kb1 = *reinterpret_cast<const uint32_t*>(Ks + (nt * 8 + qr) * 40 + ks * 16 + qc + 8);
-                mma_bf16_16816(s[nt], qa[ks], kb0, kb1);
+            for (int ks = 0; ks < 2; ++ks)
+                ldmatrix_x4(kb[ks], Ks + (np * 16 + (lane & 7) + 8 * (lane >> 4)) * 40 + ks * 16 + 8 * ((lane >> 3) & 1));
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int nt = 2 * np + half;
+                const uint2 bf = bsrc[nt * 32];
+                const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&bf.x));
+                const float2 b1 = __half22float2(*reinterpret_cast<const __half2*>(&bf.y));
+                s[nt][0] = b0.x; s[nt][1] = b0.y; s[nt][2] = b1.x; s[nt][3] = b1.y;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) mma_bf16_16816(s[nt], qa[ks], kb[ks][2 * half], kb[ks][2 * half + 1]);
             }
         }
         if (edge) {                                          // CTA-uniform
@@ -465,10 +475,8 @@ __global__ void __launch_bounds__(288, 2) window_attn_kernel(const __nv_bfloat16
         for (int nt = 0; nt < 18; ++nt) {
             const float p00 = ex2_approx(fmaf(s[nt][0], WA_SCALE_LOG2E, -mb0)), p01 = ex2_approx(fmaf(s[nt][1], WA_SCALE_LOG2E, -mb0));
             const float p10 = ex2_approx(fmaf(s[nt][2], WA_SCALE_LOG2E, -mb1)), p11 = ex2_approx(fmaf(s[nt][3], WA_SCALE_LOG2E, -mb1));
-            // the row sums run over the ROUNDED probabilities the PV product will see
             const __nv_bfloat162 t0 = __floats2bfloat162_rn(p00, p01), t1 = __floats2bfloat162_rn(p10, p11);
-            const float2 r0 = __bfloat1622float2(t0), r1 = __bfloat1622float2(t1);
-            l0 += r0.x + r0.y; l1 += r1.x + r1.y;
+            l0 += p00 + p01; l1 += p10 + p11;
             pk[nt][0] = *reinterpret_cast<const uint32_t*>(&t0);
             pk[nt][1] = *reinterpret_cast<const uint32_t*>(&t1);
         }
@@ -548,7 +556,14 @@ int swin_finalize(mnx_engine* e, SwinState** out, const mnx_config& cfg) {
     *out = st;
     SW_CUDA(e, cudaDeviceGetAttribute(&st->num_sms, cudaDevAttrMultiProcessorCount, cfg.device));
     const std::string P = "encoder.transformer.";
-    SW_TRY(up_f32(e, P + "patch_embed.proj.weight", {128, 3, 4, 4}, &st->pe_w));
+    {
+        const std::vector<float>* pw = mnx_need(e, P + "patch_embed.proj.weight", {128, 3, 4, 4});
+        if (!pw) return MNX_ERR_WEIGHTS;
+        std::vector<float> t(48 * 128);
+        for (int c = 0; c < 128; ++c)
+            for (int k = 0; k < 48; ++k) t[k * 128 + c] = (*pw)[c * 48 + k];
+        SW_CUDA(e, mnx_upload(e, t, &st->pe_w));
+    }
     SW_TRY(up_f32(e, P + "patch_embed.proj.bias", {128}, &st->pe_b));
     SW_TRY(up_f32(e, P + "patch_embed.norm.weight", {128}, &st->pe_ln_w));
     SW_TRY(up_f32(e, P + "patch_embed.norm.bias", {128}, &st->pe_ln_b));
@@ -629,7 +644,16 @@ int swin_finalize(mnx_engine* e, SwinState** out, const mnx_config& cfg) {
     SW_CUDA(e, mnx_dev_alloc_bytes(e, &p, tok * 384 * 2)); st->qkv = (__nv_bfloat16*)p;
     SW_CUDA(e, mnx_dev_alloc_bytes(e, &p, tok * 128 * 2)); st->attn = (__nv_bfloat16*)p;
     SW_CUDA(e, mnx_dev_alloc_bytes(e, &p, tok * 512 * 2)); st->hbuf = (__nv_bfloat16*)p;
-    SW_CUDA(e, mnx_dev_alloc_bytes(e, &p, tok * sizeof(int))); st->row_map = (int*)p;
+    {
+        size_t total = 0, hq = Hq, wq = Wq;
+        for (int sidx = 0; sidx < 4; ++sidx) {
+            const size_t mw = (size_t)cfg.max_batch * ((hq + WS - 1) / WS * WS) * ((wq + WS - 1) / WS * WS);
+            st->map_off[sidx][0] = total; st->map_off[sidx][1] = total + mw;
+            total += 2 * mw;
+            hq = (hq + 1) / 2; wq = (wq + 1) / 2;
+        }
+        SW_CUDA(e, mnx_dev_alloc_bytes(e, &p, total * sizeof(int))); st->row_map = (int*)p;
+    }
     return MNX_OK;
 }
 
@@ -656,6 +680,8 @@ int swin_forward(mnx_engine* e, SwinState* st, const float* images, int B, int H
     }
     float* x = st->x0;
     float* x_other = st->x1;
+    const bool maps_cached = st->map_B == B && st->map_H == H && st->map_W == W && st->map_stream == s;
+    st->map_B = 0;      // (a failed forward leaves no half-built cache behind)
     for (int stage = 0; stage < 4; ++stage) {
         const int C = 128 << stage, nH = SW_HEADS[stage];
         const int Hp = (Hc + WS - 1) / WS * WS, Wp = (Wc + WS - 1) / WS * WS;
@@ -664,17 +690,17 @@ int swin_forward(mnx_engine* e, SwinState* st, const float* images, int B, int H
             mnx_set_error(e, "swin workspace too small for this request");
             return MNX_ERR_CAPACITY;
         }
-        // one map live at a time; it is recomputed when the shift changes (one cheap launch)
-        int* map0 = st->row_map;
-        int cur_shift = -1;
+        // the two maps of the stage (plain / shifted windows) depend on the shapes only: built once per request shape
+        if (!maps_cached) {
+            for (int z = 0; z < 2; ++z) {
+                swin_row_map_kernel<<<(unsigned)((Mw + 255) / 256), 256, 0, s>>>(B, Hc, Wc, Hp, Wp, z * (WS / 2), st->row_map + st->map_off[stage][z]);
+                SW_CUDA(e, cudaGetLastError()); ++nl;
+            }
+        }
         for (int j = 0; j < SW_DEPTH[stage]; ++j) {
             const SwinBlockW& w = st->blocks[stage][j];
             const int shift = (j % 2 == 0) ? 0 : WS / 2;
-            if (shift != cur_shift) {
-                swin_row_map_kernel<<<(unsigned)((Mw + 255) / 256), 256, 0, s>>>(B, Hc, Wc, Hp, Wp, shift, map0);
-                SW_CUDA(e, cudaGetLastError()); ++nl;
-                cur_shift = shift;
-            }
+            const int* map0 = st->row_map + st->map_off[stage][j % 2];
             // norm1 -> (pad, roll, window partition) -> bf16
             SW_CUDA(e, launch_ln_rows<true>(x, map0, Mw, C, w.ln1_w, w.ln1_b, 1e-5f, st->abuf, s)); ++nl;
             SW_CUDA(e, gemm(st->abuf, w.qkv_w, Mw, 3 * C, C, GEMM_EPI_BF16, w.qkv_b, nullptr, st->qkv, s, st->cta_limit)); ++nl;
@@ -708,6 +734,7 @@ int swin_forward(mnx_engine* e, SwinState* st, const float* images, int B, int H
     const long long M = (long long)B * Hc * Wc;
     SW_CUDA(e, launch_ln_rows<false>(x, nullptr, M, 1024, st->norm_w, st->norm_b, 1e-5f, features, s)); ++nl;
     st->last_B = B; st->last_H = H; st->last_W = W;
+    st->map_B = B; st->map_H = H; st->map_W = W; st->map_stream = s;
     *launches += nl;
     return MNX_OK;
 }

@@ -337,9 +337,10 @@ class Engine:
         if not wide_ok:
             depth = 1
         elif depth <= 0:
-            # decode and encoder share the SMs: ~2/3 of them to `depth` decode kernels balances the two at bs = 32
-            # (measured on B200: depth 5 / 6 / 7 -> 875 / 918 / 859 img/s)
-            depth = max(1, min(max_cl // n_clusters, int(0.65 * num_sms) // (8 * n_clusters)))
+            # decode and encoder share the SMs: ~3/4 of them to `depth` decode kernels balances the two at bs = 32
+            # (measured on B200 with the 6.6 ms encoder, 20 batches: depth 5 / 6 / 7 / 8 -> 934 / 1000 / 1104 / 930 img/s;
+            #  with round 2's first 10.6 ms encoder the optimum was 6)
+            depth = max(1, min(max_cl // n_clusters, int(0.76 * num_sms) // (8 * n_clusters)))
         depth = min(depth, len(batches))
         if encoder_ctas <= 0:
             encoder_ctas = max(16, num_sms - depth * 8 * n_clusters) if wide_ok else 32
