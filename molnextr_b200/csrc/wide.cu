@@ -442,18 +442,20 @@ __device__ __forceinline__ void w_attend(WCtx& c, int row, const WAtt& d, const 
         }
     }
     m = warp_max(fmaxf(m, sx));
+    // exp(s - max) as exp2((s - max) * log2 e) (MUFU.EX2; within 2 ulp of expf) and the 1 / sum applied once to the context
+    // instead of to every probability: the same softmax-weighted sum up to fp32 rounding (the tests pin ids exactly and
+    // log-probs / hidden states to 5e-4), ~20 % fewer instructions per attention than expf + an IEEE division per key
     float sum = 0.f;
 #pragma unroll 1
     for (int i = 0; i < nt; ++i) {
-        const float e = expf(sc[i * W_TK + c.lane] - m);          // exp(-inf) = 0 for the padding
+        const float e = exp2f((sc[i * W_TK + c.lane] - m) * 1.4426950408889634f);      // exp2(-inf) = 0 for the padding
         sc[i * W_TK + c.lane] = e;
         sum += e;
     }
     sum = warp_sum(sum);
-    const float ex = extra ? expf(sx - m) : 0.f;
+    const float ex = extra ? exp2f((sx - m) * 1.4426950408889634f) : 0.f;
     sum += ex;
-#pragma unroll 1
-    for (int i = 0; i < nt; ++i) sc[i * W_TK + c.lane] = sc[i * W_TK + c.lane] / sum;
+    const float inv_sum = 1.0f / sum;
     __syncwarp();
     // context: lane = (key sub-index, 4-dim group); four keys per 16-byte-per-lane load
     const int ksub = c.lane >> 3, dq = c.lane & 7;
@@ -481,11 +483,11 @@ __device__ __forceinline__ void w_attend(WCtx& c, int row, const WAtt& d, const 
     }
     if (c.lane < 8) {
         if (extra) {
-            const float px = ex / sum;
             const float4 v = reinterpret_cast<const float4*>(c.sm + WSmem::vs)[row * 8 + dq];
-            acc.x = fmaf(px, v.x, acc.x); acc.y = fmaf(px, v.y, acc.y);
-            acc.z = fmaf(px, v.z, acc.z); acc.w = fmaf(px, v.w, acc.w);
+            acc.x = fmaf(ex, v.x, acc.x); acc.y = fmaf(ex, v.y, acc.y);
+            acc.z = fmaf(ex, v.z, acc.z); acc.w = fmaf(ex, v.w, acc.w);
         }
+        acc.x *= inv_sum; acc.y *= inv_sum; acc.z *= inv_sum; acc.w *= inv_sum;
         float* ctx = reinterpret_cast<float*>(c.sm + WSmem::ctxT);
         *reinterpret_cast<float2*>(ctx + W_ELEM(4 * dq, row)) = make_float2(acc.x, acc.y);
         *reinterpret_cast<float2*>(ctx + W_ELEM(4 * dq + 2, row)) = make_float2(acc.z, acc.w);
