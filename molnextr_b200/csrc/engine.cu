@@ -567,7 +567,7 @@ static int alloc_context(mnx_engine* e, size_t R) {
     CUDA_TRY(e, dev_alloc(e, &e->hidden, R * T * 256));
     CUDA_TRY(e, dev_alloc(e, &e->row_state, B));
     CUDA_TRY(e, dev_alloc(e, &e->steps_run_dev, 1));
-    CUDA_TRY(e, dev_alloc(e, &e->ticket, 1));
+    CUDA_TRY(e, dev_alloc(e, &e->ticket, 16));     // one ticket counter per wide-kernel launch of a call
     CUDA_TRY(e, dev_alloc(e, &e->hg, B * KA * 256));
     CUDA_TRY(e, dev_alloc(e, &e->AB, B * KA * 512));
     CUDA_TRY(e, dev_alloc(e, &e->prob, B * KA * KA * 8));
@@ -757,10 +757,15 @@ static int decode_internal(mnx_engine* e, const float* features, int B, int S, c
         return fail(e, MNX_ERR_CAPACITY, "throughput decode kernel forced but B=%d S=%d T=%d does not fit (%d clusters resident, <= %d keys)",
                     B, S, T, e->max_clusters_w, MGW_MAX_KEYS_H);
     // partial-label decoding lives on the multi-kernel graph path only
-    // the throughput kernel is opt-in (predict_pipelined / mnx_set_decode_path): it wins when several batches decode side
-    // by side on 16 SMs each; ONE batch of 256 rows on 16 clusters measured 331 ms against 262 ms on the multi-kernel
-    // graph path (its per-warp 4 KB K/V copies do not keep enough HBM traffic in flight once the caches outgrow L2)
-    const bool usew = !labels && e->decode_path == 6;
+    // the throughput kernel: forced (predict_pipelined / mnx_set_decode_path), or auto for batches too large for the latency
+    // kernels.  Its step time barely depends on the number of clusters (bs 32 / 64 / 128 / 192: 143 / 145 / 148 / 150 ms for
+    // 480 steps; the multi-kernel graph path: 303 ms at 128 rows, 375 ms at 256), so a batch above 16 rows x the resident
+    // clusters (15 on this part = 240 rows) runs as consecutive launches: the row-rank rule of a later launch reads the
+    // final row_state words of the earlier rows (they carry the step at which each row finished)
+    const bool wide_shapes = e->max_clusters_w > 0 && T <= MGW_MAX_KEYS_H + 1 && S <= MGW_MAX_KEYS_H;
+    const int wide_launches = wide_shapes ? (nclw + e->max_clusters_w - 1) / e->max_clusters_w : 0;
+    const bool usew = !labels && (e->decode_path == 6 ||
+                                  (e->decode_path == 0 && !fits16 && !fits8 && wide_shapes && wide_launches <= 16 && e->wide_rows == 0));
     const bool use16 = !labels && !usew && ((e->decode_path == 3) || (e->decode_path == 0 && fits16));
     const bool use8 = !labels && !usew && !use16 && ((e->decode_path == 2) || (e->decode_path == 0 && fits8));
     const bool use16s = use16 && fits16s;
@@ -772,7 +777,7 @@ static int decode_internal(mnx_engine* e, const float* features, int B, int S, c
         const int clusters = (B + G - 1) / G;
         CUDA_TRY(e, cudaMemsetAsync(e->row_state, 0, sizeof(unsigned) * B, s));
         CUDA_TRY(e, cudaMemsetAsync(e->steps_run_dev, 0, sizeof(int), s));
-        CUDA_TRY(e, cudaMemsetAsync(e->ticket, 0, sizeof(int), s));
+        CUDA_TRY(e, cudaMemsetAsync(e->ticket, 0, sizeof(int) * 16, s));
         MegaArgs a{};
         a.wpack = e->wpack; a.ppack = e->ppack; a.wpack16 = e->wpack16; a.ppack16 = e->ppack16;
         a.wpackW = e->wpackW; a.ticket = e->ticket;
@@ -787,7 +792,19 @@ static int decode_internal(mnx_engine* e, const float* features, int B, int S, c
             CUDA_TRY(e, cudaEventCreate(&ev0)); CUDA_TRY(e, cudaEventCreate(&ev1));
             CUDA_TRY(e, cudaEventRecord(ev0, s));
         }
-        CUDA_TRY(e, usew ? wide_launch(a, clusters, s) : use16s ? mega16s_launch(a, clusters, s) : use16 ? mega16_launch(a, clusters, s) : mega_launch(a, clusters, s));
+        if (usew) {
+            // as many launches as the resident clusters require (one for every batch up to 16 x max_clusters_w rows)
+            int nlaunch = 0;
+            for (int c0 = 0; c0 < clusters; c0 += e->max_clusters_w, ++nlaunch) {
+                a.row_base = c0 * G;
+                a.ticket = e->ticket + nlaunch;
+                const int ncl = clusters - c0 < e->max_clusters_w ? clusters - c0 : e->max_clusters_w;
+                CUDA_TRY(e, wide_launch(a, ncl, s));
+            }
+            e->launches += nlaunch - 1;
+        } else {
+            CUDA_TRY(e, use16s ? mega16s_launch(a, clusters, s) : use16 ? mega16_launch(a, clusters, s) : mega_launch(a, clusters, s));
+        }
         if (e->time_launches) {
             CUDA_TRY(e, cudaEventRecord(ev1, s));
             e->launch_events.emplace_back(ev0, ev1);

@@ -26,6 +26,7 @@ struct MegaArgs {
     const float* crossK;
     const float* crossV;
     int B, S, T, G;
+    int row_base;           // wide kernel: first row of this launch (batches above 16 x the resident clusters run as several launches)
     int* ids;
     float* logp;
     float* hidden;

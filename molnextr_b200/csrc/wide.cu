@@ -539,7 +539,7 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(W_THREADS, 1) decode
         asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(w_mapa(smem_u32(s_ticket), 0)));
         cluster = (int)v;
     }
-    const int row0 = cluster * a.G;
+    const int row0 = a.row_base + cluster * a.G;    // rows below row_base belong to earlier launches: their row_state is final
     c.G = min(a.G, a.B - row0);
     if (c.tid < W_G) { s_tf[2 * c.tid] = a.g.sos; s_tf[2 * c.tid + 1] = (c.tid < c.G) ? 0 : 1; s_rank[c.tid] = 0; }
     __syncthreads();

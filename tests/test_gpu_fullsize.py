@@ -78,11 +78,20 @@ def test_greedy_bs256_shard_prefix_invariance_and_grammar():
     eng.decode_greedy(feats)
     big, dt = _timed(lambda: eng.decode_greedy(feats))
     print(f"greedy bs=256 (one GPU's shard of configs[3]): {dt * 1e3:.1f} ms, {eng.last_decode_steps()} steps, {B / dt:.0f} img/s")
+    # auto path at 256 rows = the throughput kernel as two launches (15 resident clusters = 240 rows, then the last 16 rows,
+    # whose row ranks come from the final row_state words of the first launch)
+    assert int(eng.time_kernel(1003, 1)) == 6
     # the same rows through the persistent cluster kernel in a small batch (a different code path)
     small = eng.decode_greedy(feats[:7])
     torch.cuda.synchronize()
     assert torch.equal(big["lens"][:7], small["lens"])
     assert torch.equal(big["ids"][:7], small["ids"])
+    # ... and ALL 256 rows through the multi-kernel graph path
+    eng.set_decode_path("graph")
+    ref, dtg = _timed(lambda: eng.decode_greedy(feats))
+    eng.set_decode_path("auto")
+    print(f"greedy bs=256 on the multi-kernel graph path: {dtg * 1e3:.1f} ms")
+    assert torch.equal(big["lens"], ref["lens"]) and torch.equal(big["ids"], ref["ids"])
     ids, lens = big["ids"].cpu().numpy(), big["lens"].cpu().numpy()
     for i in range(B):
         _check_grammar(ids[i], int(lens[i]))

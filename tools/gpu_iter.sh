@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_decoder.py tests/test_gpu_shapes.py tests/test_gpu_swin.py -q -m gpu 2>&1 | tail -6 | tee gpurun_out/iter_pytest.log
-MNX_DECODE_PATH=wide timeout 300 python tools/quick_dec_bench.py 32 2>&1 | tail -1 | tee gpurun_out/iter_dec.log
-timeout 600 python tools/pipe_bench.py 20 7 2>&1 | tail -3 | tee gpurun_out/iter_pipe.log
+timeout 1200 python -m pytest tests/test_gpu_fullsize.py tests/test_gpu_decoder.py tests/test_gpu_shapes.py -q -m gpu -s 2>&1 | grep -vE "^\s*$" | tail -12 | tee gpurun_out/iter_pytest.log
+for b in 128 256; do echo "== auto B=$b"; timeout 300 python tools/quick_dec_bench.py $b 2>&1 | tail -1; done | tee gpurun_out/iter_dec_scale.log
+timeout 900 python bench.py --config c4 --steps 5 --warmup 3 2> gpurun_out/bench_c4.err | tee gpurun_out/r2j_bench_c4.json | cut -c1-250
+tail -2 gpurun_out/bench_c4.err
