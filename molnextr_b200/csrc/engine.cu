@@ -1143,6 +1143,8 @@ extern "C" int mnx_time_kernel(mnx_engine* e, int32_t which, int32_t iters, floa
         const int usable = usew ? (B + growsw - 1) / growsw : use16s ? (e->max_clusters16s < 8 ? e->max_clusters16s : 8)
                                   : use16 ? (e->max_clusters16 < 8 ? e->max_clusters16 : 8) : (e->max_clusters < 16 ? e->max_clusters : 16);
         const int G = (B + usable - 1) / usable, clusters = (B + G - 1) / G;
+        if (usew && clusters > e->max_clusters_w)
+            return fail(e, MNX_ERR_INVALID, "isolated timing covers single-launch decodes only (%d clusters, %d resident)", clusters, e->max_clusters_w);
         MegaArgs a{};
         a.wpack = e->wpack; a.ppack = e->ppack; a.wpack16 = e->wpack16; a.ppack16 = e->ppack16;
         a.wpackW = e->wpackW; a.ticket = e->ticket;

@@ -13,6 +13,8 @@
 
 #include <cuda.h>
 #include <cstdlib>
+#include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -456,6 +458,27 @@ static bool make_out_map(CUtensorMap* map, void* base, uint64_t rows, uint64_t c
     return r == CUDA_SUCCESS;
 }
 
+// Tensor maps depend only on (pointers, shapes): the encoders call the same ~100 GEMMs on the same engine-owned workspaces
+// for every batch, so the three cuTensorMapEncodeTiled calls per GEMM (~300 driver calls per forward, enough to make the
+// host the bottleneck of a 6 ms encoder on a busy box) are cached per process.
+struct MapKey {
+    const void *a, *w, *out;
+    int M, N, K, kind;
+    bool operator==(const MapKey& o) const { return a == o.a && w == o.w && out == o.out && M == o.M && N == o.N && K == o.K && kind == o.kind; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = reinterpret_cast<size_t>(k.a) * 0x9E3779B97F4A7C15ull;
+        h ^= reinterpret_cast<size_t>(k.w) + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+        h ^= reinterpret_cast<size_t>(k.out) + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+        h ^= ((size_t)k.M << 32 | (size_t)k.N << 12 | (size_t)k.K << 2 | (size_t)k.kind) + (h << 6) + (h >> 2);
+        return h;
+    }
+};
+struct MapTriple { CUtensorMap a, w, o; };
+static std::unordered_map<MapKey, MapTriple, MapKeyHash> g_map_cache;
+static std::mutex g_map_mutex;
+
 cudaError_t gemm_tc_launch(const GemmParams& p, cudaStream_t s) {
     if (g_encode == nullptr) return cudaErrorNotReady;
     if (p.M < 1 || p.N % 128 != 0 || p.K % BK != 0 || p.K < BK) return cudaErrorInvalidValue;
@@ -463,14 +486,26 @@ cudaError_t gemm_tc_launch(const GemmParams& p, cudaStream_t s) {
     if (p.epilogue == GEMM_EPI_LNFOLD_GELU_BF16 && (!p.colsum || !p.ln_stats || !p.bias || p.ln_splits < 1)) return cudaErrorInvalidValue;
     if ((reinterpret_cast<uintptr_t>(p.A) & 15) || (reinterpret_cast<uintptr_t>(p.W) & 15)) return cudaErrorInvalidValue;
     CUtensorMap ma, mw;
-    if (!make_map(&ma, p.A, (uint64_t)p.M, (uint64_t)p.K, BM)) return cudaErrorInvalidValue;
-    if (!make_map(&mw, p.W, (uint64_t)p.N, (uint64_t)p.K, BN)) return cudaErrorInvalidValue;
     // TMA epilogue: bf16 outputs, and the residual add when rows are not scattered through a row map
     const bool bf16_out = p.epilogue == GEMM_EPI_BF16 || p.epilogue == GEMM_EPI_GELU_BF16 || p.epilogue == GEMM_EPI_LNFOLD_GELU_BF16;
     const bool add_out = p.epilogue == GEMM_EPI_RESADD_F32 && p.row_map == nullptr;
     const int tma_out = (g_tma_epilogue && (bf16_out || add_out) && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) ? 1 : 0;
-    CUtensorMap mo = ma;
-    if (tma_out && !make_out_map(&mo, p.out, (uint64_t)p.M, (uint64_t)p.N, add_out)) return cudaErrorInvalidValue;
+    CUtensorMap mo;
+    {
+        const MapKey key{p.A, p.W, tma_out ? p.out : nullptr, p.M, p.N, p.K, tma_out ? (add_out ? 2 : 1) : 0};
+        std::lock_guard<std::mutex> lock(g_map_mutex);
+        auto it = g_map_cache.find(key);
+        if (it == g_map_cache.end()) {
+            MapTriple t;
+            if (!make_map(&t.a, p.A, (uint64_t)p.M, (uint64_t)p.K, BM)) return cudaErrorInvalidValue;
+            if (!make_map(&t.w, p.W, (uint64_t)p.N, (uint64_t)p.K, BN)) return cudaErrorInvalidValue;
+            t.o = t.a;
+            if (tma_out && !make_out_map(&t.o, p.out, (uint64_t)p.M, (uint64_t)p.N, add_out)) return cudaErrorInvalidValue;
+            if (g_map_cache.size() > 8192) g_map_cache.clear();      // (callers with ever-changing pointers: bounded memory)
+            it = g_map_cache.emplace(key, t).first;
+        }
+        ma = it->second.a; mw = it->second.w; mo = it->second.o;
+    }
     GemmKernelArgs g{p.M, p.N, p.K, p.epilogue, p.bias, p.gamma, p.row_map, p.out, p.colsum, p.ln_stats, p.ln_splits, p.ln_eps, tma_out};
     const int total_tiles = (p.N / BN) * ((p.M + BM - 1) / BM);
     int dev = 0, num_sms = 148;

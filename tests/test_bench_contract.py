@@ -12,7 +12,7 @@ def _load(name):
 
 
 def test_bench_line_has_the_contract_keys():
-    d = _load("r2h_bench.json")
+    d = _load("r2l_bench.json")
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
         assert k in d, k
@@ -37,10 +37,10 @@ def test_bench_line_has_the_contract_keys():
 
 
 def test_reference_arm_and_two_gpu_lines():
-    ref = _load("r2h_bench_ref.json")
+    ref = _load("r2k_bench_ref.json")
     assert ref["impl"] == "reference" and ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["e2e"]["d2h_bytes_per_step"] == 0
     assert ref["cpu_baseline"]["value"] == ref["value"] and ref["unit"] == "images/s" and ref["cpu_baseline"]["kind"] == "reference"
-    one, two = _load("r2h_bench.json"), _load("r2i_bench_2gpu.json")
+    one, two = _load("r2l_bench.json"), _load("r2i_bench_2gpu.json")
     assert two["n_gpus"] == 2 and two["config"]["global_batch"] == 64
     assert 1.8 < two["value"] / one["value"] < 2.1          # weak scaling: images are independent
 
@@ -50,7 +50,7 @@ def test_lines_of_the_other_baseline_configs():
     base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
     want = {"c1": "single 384x384 image", "c3": "bs=256 384x384 beam_size=5", "c4": "bs=2048 384x384 greedy", "c5": "bs=8 1024x1024"}
     for name, prefix in want.items():
-        d = _load(f"r2h_bench_{name}.json")
+        d = _load(f"r2l_bench_{name}.json" if name == "c1" else f"r2k_bench_{name}.json")
         for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data",
                   "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
             assert k in d, (name, k)

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_fullsize.py tests/test_gpu_decoder.py tests/test_gpu_shapes.py -q -m gpu -s 2>&1 | grep -vE "^\s*$" | tail -12 | tee gpurun_out/iter_pytest.log
-for b in 128 256; do echo "== auto B=$b"; timeout 300 python tools/quick_dec_bench.py $b 2>&1 | tail -1; done | tee gpurun_out/iter_dec_scale.log
-timeout 900 python bench.py --config c4 --steps 5 --warmup 3 2> gpurun_out/bench_c4.err | tee gpurun_out/r2j_bench_c4.json | cut -c1-250
-tail -2 gpurun_out/bench_c4.err
+timeout 1200 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_swin.py tests/test_gpu_convnext.py tests/test_gpu_facade.py -q -m gpu 2>&1 | tail -4 | tee gpurun_out/iter_pytest.log
+timeout 300 python tools/quick_enc_bench.py 2>&1 | tail -1 | tee gpurun_out/iter_enc.log
+timeout 600 python bench.py 2> gpurun_out/bench.err | tee gpurun_out/r2l_bench.json | cut -c1-250
+timeout 600 python bench.py --config c1 --steps 5 --warmup 3 2> gpurun_out/bench_c1.err | tee gpurun_out/r2l_bench_c1.json | cut -c1-250
