@@ -1,6 +1,14 @@
 #!/bin/bash
+# memcheck of the kernels added after the first sanitizer pass
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_swin.py tests/test_gpu_convnext.py tests/test_gpu_facade.py -q -m gpu 2>&1 | tail -4 | tee gpurun_out/iter_pytest.log
-timeout 300 python tools/quick_enc_bench.py 2>&1 | tail -1 | tee gpurun_out/iter_enc.log
-timeout 600 python bench.py 2> gpurun_out/bench.err | tee gpurun_out/r2l_bench.json | cut -c1-250
-timeout 600 python bench.py --config c1 --steps 5 --warmup 3 2> gpurun_out/bench_c1.err | tee gpurun_out/r2l_bench_c1.json | cut -c1-250
+CS=/usr/local/cuda/bin/compute-sanitizer
+run() { tool=$1; tag=$2; shift 2
+  timeout 300 $CS --tool $tool --print-limit 20 python tools/sanitize_case.py "$@" > gpurun_out/sanitize_${tool}_${tag}.log 2>&1
+  echo "== $tool $tag: rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitize_${tool}_${tag}.log | tail -1) | $(tail -1 gpurun_out/sanitize_${tool}_${tag}.log | cut -c1-100)"
+}
+run memcheck swin_b2 swin 2
+run memcheck convnext_b2 convnext 2
+run memcheck tiled_b5 tiled 5
+run memcheck auto_b250 auto 250
+run racecheck tiled_b5 tiled 5
+run racecheck swin_b2 swin 2

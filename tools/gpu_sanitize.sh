@@ -15,10 +15,14 @@ for tool in $TOOLS; do
   run $tool graph_b5 graph 5
   run $tool beam_b3 beam 3 3
   run $tool gemm gemm 0
+  run $tool swin_b2 swin 2
+  run $tool convnext_b2 convnext 2
+  run $tool tiled_b5 tiled 5
   # multi-cluster cases: racecheck serialises the clusters that spin on row_state (each hit the 900 s limit in round 2)
   if [ $tool = memcheck ]; then
     run $tool wide_b33 wide 33
     run $tool cluster16_b33 cluster16 33
     run $tool cluster_b37 cluster 37
+    run $tool auto_b250 auto 250      # throughput kernel selected automatically, two launches (240 + 10 rows)
   fi
 done

@@ -24,9 +24,23 @@ if path == "gemm":
     torch.cuda.synchronize()
     print("gemm ok", float(out.abs().mean()))
     sys.exit(0)
+if path in ("swin", "convnext"):
+    # encoder kernels: tcgen05 GEMM with the TMA store / reduce-add epilogue, pipelined window attention (cp.async), dwconv + LN fold
+    ck = synth.synthetic_checkpoint(0, "sensitised", encoder="swin_base" if path == "swin" else "convnext_base")
+    eng = E.Engine(ck, max_batch=B, max_height=128, max_width=160)
+    x = torch.randn((B, 3, 128, 160), generator=torch.Generator().manual_seed(3)).cuda()
+    f = eng.encode(x)
+    torch.cuda.synchronize()
+    print(path, "encode ok", tuple(f.shape), float(f.abs().mean()))
+    eng.close()
+    sys.exit(0)
+if path == "tiled":
+    import os
+    os.environ["MNX_TILE_GEMM_MIN_ROWS"] = "1"      # the register-tiled GEMM of the >= 128-row graph path on a small batch
+    path = "graph"
 ck = {"decoder": synth.decoder_state(0, "sensitised"), "encoder": None}
 eng = E.Engine(ck, max_batch=B, max_beam=max(1, beam))
-if path != "beam":
+if path not in ("beam", "auto"):
     eng.set_decode_path(path)
 f = seeded_features(7, B, 144).cuda()
 if path == "beam":
