@@ -197,7 +197,10 @@ int mnx_predict_host(mnx_engine* e, const float* images_host, int32_t B, int32_t
  *                               The encoder has one activation workspace: mnx_encode calls must be ordered
  *                               among themselves (one encoder stream).
  *   mnx_set_decode_path(e, p)   0 = automatic (lowest single-batch latency: 16-CTA clusters of <= 5 rows on
- *                               ~112 SMs), 1 = multi-kernel graph path, 2 = 8-CTA clusters of <= 4 rows,
+ *                               ~112 SMs up to 35 rows, 8-CTA clusters up to 60 rows, the throughput kernel above --
+ *                               as consecutive launches once a batch needs more clusters than are co-resident, 240
+ *                               rows per launch on B200 -- and the multi-kernel graph path for S > 512 memory
+ *                               positions), 1 = multi-kernel graph path, 2 = 8-CTA clusters of <= 4 rows,
  *                               3 = 16-CTA clusters, 6 = throughput kernel (8-CTA clusters of <= 16 rows: a
  *                               batch of 32 occupies 16 SMs, so ~4-8 batches decode side by side with the
  *                               encoder of the next ones).  Results are identical on every path.
