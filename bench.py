@@ -324,6 +324,20 @@ def roofline_other(extra, peaks, clocks, xattn_bytes, xattn_s):
             "achieved": xattn_bytes / xattn_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": xattn_bytes / xattn_s / 1e9 / peaks["hbm_gbs"], "traffic": 9752320,
             "algorithmic_bytes_per_launch": xattn_bytes}]
+    mhz0 = (clocks or {}).get("sm_mhz") or 1965.0
+    for key, label in (("xattn_phase_cycles_latency_kernel", "decode_mega16_kernel (latency path, 112 SMs)"),
+                       ("xattn_phase_cycles_wide_kernel", "decode_wide_kernel (one batch alone on 16 SMs)")):
+        cyc = extra.get(key)
+        if cyc:
+            t_s = cyc / (mhz0 * 1e6)
+            out.append({"kernel": f"cross-attention phase inside {label}: all rows x heads of the batch in one phase", "bound": "hbm",
+                        "achieved": xattn_bytes / t_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": xattn_bytes / t_s / 1e9 / peaks["hbm_gbs"],
+                        "traffic": None, "algorithmic_bytes_per_launch": xattn_bytes, "phase_cycles": cyc,
+                        "timing": "clock64 stamps of cluster 0 / CTA 0 around the phase at step 100, layer 1 (every CTA of the launch runs the "
+                                  "phase at the same time); cycles / the sampled SM clock.  The memory-bank K/V of a 32-image batch (56 MB) "
+                                  "stay in L2 across steps, so this is an L2-served rate set against the HBM roofline SURVEY.md 8(d) names"})
+    if "xattn_phase_error" in extra:
+        out.append({"kernel": "cross-attention phase (cycle stamps)", "error": extra["xattn_phase_error"]})
     if "convnext_error" in extra:
         out.append({"kernel": "dwconv_stats_kernel", "error": extra["convnext_error"]})
     if "dwconv_us" in extra:
@@ -452,14 +466,17 @@ def run_ours(args):
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         feats = eng.encode(x_dev)
         torch.cuda.synchronize()
+        enc_sampler = ClockSampler(local)       # the encoder alone is tensor-heavy: on a power-capped box its clock drops
+        enc_sampler.start()
         e0.record()
-        for _ in range(5):
+        for _ in range(40):
             feats = eng.encode(x_dev)
         e1.record()
         eng.decode_greedy(feats)
         e2.record()
         torch.cuda.synchronize()
-        extra["encoder_ms"] = e0.elapsed_time(e1) / 5
+        extra["encoder_clocks"] = enc_sampler.stop()
+        extra["encoder_ms"] = e0.elapsed_time(e1) / 40
         extra["decode_ms"] = e1.elapsed_time(e2)
         extra["decode_us_per_step"] = 1000.0 * extra["decode_ms"] / max(1, eng.last_decode_steps())
         names = {1: "cross_attn", 2: "self_attn_t240", 3: "ln1_qkv", 4: "sum_ln_w1_gelu", 5: "w2_partials", 6: "pick"}
@@ -475,6 +492,25 @@ def run_ours(args):
             extra["wide_error"] = str(ex)
         finally:
             eng.set_decode_path("auto")
+        # ---- the cross-attention PHASE inside the persistent kernels (cycle stamps of cluster 0 / CTA 0 at step 100, layer 1) ----
+        try:
+            eng.time_kernel(1008, 1)
+            torch.cuda.synchronize()
+            eng.decode_greedy(feats)
+            torch.cuda.synchronize()
+            extra["xattn_phase_cycles_latency_kernel"] = eng.time_kernel(1009, 10)      # mega16_impl.cuh H_MARK 10: cross attention
+            eng.set_decode_path("wide")
+            eng.decode_greedy(feats)
+            torch.cuda.synchronize()
+            extra["xattn_phase_cycles_wide_kernel"] = eng.time_kernel(1009, 7)          # wide.cu W_MARK: sub-layer 1, attention
+        except Exception as ex:
+            extra["xattn_phase_error"] = str(ex)
+        finally:
+            try:
+                eng.time_kernel(1008, 2)
+                eng.set_decode_path("auto")
+            except Exception as ex:
+                extra["xattn_phase_error"] = str(ex)
         # ---- ConvNeXt-B encoder (north_star's named dwconv target), same batch, separate engine ----
         try:
             eng.close()
@@ -580,7 +616,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": roof,
             "roofline_other": roofline_other(extra, peaks, clocks, xattn_bytes, xattn_s),
-            "encoder": {"ms": extra["encoder_ms"], "tflops": enc_tflops, "peak_tflops": peaks["bf16_tflops_sustained"],
+            "encoder": {"ms": extra["encoder_ms"], "clocks": extra.get("encoder_clocks"), "tflops": enc_tflops, "peak_tflops": peaks["bf16_tflops_sustained"],
                         "frac": enc_tflops / peaks["bf16_tflops_sustained"], "flops_per_image": 94.16e9},
             "decode": {"ms": extra["decode_ms"], "us_per_step": extra["decode_us_per_step"], "latency_path": extra.get("latency_path"),
                        "throughput_kernel_alone_ms": extra.get("wide_alone_ms"), "kernel_us_graph_path": extra["kernel_us"]},

@@ -1130,6 +1130,14 @@ extern "C" int mnx_time_kernel(mnx_engine* e, int32_t which, int32_t iters, floa
         *ms = 0.f;
         return MNX_OK;
     }
+    if (which == 1008) { e->decode_profile = iters == 1; *ms = 0.f; return MNX_OK; }   // cycle stamps: iters 1 = on, 2 = off (as MNX_DECODE_PROFILE)
+    if (which == 1009) {   // cycles between stamp iters-1 and stamp iters of the last profiled cluster decode (cluster 0, CTA 0, step 100, layer 1)
+        long long h[64];
+        if (iters < 1 || iters > 63) return fail(e, MNX_ERR_INVALID, "stamp index out of range");
+        CUDA_TRY(e, cudaMemcpy(h, e->prof_dev, sizeof(h), cudaMemcpyDeviceToHost));
+        *ms = (h[iters] != 0 && h[iters - 1] != 0) ? (float)(h[iters] - h[iters - 1]) : 0.f;
+        return MNX_OK;
+    }
     if (!e->finalized) return fail(e, MNX_ERR_INVALID, "weights not finalized");
     ON_ENGINE_DEVICE(e);
     cudaStream_t s = (cudaStream_t)cuda_stream;

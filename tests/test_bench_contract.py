@@ -12,7 +12,7 @@ def _load(name):
 
 
 def test_bench_line_has_the_contract_keys():
-    d = _load("r2l_bench.json")
+    d = _load("r2n_bench.json")
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
         assert k in d, k
@@ -40,7 +40,7 @@ def test_reference_arm_and_two_gpu_lines():
     ref = _load("r2k_bench_ref.json")
     assert ref["impl"] == "reference" and ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["e2e"]["d2h_bytes_per_step"] == 0
     assert ref["cpu_baseline"]["value"] == ref["value"] and ref["unit"] == "images/s" and ref["cpu_baseline"]["kind"] == "reference"
-    one, two = _load("r2l_bench.json"), _load("r2i_bench_2gpu.json")
+    one, two = _load("r2n_bench.json"), _load("r2i_bench_2gpu.json")
     assert two["n_gpus"] == 2 and two["config"]["global_batch"] == 64
     assert 1.8 < two["value"] / one["value"] < 2.1          # weak scaling: images are independent
 

@@ -1,14 +1,6 @@
 #!/bin/bash
-# memcheck of the kernels added after the first sanitizer pass
 mkdir -p gpurun_out
-CS=/usr/local/cuda/bin/compute-sanitizer
-run() { tool=$1; tag=$2; shift 2
-  timeout 300 $CS --tool $tool --print-limit 20 python tools/sanitize_case.py "$@" > gpurun_out/sanitize_${tool}_${tag}.log 2>&1
-  echo "== $tool $tag: rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitize_${tool}_${tag}.log | tail -1) | $(tail -1 gpurun_out/sanitize_${tool}_${tag}.log | cut -c1-100)"
-}
-run memcheck swin_b2 swin 2
-run memcheck convnext_b2 convnext 2
-run memcheck tiled_b5 tiled 5
-run memcheck auto_b250 auto 250
-run racecheck tiled_b5 tiled 5
-run racecheck swin_b2 swin 2
+timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -3 | tee gpurun_out/r2n_pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | tee gpurun_out/r2n_smoke.log
+timeout 600 python bench.py 2> gpurun_out/bench.err | tee gpurun_out/r2n_bench.json | cut -c1-200
+tail -3 gpurun_out/bench.err
