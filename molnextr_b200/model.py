@@ -5,7 +5,8 @@ Differences, all deliberate:
   * there is no CPU mode: `device` must be a CUDA device (north_star: no CPU fallback);
   * the checkpoint is loaded strictly (the reference uses strict=False and hides key mismatches);
   * graph -> SMILES/molfile post-processing (MolNexTR/chemical.py, RDKit) is outside the accelerated
-    path.  If RDKit and the reference's `chemical` module are importable they are used unchanged;
+    path.  If RDKit and the reference's `chemical` module are importable its per-molecule function runs
+    on a persistent worker pool (postprocess.py; the reference forks 16 processes per call);
     otherwise `predicted_smiles` is the decoder's own token-stream SMILES and `predicted_molfile`
     is None, and `postprocess` in the result says so."""
 from __future__ import annotations
@@ -25,9 +26,10 @@ BOND_TYPES = ["", "single", "double", "triple", "aromatic", "solid wedge", "dash
 
 
 def _load_postprocessor():
+    """The reference's own RDKit stage behind a persistent worker pool (postprocess.py); None without RDKit."""
     try:
-        from MolNexTR.chemical import convert_graph_to_smiles  # the reference's own RDKit stage
-        return convert_graph_to_smiles
+        from .postprocess import GraphPostProcessor
+        return GraphPostProcessor()
     except Exception:
         return None
 
