@@ -31,6 +31,8 @@
  *                            MolNexTR/tokenization.py:464-515
  *   mnx_edges             <- GraphPredictor.forward + get_edge_prediction
  *                            MolNexTR/components.py:365-400, driver :470-484
+ *   mnx_confidence        <- Decoder.decode with compute_confidence (atom_scores, average token score,
+ *                            overall_score)             MolNexTR/components.py:456-469,485-491
  *   mnx_predict           <- `features, hiddens = self.encoder(images)` followed by
  *                            `self.decoder.decode(features, hiddens)`  MolNexTR/model.py:106-108
  *
@@ -173,6 +175,16 @@ int mnx_atom_indices(mnx_engine* e, const int32_t* ids, const int32_t* lens, int
  * hidden may be NULL to use the engine-internal copy from the last mnx_decode_greedy. */
 int mnx_edges(mnx_engine* e, const float* hidden, const int32_t* atom_idx, const int32_t* n_atoms,
               int32_t B, uint8_t* edges, float* edge_score, void* cuda_stream);
+
+/* Confidence outputs of Decoder.decode(compute_confidence=True) (MolNexTR/components.py:456-469,485-491) from the results
+ * of the calls above: ids / lens / token_logp of a greedy (or best-beam) decode, edge_score of mnx_edges.
+ * atom_scores   fp32 (B, max_atoms)  geometric mean of the probabilities of the atom's symbol tokens
+ * seq_score     fp32 (B)             exp(mean(token log-prob)) = the reference's `scores` / average_token_score
+ * overall_score fp64 (B)             seq_score * sqrt(prod(edge_score[:k, :k])) -- fp64 like the reference's numpy product,
+ *                                    including its underflow to 0 for large molecules */
+int mnx_confidence(mnx_engine* e, const int32_t* ids, const int32_t* lens, const float* token_logp, int32_t B,
+                   const float* edge_score, float* atom_scores, float* seq_score, double* overall_score,
+                   void* cuda_stream);
 
 /* encoder -> decode -> atom scan -> bond head in one call, device pointers in and out. */
 int mnx_predict(mnx_engine* e, const float* images, int32_t B, int32_t H, int32_t W,

@@ -14,7 +14,7 @@ ENCODER_NONE, ENCODER_SWIN_B, ENCODER_CONVNEXT_B = 0, 1, 2
 
 EXPORTS = [
     "mnx_create", "mnx_destroy", "mnx_last_error", "mnx_load_tensor", "mnx_finalize_weights",
-    "mnx_preprocess", "mnx_encode", "mnx_decode_greedy", "mnx_decode_greedy_labels", "mnx_decode_beam", "mnx_atom_indices", "mnx_edges", "mnx_predict",
+    "mnx_preprocess", "mnx_encode", "mnx_decode_greedy", "mnx_decode_greedy_labels", "mnx_decode_beam", "mnx_atom_indices", "mnx_edges", "mnx_confidence", "mnx_predict",
     "mnx_predict_host", "mnx_set_encoder_cta_limit", "mnx_beam_trace", "mnx_launch_count", "mnx_last_decode_steps", "mnx_time_kernel",
     "mnx_test_gemm_bf16", "mnx_reserve_contexts", "mnx_set_context", "mnx_set_decode_path", "mnx_set_wide_rows",
 ]
@@ -56,6 +56,7 @@ def load() -> C.CDLL:
     lib.mnx_decode_beam.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.mnx_atom_indices.argtypes = [vp, vp, vp, i32, vp, vp, vp]
     lib.mnx_edges.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp]
+    lib.mnx_confidence.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.mnx_predict.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.mnx_predict_host.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     lib.mnx_set_encoder_cta_limit.argtypes = [vp, i32]

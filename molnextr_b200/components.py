@@ -56,6 +56,10 @@ class Decoder:
         atom_idx, n_atoms = eng.atom_indices(out["ids"], out["lens"])
         if self.compute_confidence:
             edges, escore = eng.edges(atom_idx, n_atoms, return_scores=True)
+            # atom scores / average token score / overall score on the device (mnx_confidence); the k x k edge-score
+            # lists of the result schema still come to the host
+            atom_sc, _, overall = eng.confidence(out["ids"], out["lens"], out["logp"], escore)
+            atom_sc, overall = atom_sc.cpu().numpy(), overall.cpu().numpy()
             escore = escore.cpu().numpy()
         else:
             edges = eng.edges(atom_idx, n_atoms)
@@ -72,16 +76,8 @@ class Decoder:
                 raise RuntimeError("device atom scan disagrees with the tokenizer")   # never expected
             pred = {"chartok_coords": ct, "edges": edges[i, :k, :k].astype(int).tolist()}
             if self.compute_confidence:
-                token_scores = np.exp(logp[i, :L].astype(np.float64))
-                idx = np.array(ct["indices"]) - 3
-                atom_scores = []
-                for symbol, index in zip(ct["symbols"], idx):
-                    s = token_scores[index - len(symbol) + 1:index + 1]
-                    atom_scores.append(float(np.prod(s) ** (1 / len(symbol))))
-                ct["atom_scores"] = atom_scores
-                avg = float(np.exp(np.mean(logp[i, :L].astype(np.float64))))
-                es = escore[i, :k, :k].astype(np.float64)
-                pred["edge_scores"] = es.tolist()
-                pred["overall_score"] = avg * float(np.sqrt(np.prod(es)))
+                ct["atom_scores"] = atom_sc[i, :k].astype(np.float64).tolist()
+                pred["edge_scores"] = escore[i, :k, :k].astype(np.float64).tolist()
+                pred["overall_score"] = float(overall[i])
             predictions.append(pred)
         return predictions

@@ -1123,13 +1123,10 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
 // =====================================================================================
 // atom scan (CharTokenizer.sequence_to_smiles, tokenization.py:464-515: `indices` only)
 // =====================================================================================
-__global__ void atom_scan_kernel(const int* __restrict__ ids, const int* __restrict__ lens, int B, int T,
-                                 const uint8_t* __restrict__ cls, Grammar g, int max_atoms,
-                                 int* __restrict__ atom_idx, int* __restrict__ n_atoms) {
-    const int row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= B) return;
-    const int* seq = ids + (size_t)row * T;
-    const int n = lens[row];
+// walks the atom tokens of one sequence: on_atom(k, i, j) for atom k whose symbol tokens are seq[i..j) followed by its X and Y
+// tokens (so `indices[k]` = j + 2, tokenization.py:464-515); returns the number of atoms
+template <class F>
+__device__ __forceinline__ int scan_atoms(const int* __restrict__ seq, int n, const uint8_t* __restrict__ cls, const Grammar& g, F on_atom) {
     int i = 0, k = 0;
     auto is_x = [&](int v) { return v >= g.offset && v < g.offset + g.maxx; };
     auto is_y = [&](int v) { return v >= g.offset + g.maxx; };
@@ -1157,14 +1154,70 @@ __global__ void atom_scan_kernel(const int* __restrict__ ids, const int* __restr
             }
         }
         if (j + 2 < n && is_x(seq[j]) && is_y(seq[j + 1])) {
-            if (k < max_atoms) atom_idx[(size_t)row * max_atoms + k] = j + 2;
+            on_atom(k, i, j);
             ++k;
             i = j + 2;
         } else {
             i = j;
         }
     }
-    n_atoms[row] = k;
+    return k;
+}
+
+__global__ void atom_scan_kernel(const int* __restrict__ ids, const int* __restrict__ lens, int B, int T,
+                                 const uint8_t* __restrict__ cls, Grammar g, int max_atoms,
+                                 int* __restrict__ atom_idx, int* __restrict__ n_atoms) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= B) return;
+    n_atoms[row] = scan_atoms(ids + (size_t)row * T, lens[row], cls, g, [&](int k, int, int j) {
+        if (k < max_atoms) atom_idx[(size_t)row * max_atoms + k] = j + 2;
+    });
+}
+
+// =====================================================================================
+// confidences (Decoder.decode with compute_confidence, components.py:456-469,485-491): per atom the geometric mean of
+// the probabilities of its symbol tokens, per image exp(mean(token log-prob)) and
+// overall = average_token_score * sqrt(prod(edge_scores[:k, :k])).  One CTA per image; the products run in fp64 like
+// numpy's (np.prod of Python floats), including its underflow to 0 for large molecules.
+// =====================================================================================
+__global__ void __launch_bounds__(128) confidence_kernel(const int* __restrict__ ids, const int* __restrict__ lens,
+                                                         const float* __restrict__ logp, int T, const uint8_t* __restrict__ cls,
+                                                         Grammar g, int max_atoms, const float* __restrict__ edge_score,
+                                                         float* __restrict__ atom_scores, float* __restrict__ seq_score,
+                                                         double* __restrict__ overall) {
+    __shared__ float redf[4];
+    __shared__ int s_k;
+    const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n = lens[row];
+    const float* lp = logp + (size_t)row * T;
+    if (tid == 0) {
+        s_k = scan_atoms(ids + (size_t)row * T, n, cls, g, [&](int k, int i, int j) {
+            if (k >= max_atoms) return;
+            double prod = 1.0;
+            for (int p = i; p < j; ++p) prod *= (double)expf(lp[p]);          // token_scores = exp(log-prob) in fp32, then Python floats
+            atom_scores[(size_t)row * max_atoms + k] = (float)pow(prod, 1.0 / (double)(j - i));
+        });
+    }
+    float s = 0.f;
+    for (int p = tid; p < n; p += 128) s += lp[p];
+    s = warp_sum(s);
+    if (lane == 0) redf[wid] = s;
+    __syncthreads();
+    const float avg = expf(((redf[0] + redf[1]) + (redf[2] + redf[3])) / (float)max(n, 1));
+    const int k = min(s_k, max_atoms);
+    // np.prod multiplies the k * k fp64 factors one after the other, and that ORDER is part of the result: once the running
+    // product reaches the denormal range it either sticks at the smallest denormal (every later factor > 0.5 rounds back up
+    // to it) or drops to 0 -- the reference's fixtures contain both.  So: stage the scores in shared memory, one thread
+    // multiplies them in row-major order (fp64 on the GPU keeps denormals and rounds to nearest even like the host).
+    extern __shared__ float es[];
+    for (int idx = tid; idx < k * k; idx += 128) es[idx] = edge_score[((size_t)row * max_atoms + idx / k) * max_atoms + idx % k];
+    __syncthreads();
+    if (tid == 0) {
+        double prod = 1.0;
+        for (int idx = 0; idx < k * k; ++idx) prod *= (double)es[idx];
+        seq_score[row] = avg;
+        overall[row] = (double)avg * sqrt(prod);
+    }
 }
 
 // =====================================================================================
@@ -1429,6 +1482,15 @@ cudaError_t dec_precompute(const DecBuffers& b, const DecWeights& w, const float
 cudaError_t dec_atom_scan(const int* ids, const int* lens, int B, int T, const uint8_t* cls, const Grammar& g,
                           int max_atoms, int* atom_idx, int* n_atoms, cudaStream_t s) {
     atom_scan_kernel<<<(B + 63) / 64, 64, 0, s>>>(ids, lens, B, T, cls, g, max_atoms, atom_idx, n_atoms);
+    return cudaGetLastError();
+}
+
+cudaError_t dec_confidence(const int* ids, const int* lens, const float* logp, int B, int T, const uint8_t* cls, const Grammar& g,
+                           int max_atoms, const float* edge_score, float* atom_scores, float* seq_score, double* overall, cudaStream_t s) {
+    const size_t smem = (size_t)max_atoms * max_atoms * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(confidence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    confidence_kernel<<<B, 128, smem, s>>>(ids, lens, logp, T, cls, g, max_atoms, edge_score, atom_scores, seq_score, overall);
     return cudaGetLastError();
 }
 

@@ -22,6 +22,8 @@
 namespace mnx {
 // decoder.cu
 cudaError_t dec_configure();
+cudaError_t dec_confidence(const int* ids, const int* lens, const float* logp, int B, int T, const uint8_t* cls, const Grammar& g,
+                           int max_atoms, const float* edge_score, float* atom_scores, float* seq_score, double* overall, cudaStream_t s);
 cudaError_t dec_set_label_len(const DecBuffers& b, int lab_len, cudaStream_t s);
 cudaError_t dec_label_merge(const DecBuffers& b, int lab_len, cudaStream_t s);
 int dec_launch_step(const DecBuffers& b, const DecWeights& w, const Grammar& g, const BeamBuffers* bm, cudaStream_t s,
@@ -986,6 +988,20 @@ extern "C" int mnx_edges(mnx_engine* e, const float* hidden, const int32_t* atom
     CUDA_TRY(e, dec_edges(hidden ? hidden : e->edge_hidden, atom_idx, n_atoms, B, e->cfg.max_len, e->cfg.max_atoms, e->dw,
                           e->hg, e->AB, e->prob, edges, edge_score, (cudaStream_t)cuda_stream, &nl));
     e->launches += nl;
+    return MNX_OK;
+}
+
+extern "C" int mnx_confidence(mnx_engine* e, const int32_t* ids, const int32_t* lens, const float* token_logp, int32_t B,
+                              const float* edge_score, float* atom_scores, float* seq_score, double* overall_score, void* cuda_stream) {
+    if (!e || !ids || !lens || !token_logp || !edge_score || !atom_scores || !seq_score || !overall_score)
+        return fail(e, MNX_ERR_INVALID, "mnx_confidence: null argument");
+    if (!e->finalized) return fail(e, MNX_ERR_INVALID, "weights not finalized");
+    if (B < 1 || B > e->cfg.max_batch) return fail(e, MNX_ERR_CAPACITY, "batch %d exceeds max_batch %d", B, e->cfg.max_batch);
+    ON_ENGINE_DEVICE(e);
+    WorkMark work_mark(e, (cudaStream_t)cuda_stream);
+    CUDA_TRY(e, dec_confidence(ids, lens, token_logp, B, e->cfg.max_len, e->d_cls, e->g, e->cfg.max_atoms, edge_score, atom_scores,
+                               seq_score, overall_score, (cudaStream_t)cuda_stream));
+    e->launches += 1;
     return MNX_OK;
 }
 

@@ -252,6 +252,19 @@ class Engine:
                                        self._p(edges), self._p(score), self._stream()), "mnx_edges")
         return (edges, score) if return_scores else edges
 
+    def confidence(self, ids: torch.Tensor, lens: torch.Tensor, logp: torch.Tensor, edge_score: torch.Tensor):
+        """Decoder.decode's compute_confidence outputs (components.py:456-469,485-491) on the device: per-atom geometric-mean
+        token score (B, max_atoms) fp32, average token score (B,) fp32, overall score (B,) fp64."""
+        self._same_device(ids, lens, logp, edge_score)
+        B = ids.size(0)
+        atom_scores = torch.zeros((B, MAX_ATOMS), device=ids.device, dtype=torch.float32)
+        seq_score = torch.empty((B,), device=ids.device, dtype=torch.float32)
+        overall = torch.empty((B,), device=ids.device, dtype=torch.float64)
+        self._check(self.lib.mnx_confidence(self.h, self._p(ids.contiguous()), self._p(lens.contiguous()), self._p(logp.contiguous()), B,
+                                            self._p(edge_score.contiguous()), self._p(atom_scores), self._p(seq_score), self._p(overall),
+                                            self._stream()), "mnx_confidence")
+        return atom_scores, seq_score, overall
+
     def predict(self, images: torch.Tensor):
         """encoder -> greedy decode -> atom scan -> bond head, device tensors in and out."""
         assert images.is_cuda and images.dtype == torch.float32
