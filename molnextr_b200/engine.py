@@ -44,6 +44,34 @@ def encoder_kind_of(enc_state: Optional[Dict[str, torch.Tensor]]) -> int:
     raise ValueError(f"unrecognised encoder state-dict (first key {key!r})")
 
 
+def pipeline_plan(n_batches: int, batch: int, seq_len: int, max_clusters: int, num_sms: int, depth: int = 0, encoder_ctas: int = 0) -> dict:
+    """Schedule of `Engine.predict_pipelined` (pure host logic, CPU-testable).
+
+    A batch decodes on `clusters_per_batch` 8-CTA clusters of 16 rows; `depth` batches decode side by side while the encoders of
+    the following ones run on the remaining SMs (`encoder_ctas` = cap of their persistent GEMM grids).  The throughput kernel
+    needs every cluster of a batch co-resident (`max_clusters`) and at most 512 memory positions; otherwise the batches run one
+    at a time on the automatic path (depth 1).  The last wave may be partial: its batches then use `16 // spread` rows per cluster,
+    i.e. `spread` times the SMs, so the tail of a run does not idle the GPU."""
+    n_clusters = (batch + 15) // 16
+    wide_ok = 0 < n_clusters <= max_clusters and seq_len <= 512
+    if not wide_ok:
+        depth = 1
+    elif depth <= 0:
+        # decode and encoder share the SMs: ~3/4 of them to `depth` decode kernels balances the two at bs = 32
+        # (measured on B200 with the 6.6 ms encoder, 20 batches: depth 5 / 6 / 7 / 8 -> 934 / 1000 / 1104 / 930 img/s;
+        #  with round 2's first 10.6 ms encoder the optimum was 6)
+        depth = max(1, min(max_clusters // n_clusters, int(0.76 * num_sms) // (8 * n_clusters)))
+    depth = max(1, min(depth, n_batches))
+    if encoder_ctas <= 0:
+        encoder_ctas = max(16, num_sms - depth * 8 * n_clusters) if wide_ok else 32
+    last_wave, tail = (n_batches - 1) // depth, n_batches - depth * ((n_batches - 1) // depth)
+    spread = 1
+    while wide_ok and spread * 2 <= depth // tail and spread < 4:
+        spread *= 2
+    return {"depth": depth, "throughput_kernel": bool(wide_ok), "encoder_ctas": encoder_ctas, "clusters_per_batch": n_clusters,
+            "last_wave": last_wave, "tail": tail, "spread": spread}
+
+
 class EngineError(RuntimeError):
     pass
 
@@ -343,28 +371,17 @@ class Engine:
             return []
         B0 = max(int(x.shape[0]) for x in batches)
         H0, W0 = int(batches[0].shape[2]), int(batches[0].shape[3])
-        n_clusters = (B0 + 15) // 16
         max_cl = int(self.time_kernel(1004, 1))
         num_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
-        wide_ok = 0 < n_clusters <= max_cl and self.seq_len(H0, W0) <= 512
-        if not wide_ok:
-            depth = 1
-        elif depth <= 0:
-            # decode and encoder share the SMs: ~3/4 of them to `depth` decode kernels balances the two at bs = 32
-            # (measured on B200 with the 6.6 ms encoder, 20 batches: depth 5 / 6 / 7 / 8 -> 934 / 1000 / 1104 / 930 img/s;
-            #  with round 2's first 10.6 ms encoder the optimum was 6)
-            depth = max(1, min(max_cl // n_clusters, int(0.76 * num_sms) // (8 * n_clusters)))
-        depth = min(depth, len(batches))
-        if encoder_ctas <= 0:
-            encoder_ctas = max(16, num_sms - depth * 8 * n_clusters) if wide_ok else 32
+        plan = pipeline_plan(len(batches), B0, self.seq_len(H0, W0), max_cl, num_sms, depth, encoder_ctas)
+        wide_ok, depth, encoder_ctas, n_clusters = plan["throughput_kernel"], plan["depth"], plan["encoder_ctas"], plan["clusters_per_batch"]
         cur = torch.cuda.current_stream(self.device)
         if self._pipe_streams is None or len(self._pipe_streams[1]) < depth:
             # torch: priority -1 = high, 0 = low
             old = self._pipe_streams[1] if self._pipe_streams else []
             self._pipe_streams = (self._pipe_streams[0] if self._pipe_streams else torch.cuda.Stream(self.device, priority=0),
                                   old + [torch.cuda.Stream(self.device, priority=-1) for _ in range(depth - len(old))])
-        self.last_pipeline = {"depth": depth, "throughput_kernel": bool(wide_ok), "encoder_ctas": encoder_ctas,
-                              "clusters_per_batch": n_clusters}
+        self.last_pipeline = dict(plan)
         enc, decs = self._pipe_streams[0], self._pipe_streams[1][:depth]
         enc.wait_stream(cur)
         for d in decs:
@@ -374,13 +391,7 @@ class Engine:
         if wide_ok:
             self.reserve_contexts(depth)
             self.set_decode_path("wide")
-        # the last wave may be partial: its batches spread over the SMs the missing ones would have used (fewer rows
-        # per cluster = more clusters per batch = a shorter decode), so the tail of a run does not idle the GPU
-        n = len(batches)
-        last_wave, tail = (n - 1) // depth, n - depth * ((n - 1) // depth)
-        spread = 1
-        while wide_ok and spread * 2 <= depth // tail and spread < 4:
-            spread *= 2
+        last_wave, spread = plan["last_wave"], plan["spread"]
         try:
             for i, x in enumerate(batches):
                 dec = decs[i % depth]

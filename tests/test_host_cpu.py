@@ -57,3 +57,22 @@ def test_engine_refuses_to_run_without_cuda():
     from molnextr_b200.engine import Engine, EngineError
     with pytest.raises(EngineError, match="no CPU fallback"):
         Engine({"decoder": synth.decoder_state(0), "encoder": None})
+
+
+def test_pipeline_plan_schedule():
+    """Engine.predict_pipelined's schedule is pure host logic: depth from the SM budget and the co-resident clusters, the
+    encoder's CTA cap = what the decode kernels leave free, tail spreading, fallback to one batch at a time."""
+    from molnextr_b200.engine import pipeline_plan
+    p = pipeline_plan(20, 32, 144, 15, 148)                     # the bench: 20 batches of 32 at 384 x 384 on a B200
+    assert p["throughput_kernel"] and p["clusters_per_batch"] == 2 and p["depth"] == 7 and p["encoder_ctas"] == 148 - 7 * 16
+    assert p["last_wave"] == 2 and p["tail"] == 6 and p["spread"] == 1
+    p = pipeline_plan(15, 32, 144, 15, 148)                     # 7 + 7 + 1: the single tail batch spreads over 4x the clusters
+    assert p["last_wave"] == 2 and p["tail"] == 1 and p["spread"] == 4
+    p = pipeline_plan(3, 32, 144, 15, 148)                      # fewer batches than the budget allows
+    assert p["depth"] == 3 and p["encoder_ctas"] == 148 - 3 * 16
+    assert pipeline_plan(8, 32, 144, 15, 148, depth=5)["depth"] == 5          # explicit depth wins
+    assert pipeline_plan(8, 16, 144, 15, 148)["depth"] == 8                   # one cluster per batch: up to 14 fit, 8 batches given
+    p = pipeline_plan(8, 64, 144, 15, 148)                      # 4 clusters per batch
+    assert p["clusters_per_batch"] == 4 and p["depth"] == 3
+    for bad in (pipeline_plan(8, 8, 1024, 15, 148), pipeline_plan(8, 256, 144, 15, 148)):   # S > 512, or 16 clusters > 15 resident
+        assert not bad["throughput_kernel"] and bad["depth"] == 1 and bad["encoder_ctas"] == 32 and bad["spread"] == 1
