@@ -330,7 +330,16 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(MG_THREADS, 1) decod
         asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
         c.h = (int)r;
     }
-    const int cluster = blockIdx.x >> 3;
+    // cluster order = scheduling order (see mega16_impl.cuh): rows are handed out by a ticket taken at kernel start
+    int* s_ticket = reinterpret_cast<int*>(sm + MegaSmem::ring);      // free until the barrier after the mbarrier initialisation
+    if (c.tid == 0 && c.h == 0) *s_ticket = atomicAdd(a.ticket, 1);
+    cluster_sync_all();
+    int cluster;
+    {
+        uint32_t v;
+        asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(mapa_u32(smem_u32(s_ticket), 0)));
+        cluster = (int)v;
+    }
     const int row0 = cluster * a.G;
     c.G = min(a.G, a.B - row0);
     c.tile_seq = 0; c.kv_seq = 0; c.x_seq = 0;
@@ -413,7 +422,7 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(MG_THREADS, 1) decod
         uint32_t pseq = 0;
         int t = 0;
         int pm = 0;
-#define MG_MARK() do { if (a.prof && t == 100 && blockIdx.x == 0 && c.tid == 0 && pm < 64) a.prof[pm++] = clock64(); } while (0)
+#define MG_MARK() do { if (a.prof && t == 100 && cluster == 0 && c.h == 0 && c.tid == 0 && pm < 64) a.prof[pm++] = clock64(); } while (0)
         for (;; ++t) {
             MG_MARK();
             // ---- is there anything left to do in this cluster? ----

@@ -17,7 +17,7 @@ struct MegaArgs {
     const float* wpack16;   // 16-CTA-cluster variant: [16][L*14 + 1][256*16]
     const float* ppack16;   // [16][L][1728]
     const float* wpackW;    // wide kernel (wide.cu): [8][L*14 + 1] slots of 8192 floats, see finalize_decoder
-    int* ticket;            // wide kernel: cluster-order ticket counter, zeroed before every launch
+    int* ticket;            // cluster-order ticket counter (every cluster kernel), zeroed before every launch
     const float* finalp;
     const float* emb;
     const float* pe;

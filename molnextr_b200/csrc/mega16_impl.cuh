@@ -393,7 +393,20 @@ __global__ void __launch_bounds__(H_THREADS, 1) H_KERNEL(MegaArgs a) {
     }
     c.head = c.rank >> 1; c.half = c.rank & 1;
     c.grp = (c.warp < H_CW) ? c.warp / H_GW : 0; c.gwarp = c.warp - H_GW * c.grp; c.gtid = c.gwarp * 32 + c.lane;
-    const int cluster = blockIdx.x / H_CS;
+    // cluster order = scheduling order: a ticket taken at kernel start decides which rows a cluster owns, so the spin on
+    // `row_state` of lower rows (row-rank PE rule) can never wait for a cluster that is not resident yet -- co-residency of
+    // all clusters is measured on an idle GPU, but another engine or kernel may hold SMs when this one starts
+    // (the ticket sits in the first word of the weight ring: nothing is copied there before the cluster barrier that follows
+    //  the mbarrier initialisation below)
+    int* s_ticket = reinterpret_cast<int*>(sm + HSmem::ring);
+    if (c.tid == 0 && c.rank == 0) *s_ticket = atomicAdd(a.ticket, 1);
+    h_cluster_sync_all();
+    int cluster;
+    {
+        uint32_t v;
+        asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(h_mapa(smem_u32(s_ticket), 0)));
+        cluster = (int)v;
+    }
     const int row0 = cluster * a.G;
     c.G = min(a.G, a.B - row0);
     c.tile_seq = 0; c.x_seq = 0; c.kv_seq = 0;
@@ -516,7 +529,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) H_KERNEL(MegaArgs a) {
         const float* fp = reinterpret_cast<const float*>(sm + HSmem::finalp);
         uint32_t pseq = 0;
         int pm = 0;
-#define H_MARK() do { if (a.prof && t == 100 && l == 1 && blockIdx.x == 0 && c.tid == 0 && pm < 64) a.prof[pm++] = clock64(); } while (0)
+#define H_MARK() do { if (a.prof && t == 100 && l == 1 && cluster == 0 && c.rank == 0 && c.tid == 0 && pm < 64) a.prof[pm++] = clock64(); } while (0)
         for (int t = 0;; ++t) {
             int n_alive = 0;
             for (int g = 0; g < c.G; ++g) n_alive += (s_fin[g] == 0) ? 1 : 0;

@@ -1,4 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_swin.py -q -m gpu 2>&1 | tail -3 | tee gpurun_out/iter_pytest.log
-timeout 600 python tools/pipe_bench.py 20 2>&1 | tail -3 | tee gpurun_out/iter_pipe.log
+timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -3 | tee gpurun_out/r2p_pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | tee gpurun_out/r2p_smoke.log
+timeout 300 python tools/quick_dec_bench.py 32 2>&1 | tail -1 | tee gpurun_out/iter_dec.log
