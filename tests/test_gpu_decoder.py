@@ -167,3 +167,31 @@ def test_partial_label_decode_matches_reference_fixture():
         assert free["lens"].cpu().numpy().tolist() == g["free_lens"].tolist()
     finally:
         eng.close()
+
+
+def test_partial_label_edge_cases_match_oracle():
+    """Every token given / <eos> as the first label (row finished after step 0) / nothing given: merged ids and lengths equal
+    the oracle's (which tests/test_oracle_vs_reference.py pins to the reference for exactly these label patterns)."""
+    from molnextr_b200.engine import Engine
+    from oracle import restate
+    dec = synth.decoder_state(6, "sensitised")
+    feats = seeded_features(78, 3, 36)
+    free = restate.greedy_decode(dec, feats)
+    labels = torch.zeros((3, 481), dtype=torch.long)
+    labels[:, 0] = 1
+    n0 = min(len(free[0]["ids"]), 40)
+    labels[0, 1:1 + n0] = free[0]["ids"][:n0]
+    labels[0, n0] = 2
+    labels[1, 1] = 2
+    labels[2, 1:] = 4
+    ref = restate.greedy_decode(dec, feats, labels=labels)
+    eng = Engine({"decoder": dec, "encoder": None}, max_batch=3, max_height=192, max_width=192)
+    try:
+        out = eng.decode_greedy(feats.cuda(), labels=labels.cuda())
+        torch.cuda.synchronize()
+        lens, ids = out["lens"].cpu().tolist(), out["ids"].cpu().numpy()
+        assert lens == [len(r["ids"]) for r in ref] and lens[1] == 1 and lens[2] == 480
+        for i, r in enumerate(ref):
+            assert ids[i, :lens[i]].tolist() == r["ids"].tolist(), f"row {i}"
+    finally:
+        eng.close()
