@@ -571,6 +571,7 @@ def run_ours(args):
         if achieved is not None:
             roof = {"kernel": kname + " (persistent cluster decode of one batch: 480 steps x 6 layers, one launch)",
                     "bound": "hbm",
+                    "limiter": "latency / issue-bound on an L2-resident working set (not HBM bandwidth)",
                     "bound_note": "the roofline is HBM bytes, but the kernel is latency-bound: 8 warps per SM walk a serial chain of phases "
                                   "(issue slots 32 % active, shared-memory pipe 50 %, FMA pipe 22 %, DRAM 5 % in the ncu capture); throughput comes "
                                   "from running `concurrent_launches` of them side by side",
