@@ -1,2 +1,4 @@
 #!/bin/bash
-timeout 300 python -m pytest tests/test_gpu_decoder.py -q -m gpu -k "partial_label" 2>&1 | tail -3
+mkdir -p gpurun_out
+timeout 300 python bench.py --steps 7 --warmup 3 2> gpurun_out/bench.err | tee gpurun_out/r2r_bench_short.json | cut -c1-160
+tail -2 gpurun_out/bench.err
