@@ -76,3 +76,27 @@ def test_pipeline_plan_schedule():
     assert p["clusters_per_batch"] == 4 and p["depth"] == 3
     for bad in (pipeline_plan(8, 8, 1024, 15, 148), pipeline_plan(8, 256, 144, 15, 148)):   # S > 512, or 16 clusters > 15 resident
         assert not bad["throughput_kernel"] and bad["depth"] == 1 and bad["encoder_ctas"] == 32 and bad["spread"] == 1
+
+
+def test_pipeline_plan_invariants_fuzz():
+    """Whatever the request, the schedule never asks for more co-resident clusters than the GPU holds, always leaves the
+    encoder a positive CTA budget, and only spreads the tail by 1, 2 or 4."""
+    from hypothesis import given, settings, strategies as st
+    from molnextr_b200.engine import pipeline_plan
+
+    @settings(max_examples=300, deadline=None)
+    @given(n=st.integers(1, 200), b=st.integers(1, 400), s=st.integers(1, 1100), cl=st.integers(0, 20), sms=st.integers(16, 160),
+           depth=st.integers(0, 12))
+    def check(n, b, s, cl, sms, depth):
+        p = pipeline_plan(n, b, s, cl, sms, depth)
+        assert 1 <= p["depth"] <= n and p["encoder_ctas"] >= 16 and p["spread"] in (1, 2, 4)
+        assert p["last_wave"] == (n - 1) // p["depth"] and 1 <= p["tail"] <= p["depth"]
+        if p["throughput_kernel"]:
+            assert s <= 512 and p["clusters_per_batch"] <= cl
+            if depth == 0:
+                assert p["depth"] * p["clusters_per_batch"] <= cl
+                assert p["tail"] * p["spread"] <= p["depth"]          # the spread tail uses no more clusters than a full wave
+        else:
+            assert p["depth"] == 1 and p["spread"] == 1
+
+    check()
